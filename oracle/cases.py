@@ -1,0 +1,47 @@
+"""TEST INFRASTRUCTURE — the seeded synthetic parity cases.
+
+A case = config overrides + weight seed + raw-image (h, w, seed) list.  Inputs are
+regenerated from the seeds everywhere (here, in CPU tests, on the GPU box); only the
+reference's OUTPUTS are committed under tests/golden/.
+"""
+from __future__ import annotations
+
+from vltk_b200.config import FRCNNConfig
+
+# name -> (cfg overrides, weight seed, [(raw_h, raw_w, image seed), ...])
+CASES = {
+    # CPU-quick: identity resize, reduced proposal counts
+    "tiny": (dict(min_size_test=192, max_size_test=256, rpn_pre_nms_topk=600,
+                  rpn_post_nms_topk=40, min_detections=12, max_detections=12),
+             0, [(192, 256, 1)]),
+    # real bilinear resize, two aspect ratios -> bottom/right padding, non-unit scales_yx,
+    # nms_thresh list retry, variable preds_per_image
+    "mixed": (dict(min_size_test=192, max_size_test=288, rpn_pre_nms_topk=600,
+                   rpn_post_nms_topk=48, min_detections=8, max_detections=20,
+                   nms_thresh_test=[0.05, 0.3]),
+              0, [(150, 200, 2), (240, 160, 3)]),
+    # full proposal/detection counts on a mid-size image (6000 -> 300 -> 36)
+    "full36": (dict(min_size_test=384, max_size_test=576), 0, [(384, 576, 4)]),
+    # BASELINE.json configs[0]: 1 image 800x1333, 36 boxes
+    "cfg1": (dict(), 0, [(800, 1333, 0)]),
+    # BASELINE.json configs[1] (2 of its 8 images — the bench runs all 8): 600x1000
+    "cfg2x2": (dict(min_size_test=600, max_size_test=1000), 0, [(600, 1000, 10), (600, 1000, 11)]),
+    # BASELINE.json configs[2] flavour: mixed aspect ratios with padding, max_detections=100
+    "cfg3x2": (dict(min_detections=10, max_detections=100), 0, [(600, 800, 20), (1000, 750, 21)]),
+}
+
+CPU_CASES = ("tiny", "mixed")          # cheap enough for the no-GPU suite
+GPU_CASES = ("tiny", "mixed", "full36", "cfg1", "cfg2x2", "cfg3x2")
+
+
+def case_config(name: str) -> FRCNNConfig:
+    return FRCNNConfig().replace(**CASES[name][0])
+
+
+def case_inputs(name: str):
+    """-> (cfg, weight_seed, [raw BGR u8 images])."""
+    from vltk_b200 import synthetic
+    over, wseed, imgs = CASES[name]
+    cfg = FRCNNConfig().replace(**over)
+    raws = [synthetic.make_raw_image(h, w, s) for (h, w, s) in imgs]
+    return cfg, wseed, raws
