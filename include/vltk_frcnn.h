@@ -1,0 +1,168 @@
+/*
+ * C ABI of libvltk_frcnn.so — the B200-native drop-in for vltk's Faster R-CNN R101-C4
+ * Visual-Genome region-feature extraction path.
+ *
+ * The reference has no native boundary for this path (it is pure Python over torch /
+ * torchvision); the entry points below are what a binding of that path
+ * replaces.  Each one cites the reference interface it stands in for (paths relative to
+ * the reference tree).  INTEGRATION.md shows the ctypes stub a vltk maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a
+ * negative code on failure (vltk_frcnn_last_error() describes it); nothing throws; calls
+ * are stream-ordered on the cudaStream_t passed as `void* stream` (NULL = default stream);
+ * a handle is bound to one device and is not thread-safe (the reference caller is a
+ * single-threaded loop, vltk/abc/extraction.py:142-199).  There is NO CPU fallback.
+ */
+#ifndef VLTK_FRCNN_H_
+#define VLTK_FRCNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vltk_frcnn vltk_frcnn_t;
+
+/* Arithmetic modes of the dense layers (activations NHWC in both). */
+enum {
+  VLTK_MODE_FP32 = 0, /* fp32 storage, fp32 FMA on the CUDA cores: index-exact parity mode      */
+  VLTK_MODE_BF16 = 1  /* bf16 storage, tcgen05 tensor-core implicit GEMM, fp32 accumulate       */
+};
+
+/* Architecture + selection knobs.  Mirrors the cfg.* keys FRCNN.__init__ reads
+ * (vltk/modeling/frcnn.py:1744-1755 and the constructors it calls). */
+typedef struct {
+  int stem_out_channels;    /* RESNETS.STEM_OUT_CHANNELS   (64)   */
+  int res2_out_channels;    /* RESNETS.RES2_OUT_CHANNELS   (256)  */
+  int blocks[3];            /* res2,res3,res4 block counts (3,4,23) */
+  int res5_blocks;          /* 3 */
+  int num_anchors;          /* len(sizes)*len(ratios)      (15)   */
+  int anchor_stride;        /* 16 */
+  int rpn_hidden;           /* PROPOSAL_GENERATOR.HIDDEN_CHANNELS (512) */
+  float rpn_nms_thresh;     /* RPN.NMS_THRESH              (0.7)  */
+  int rpn_pre_nms_topk;     /* RPN.PRE_NMS_TOPK_TEST       (6000, <= 8192) */
+  int rpn_post_nms_topk;    /* RPN.POST_NMS_TOPK_TEST      (300,  <= 512)  */
+  float rpn_min_size;       /* PROPOSAL_GENERATOR.MIN_SIZE (0)    */
+  float rpn_bbox_weights[4];/* RPN.BBOX_REG_WEIGHTS        (1,1,1,1) */
+  int pooler_resolution;    /* ROI_BOX_HEAD.POOLER_RESOLUTION (14) */
+  int num_classes;          /* ROI_HEADS.NUM_CLASSES       (1600) */
+  int num_attrs;            /* ROI_BOX_HEAD.NUM_ATTRS      (400)  */
+  float roi_bbox_weights[4];/* ROI_BOX_HEAD.BBOX_REG_WEIGHTS (10,10,5,5) */
+  int mode;                 /* VLTK_MODE_* */
+} vltk_frcnn_config;
+
+/* Per-call detection knobs == the mutable ROIOutputs attributes callers poke
+ * (frcnn.py:1233-1240; tests/frcnn_test.py:16-19). */
+typedef struct {
+  float nms_thresh[4];      /* roi_outputs.nms_thresh (list, tried in order) */
+  int n_nms_thresh;         /* 1..4 */
+  int min_detections;
+  int max_detections;
+  float pad_value;          /* forward(..., pad_value=) */
+} vltk_frcnn_knobs;
+
+/* Dense, caller-allocated DEVICE outputs of one forward call: the model-dict of
+ * FRCNN.inference (frcnn.py:1996-2004) in its padding="max_detections" layout
+ * (v1.0.0 contract). */
+typedef struct {
+  float* boxes;             /* [N, max_det, 4] x1,y1,x2,y2 scaled by scales_yx          */
+  float* normalized_boxes;  /* [N, max_det, 4] boxes / (sizes*scales_yx)                 */
+  int64_t* obj_ids;         /* [N, max_det]                                              */
+  float* obj_probs;         /* [N, max_det]                                              */
+  int64_t* attr_ids;        /* [N, max_det]                                              */
+  float* attr_probs;        /* [N, max_det]                                              */
+  float* roi_features;      /* [N, max_det, 2048]                                        */
+  int32_t* preds_per_image; /* [N]                                                       */
+  int32_t* keep_idx;        /* [N, max_det] index into the image's proposal list, -1 pad */
+} vltk_frcnn_out;
+
+const char* vltk_frcnn_last_error(void);
+const char* vltk_frcnn_version(void);
+
+/* FRCNN(cfg) — vltk/modeling/frcnn.py:1744-1755. */
+int vltk_frcnn_create(const vltk_frcnn_config* cfg, int device, vltk_frcnn_t** out);
+void vltk_frcnn_destroy(vltk_frcnn_t* h);
+
+/* model.load_state_dict(state_dict) — frcnn.py:1881 (keys/shapes: SURVEY.md Appendix C).
+ * `data` is a HOST fp32 array of `numel` elements in the reference's own layout
+ * ([Cout,Cin,kH,kW] convs, [out,in] linears); BN buffers under "<conv>.norm.*". */
+int vltk_frcnn_load_tensor(vltk_frcnn_t* h, const char* name, const float* data, int64_t numel);
+/* Folds frozen BN (eps 1e-5) into per-channel scale/shift, repacks weights for the kernels
+ * and uploads them.  Must be called once after all tensors are loaded. */
+int vltk_frcnn_finalize(vltk_frcnn_t* h);
+
+/* Scratch the engine needs for a batch of N padded HxW images. */
+size_t vltk_frcnn_workspace_bytes(vltk_frcnn_t* h, int n, int height, int width);
+
+/* FRCNN.forward(images, image_shapes, scales_yx=..., padding="max_detections",
+ * max_detections=...) — frcnn.py:1924-2004.
+ *   images_nchw : DEVICE [N,3,H,W] f32, normalised + padded (Preprocess output)
+ *   sizes_hw    : HOST   [N,2] int32, resized (h,w) per image (clip + pooling use these)
+ *   scales_yx   : HOST   [N,2] f32 raw/resized, or NULL
+ *   workspace   : DEVICE scratch of >= vltk_frcnn_workspace_bytes(N,H,W)           */
+int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images_nchw, const int32_t* sizes_hw,
+                       const float* scales_yx, int n, int height, int width,
+                       const vltk_frcnn_knobs* knobs, const vltk_frcnn_out* out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Preprocess.__call__ for one image — vltk/legacy/processing.py:112-150: raw BGR u8
+ * [raw_h, raw_w, 3] (DEVICE) -> bilinear shortest-edge resize to (new_h,new_w) -> (x-mean)/std
+ * -> written at batch slot `index` of the zero-padded canvas images_nchw [N,3,H,W] (DEVICE). */
+int vltk_frcnn_preprocess(const uint8_t* raw_bgr, int raw_h, int raw_w, int new_h, int new_w,
+                          const float mean[3], const float std[3], float pad_value,
+                          float* images_nchw, int index, int height, int width, void* stream);
+
+/* ---- stage entry points (teacher-forced parity tests and the config-4 microbenchmarks) ---- */
+
+/* One conv / linear layer on NHWC activations with the fused epilogue
+ * y = act((x (*) w) * scale + shift + residual)   — frcnn.py:794-822, 963-979.
+ * weight: DEVICE f32 in the reference layout [Cout,Cin,KH,KW]; scale/shift/residual may be NULL.
+ * x/y/residual dtype follows `mode` (f32 or bf16); `use_tensor_cores` selects tcgen05 (bf16 only). */
+int vltk_conv2d_nhwc(const void* x, const float* weight, const float* scale, const float* shift,
+                     const void* residual, void* y, int n, int h, int w, int cin, int cout,
+                     int kh, int kw, int stride, int pad, int dil, int relu, int mode,
+                     int use_tensor_cores, void* stream);
+
+/* find_top_rpn_proposals + RPN.inference — frcnn.py:264-390, 1615-1638 — on the RPN head's
+ * NCHW outputs (DEVICE): logits [N,A,H4,W4], deltas [N,4A,H4,W4]; cell anchors [A,4] (HOST).
+ * Outputs (DEVICE): proposals [N,post,4], proposal_logits [N,post], counts [N]. */
+int vltk_rpn_proposals(const float* logits_nchw, const float* deltas_nchw, const float* cell_anchors,
+                       const int32_t* sizes_hw, int n, int a, int h4, int w4, int stride,
+                       int pre_topk, int post_topk, float nms_thresh, float min_size,
+                       const float weights[4], float* proposals, float* proposal_logits,
+                       int32_t* counts, void* stream);
+
+/* torchvision.ops.nms on DEVICE boxes [K,4] / scores [K] (frcnn.py:132, 383):
+ * keep [max_keep] int32 indices into boxes (score order), count [1]. */
+int vltk_nms(const float* boxes, const float* scores, int k, float thresh, int max_keep,
+             int32_t* keep, int32_t* count, void* stream);
+
+/* torchvision.ops.RoIPool(P, scale) (frcnn.py:1179,1198) on an NCHW f32 DEVICE map [N,C,H,W]
+ * with rois [R,5]=(batch,x1,y1,x2,y2) (DEVICE); out [R,C,P,P] f32 (DEVICE). */
+int vltk_roi_pool_nchw(const float* feat, int n, int c, int h, int w, const float* rois, int r,
+                       int p, float scale, float* out, void* stream);
+
+/* ROIOutputs.inference — frcnn.py:1262-1294 — from predictor outputs (all DEVICE f32):
+ * obj_logits [N*R, C+1], attr_logits [N*R, A+1], box_deltas [N*R, 4C], feats [N*R, D],
+ * proposals [N,R,4], counts [N]; sizes/scales HOST as in vltk_frcnn_forward. */
+int vltk_roi_outputs(const float* obj_logits, const float* attr_logits, const float* box_deltas,
+                     const float* feats, const float* proposals, const int32_t* counts,
+                     const int32_t* sizes_hw, const float* scales_yx, int n, int r,
+                     int num_classes, int num_attrs, int d, const float weights[4],
+                     const vltk_frcnn_knobs* knobs, const vltk_frcnn_out* out, void* stream);
+
+/* Debug taps: after a forward call, copies an intermediate to HOST memory (tests only).
+ * name in {"res4" [N,H4,W4,1024], "rpn_head" [N,H4*W4,80], "proposals" [N,post,4],
+ * "proposal_count" [N] (as f32), "feats" [N*post,2048], "cls_logits", "attr_logits",
+ * "bbox_deltas"}; returns the number of floats written, or <0.  bf16 taps are widened. */
+int64_t vltk_frcnn_debug_read(vltk_frcnn_t* h, const char* name, float* host_dst, int64_t capacity);
+
+/* Number of kernels the engine launched since creation (bench.py's gpu_launches). */
+int64_t vltk_frcnn_launch_count(vltk_frcnn_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLTK_FRCNN_H_ */

@@ -1,0 +1,31 @@
+// tcgen05 implicit-GEMM convolution (conv_tc.cu) + weight packing helpers (pack.cu).
+#pragma once
+#include <cuda.h>
+
+#include <map>
+#include <tuple>
+
+#include "conv.cuh"
+
+namespace vltk {
+
+// Host-side cache of encoded TMA descriptors: encoding costs ~1 us of driver work per map and
+// the engine replays the same ~220 (activation, weight) maps every forward.
+struct TensorMapCache {
+  typedef std::tuple<const void*, int, int, int, int, int, int, int, int, int, int> Key;
+  std::map<Key, CUtensorMap> maps;
+};
+
+// y = act((x (*) w) * scale + shift + residual) on the tensor pipe.
+//   x, y, residual: bf16 NHWC;  w_nk: bf16 [cout_pad][KH*KW*Cin] (cin fastest), cout_pad % 64 == 0
+//   requires Cin % 64 == 0; scale/shift must hold cout_pad entries.
+int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorMapCache* cache,
+                   cudaStream_t st);
+
+// ---- pack.cu: reference-layout weights [cout][cin][taps] (DEVICE f32) -> kernel layouts
+int pack_weight_kn(const float* w, float* w_kn, int cout, int cin, int taps, int ldw, bool round_bf16,
+                   cudaStream_t st);
+int pack_weight_nk(const float* w, bf16* w_nk, int cout, int cin, int taps, cudaStream_t st);
+int pad_vector(const float* src, float* dst, int n, int n_pad, float fill, cudaStream_t st);
+
+}  // namespace vltk

@@ -1,0 +1,769 @@
+// C ABI + host-side orchestration of the extraction path (include/vltk_frcnn.h).
+// The whole forward is enqueued on one stream with no host synchronisation: dynamic counts
+// (non-empty proposals, NMS survivors, detections) stay on the device.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/vltk_frcnn.h"
+#include "conv.cuh"
+#include "conv_tc.cuh"
+#include "kernels.cuh"
+
+namespace vltk {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+namespace {
+
+struct LayerW {           // one conv / linear layer, packed for the kernels
+  int cin = 0, cout = 0, k = 1, stride = 1, pad = 0, dil = 1, relu = 0;
+  int cin_pad = 0;        // cin as stored in the activation (stem: 3 -> 4)
+  int ldw = 0;            // round_up(cout, 4)
+  float* w_kn = nullptr;  // SIMT: f32 [K_pad][ldw]
+  bf16* w_nk = nullptr;   // tcgen05: bf16 [cout_pad][K]  (bf16 mode, Cin % 64 == 0 only)
+  int cout_pad = 0;
+  float* scale = nullptr; // [ldw] or nullptr
+  float* shift = nullptr; // [ldw]
+};
+
+struct Block { LayerW c1, c2, c3, sc; bool has_sc = false; };
+
+struct Tap { const void* p = nullptr; int64_t n = 0; DType dt = DT_F32; };
+
+}  // namespace
+}  // namespace vltk
+
+using namespace vltk;
+
+struct vltk_frcnn {
+  vltk_frcnn_config cfg;
+  int device = 0;
+  bool finalized = false;
+  bool use_tc = false;
+  DType act = DT_F32;
+  std::map<std::string, std::vector<float>> host;
+  std::vector<void*> owned;  // device allocations
+  LayerW stem;
+  std::vector<std::vector<Block>> stages;  // res2, res3, res4
+  std::vector<Block> res5;
+  LayerW rpn_conv, rpn_head, cls_score, bbox_pred, fc_attr, attr_score;
+  float* attr_table = nullptr;  // [C+1][512] = emb @ fc_attr.W[:, D:]^T  (bias stays in fc_attr.shift)
+  float* cell = nullptr;        // [A,4]
+  std::map<std::string, Tap> taps;
+  int64_t launches = 0;
+  TensorMapCache tmaps;
+};
+
+namespace vltk_eng {
+
+int dev_alloc(vltk_frcnn* h, void** p, size_t bytes) {
+  VLTK_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+  h->owned.push_back(*p);
+  return 0;
+}
+
+int upload(vltk_frcnn* h, const std::vector<float>& v, float** p) {
+  if (dev_alloc(h, (void**)p, v.size() * 4)) return -1;
+  VLTK_CUDA(cudaMemcpy(*p, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+inline float bf16_round(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
+
+const std::vector<float>* find(vltk_frcnn* h, const std::string& k, int64_t numel) {
+  auto it = h->host.find(k);
+  if (it == h->host.end()) { set_error("state_dict is missing '%s'", k.c_str()); return nullptr; }
+  if ((int64_t)it->second.size() != numel) {
+    set_error("'%s' has %lld elements, expected %lld", k.c_str(), (long long)it->second.size(), (long long)numel);
+    return nullptr;
+  }
+  return &it->second;
+}
+
+// Packs a reference-layout weight [cout][cin][k][k] into the kernel layouts.
+//   round_bf16: weights are rounded to bf16 values (bf16 mode), so the SIMT cross-check and the
+//   tensor-core kernel see identical operands.
+int pack_layer(vltk_frcnn* h, LayerW& L, const std::string& name, int cin, int cout, int k, int stride,
+               int pad, int dil, int relu, bool bn, bool bias, bool round_bf16, bool want_tc) {
+  L.cin = cin; L.cout = cout; L.k = k; L.stride = stride; L.pad = pad; L.dil = dil; L.relu = relu;
+  L.cin_pad = round_up(cin, 4);
+  L.ldw = round_up(cout, 4);
+  const std::vector<float>* w = find(h, name + ".weight", (int64_t)cout * cin * k * k);
+  if (!w) return -2;
+  const int K = k * k * L.cin_pad, K_pad = round_up(K, 16);
+  std::vector<float> kn((size_t)K_pad * L.ldw, 0.f);
+  for (int o = 0; o < cout; ++o)
+    for (int c = 0; c < cin; ++c)
+      for (int t = 0; t < k * k; ++t) {
+        float v = (*w)[((size_t)o * cin + c) * k * k + t];
+        if (round_bf16) v = bf16_round(v);
+        kn[((size_t)t * L.cin_pad + c) * L.ldw + o] = v;
+      }
+  if (upload(h, kn, &L.w_kn)) return -1;
+  if (want_tc && cin % 64 == 0) {
+    L.cout_pad = round_up(cout, 64);
+    std::vector<bf16> nk((size_t)L.cout_pad * K, __float2bfloat16_rn(0.f));
+    for (int o = 0; o < cout; ++o)
+      for (int c = 0; c < cin; ++c)
+        for (int t = 0; t < k * k; ++t)
+          nk[(size_t)o * K + (size_t)t * cin + c] = __float2bfloat16_rn((*w)[((size_t)o * cin + c) * k * k + t]);
+    if (dev_alloc(h, (void**)&L.w_nk, nk.size() * 2)) return -1;
+    VLTK_CUDA(cudaMemcpy(L.w_nk, nk.data(), nk.size() * 2, cudaMemcpyHostToDevice));
+  }
+  std::vector<float> sc(std::max(L.ldw, L.cout_pad), 1.f), sh(std::max(L.ldw, L.cout_pad), 0.f);
+  if (bn) {
+    const std::string n = name + ".norm";
+    const auto* g = find(h, n + ".weight", cout); const auto* b = find(h, n + ".bias", cout);
+    const auto* m = find(h, n + ".running_mean", cout); const auto* v = find(h, n + ".running_var", cout);
+    if (!g || !b || !m || !v) return -2;
+    for (int o = 0; o < cout; ++o) {  // frozen BN, eps 1e-5 (frcnn.py:163-173): y = x*alpha + beta
+      float invstd = 1.0f / sqrtf((*v)[o] + 1e-5f);
+      sc[o] = (*g)[o] * invstd;
+      sh[o] = (*b)[o] - (*m)[o] * sc[o];
+    }
+    if (upload(h, sc, &L.scale)) return -1;
+  }
+  if (bias) {
+    const auto* b = find(h, name + ".bias", cout);
+    if (!b) return -2;
+    for (int o = 0; o < cout; ++o) sh[o] = (*b)[o];
+  }
+  if (bn || bias) { if (upload(h, sh, &L.shift)) return -1; }
+  return 0;
+}
+
+int pack_block(vltk_frcnn* h, Block& B, const std::string& p, int cin, int mid, int cout, int stride,
+               int dil, bool rb, bool tc) {
+  B.has_sc = cin != cout;
+  if (B.has_sc && pack_layer(h, B.sc, p + ".shortcut", cin, cout, 1, stride, 0, 1, 0, true, false, rb, tc)) return -1;
+  if (pack_layer(h, B.c1, p + ".conv1", cin, mid, 1, stride, 0, 1, 1, true, false, rb, tc)) return -1;
+  if (pack_layer(h, B.c2, p + ".conv2", mid, mid, 3, 1, dil, dil, 1, true, false, rb, tc)) return -1;
+  // conv3: BN only; the ReLU comes after the residual add and is applied by the same epilogue
+  if (pack_layer(h, B.c3, p + ".conv3", mid, cout, 1, 1, 0, 1, 1, true, false, rb, tc)) return -1;
+  return 0;
+}
+
+struct Bump {  // workspace carve-up, 256-byte aligned
+  char* base; size_t off = 0, cap;
+  Bump(void* b, size_t c) : base((char*)b), cap(c) {}
+  void* take(size_t bytes) {
+    size_t o = (off + 255) & ~(size_t)255;
+    off = o + bytes;
+    return base ? base + o : nullptr;
+  }
+};
+
+size_t esz(DType d) { return d == DT_F32 ? 4 : 2; }
+
+struct Shapes {
+  int N, H, W, Hs, Ws, Hp, Wp, h2, w2, h3, w3, h4, w4, R, P, K;
+};
+
+Shapes make_shapes(const vltk_frcnn_config& c, int N, int H, int W) {
+  Shapes s;
+  s.N = N; s.H = H; s.W = W;
+  s.Hs = (H + 6 - 7) / 2 + 1; s.Ws = (W + 6 - 7) / 2 + 1;
+  auto pool = [](int n) { int o = (n - 3 + 1) / 2 + 1; if ((o - 1) * 2 >= n) --o; return o; };
+  s.Hp = pool(s.Hs); s.Wp = pool(s.Ws);
+  s.h2 = s.Hp; s.w2 = s.Wp;
+  s.h3 = (s.h2 - 1) / 2 + 1; s.w3 = (s.w2 - 1) / 2 + 1;
+  s.h4 = (s.h3 - 1) / 2 + 1; s.w4 = (s.w3 - 1) / 2 + 1;
+  s.R = c.rpn_post_nms_topk; s.P = c.pooler_resolution;
+  s.K = std::min(c.rpn_pre_nms_topk, s.h4 * s.w4 * c.num_anchors);
+  return s;
+}
+
+// Runs one layer.  x: [N,H,W,cin_pad]
+int run_conv(vltk_frcnn* h, const LayerW& L, const void* x, DType xdt, int N, int H, int W, void* y,
+             DType ydt, int ldy, const void* residual, int ldr, int relu, cudaStream_t st, int* oh_out = nullptr,
+             int* ow_out = nullptr) {
+  ConvProblem p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.ldx = L.cin_pad; p.y = y; p.ldy = ldy; p.residual = residual; p.ldr = ldr;
+  p.N = N; p.H = H; p.W = W; p.Cin = L.cin_pad;
+  p.KH = p.KW = L.k; p.stride = L.stride; p.pad = L.pad; p.dil = L.dil;
+  p.OH = (H + 2 * L.pad - (L.dil * (L.k - 1) + 1)) / L.stride + 1;
+  p.OW = (W + 2 * L.pad - (L.dil * (L.k - 1) + 1)) / L.stride + 1;
+  p.Cout = L.cout; p.scale = L.scale; p.shift = L.shift; p.relu = relu;
+  p.in_dtype = xdt; p.out_dtype = ydt;
+  if (oh_out) *oh_out = p.OH;
+  if (ow_out) *ow_out = p.OW;
+  h->launches++;
+  if (h->use_tc && L.w_nk && xdt == DT_BF16 && ydt == DT_BF16)
+    return conv_tc_launch(p, L.w_nk, L.cout_pad, &h->tmaps, st);
+  return conv_simt_launch(p, L.w_kn, L.ldw, st);
+}
+
+struct StageBufs { void *a, *b, *t1, *t2, *s; };
+
+// bottleneck (frcnn.py:963-979): x -> conv1 -> conv2 -> conv3 (+shortcut(x) | x) -> relu
+int run_block(vltk_frcnn* h, const Block& B, const void* x, int N, int H, int W, void* out, void* t1,
+              void* t2, void* sbuf, cudaStream_t st, int* oh, int* ow) {
+  const DType d = h->act;
+  int h1, w1;
+  if (run_conv(h, B.c1, x, d, N, H, W, t1, d, B.c1.ldw, nullptr, 0, 1, st, &h1, &w1)) return -1;
+  if (run_conv(h, B.c2, t1, d, N, h1, w1, t2, d, B.c2.ldw, nullptr, 0, 1, st)) return -1;
+  const void* res = x;
+  int ldr = B.c3.ldw;
+  if (B.has_sc) {
+    if (run_conv(h, B.sc, x, d, N, H, W, sbuf, d, B.sc.ldw, nullptr, 0, 0, st)) return -1;
+    res = sbuf;
+  }
+  if (run_conv(h, B.c3, t2, d, N, h1, w1, out, d, B.c3.ldw, res, ldr, 1, st)) return -1;
+  *oh = h1; *ow = w1;
+  return 0;
+}
+
+// NCHW f32 <-> NHWC helpers for the stage entry points
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW, int ldy, int coff, int64_t tot) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= tot) return;
+  int c = (int)(i % C);
+  int64_t t = i / C;
+  int p = (int)(t % HW);
+  int n = (int)(t / HW);
+  y[((int64_t)n * HW + p) * ldy + coff + c] = x[((int64_t)n * C + c) * HW + p];
+}
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW, int64_t tot) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= tot) return;
+  int p = (int)(i % HW);
+  int64_t t = i / HW;
+  int c = (int)(t % C);
+  int n = (int)(t / C);
+  y[i] = x[((int64_t)n * HW + p) * C + c];
+}
+__global__ void rois5_split_kernel(const float* __restrict__ r5, int R, float* __restrict__ boxes, int* __restrict__ bidx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  bidx[i] = (int)r5[5 * i];
+  reinterpret_cast<float4*>(boxes)[i] = make_float4(r5[5 * i + 1], r5[5 * i + 2], r5[5 * i + 3], r5[5 * i + 4]);
+}
+__global__ void widen_bf16_kernel(const bf16* __restrict__ x, float* __restrict__ y, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __bfloat162float(x[i]);
+}
+
+void tap(vltk_frcnn* h, const char* name, const void* p, int64_t n, DType dt) {
+  Tap t; t.p = p; t.n = n; t.dt = dt;
+  h->taps[name] = t;
+}
+
+}  // namespace vltk_eng
+using namespace vltk_eng;
+
+// =========================================================================================
+extern "C" {
+
+const char* vltk_frcnn_last_error(void) { return get_error(); }
+const char* vltk_frcnn_version(void) { return "vltk_b200 frcnn 0.1 (sm_100a)"; }
+
+int vltk_frcnn_create(const vltk_frcnn_config* cfg, int device, vltk_frcnn_t** out) {
+  VLTK_CHECK(cfg && out, "create: null argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device available (%s): this library has no CPU fallback", cudaGetErrorString(e));
+    return -3;
+  }
+  VLTK_CHECK(device >= 0 && device < ndev, "create: device %d out of range", device);
+  VLTK_CHECK(cfg->rpn_pre_nms_topk >= 1 && cfg->rpn_pre_nms_topk <= 8192, "rpn_pre_nms_topk must be in 1..8192");
+  VLTK_CHECK(cfg->rpn_post_nms_topk >= 1 && cfg->rpn_post_nms_topk <= 512, "rpn_post_nms_topk must be in 1..512");
+  VLTK_CHECK(cfg->mode == VLTK_MODE_FP32 || cfg->mode == VLTK_MODE_BF16, "unknown mode %d", cfg->mode);
+  VLTK_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  VLTK_CUDA(cudaGetDeviceProperties(&prop, device));
+  VLTK_CHECK(prop.major == 10, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  vltk_frcnn* h = new vltk_frcnn();
+  h->cfg = *cfg;
+  h->device = device;
+  h->act = cfg->mode == VLTK_MODE_BF16 ? DT_BF16 : DT_F32;
+  const char* notc = getenv("VLTK_NO_TC");
+  h->use_tc = cfg->mode == VLTK_MODE_BF16 && !(notc && notc[0] == '1');
+  *out = h;
+  return 0;
+}
+
+void vltk_frcnn_destroy(vltk_frcnn_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (void* p : h->owned) cudaFree(p);
+  delete h;
+}
+
+int vltk_frcnn_load_tensor(vltk_frcnn_t* h, const char* name, const float* data, int64_t numel) {
+  VLTK_CHECK(h && name && data && numel >= 0, "load_tensor: bad argument");
+  VLTK_CHECK(!h->finalized, "load_tensor: weights already finalized");
+  h->host[name].assign(data, data + numel);
+  return 0;
+}
+
+int vltk_frcnn_finalize(vltk_frcnn_t* h) {
+  VLTK_CHECK(h && !h->finalized, "finalize: bad handle or already finalized");
+  VLTK_CUDA(cudaSetDevice(h->device));
+  const vltk_frcnn_config& c = h->cfg;
+  const bool rb = h->act == DT_BF16, tc = h->use_tc;
+  // stem consumes the fp32 NHWC4 image directly; its weights stay fp32 in both modes
+  if (pack_layer(h, h->stem, "backbone.stem.conv1", 3, c.stem_out_channels, 7, 2, 3, 1, 1, true, false, false, false)) return -1;
+  int cin = c.stem_out_channels, cout = c.res2_out_channels, mid = c.res2_out_channels / 4;
+  h->stages.resize(3);
+  for (int s = 0; s < 3; ++s) {
+    h->stages[s].resize(c.blocks[s]);
+    for (int b = 0; b < c.blocks[s]; ++b) {
+      char p[64];
+      snprintf(p, sizeof(p), "backbone.res%d.%d", s + 2, b);
+      if (pack_block(h, h->stages[s][b], p, b == 0 ? cin : cout, mid, cout, (b == 0 && s > 0) ? 2 : 1, 1, rb, tc)) return -1;
+    }
+    cin = cout; cout *= 2; mid *= 2;
+  }
+  h->res5.resize(c.res5_blocks);
+  for (int b = 0; b < c.res5_blocks; ++b) {  // VG head: stride 1, conv2 dilation 2 (frcnn.py:1345-1355)
+    char p[64];
+    snprintf(p, sizeof(p), "roi_heads.res5.%d", b);
+    if (pack_block(h, h->res5[b], p, b == 0 ? cin : cout, mid, cout, 1, 2, rb, tc)) return -1;
+  }
+  const int c4 = cin, D = cout, A = c.num_anchors, hid = c.rpn_hidden;
+  if (pack_layer(h, h->rpn_conv, "proposal_generator.rpn_head.conv", c4, hid, 3, 1, 1, 1, 1, false, true, rb, tc)) return -1;
+  {  // fused 1x1 head: columns [0,4A) anchor deltas, [4A,5A) objectness (frcnn.py:1569-1571)
+    const auto* wd = find(h, "proposal_generator.rpn_head.anchor_deltas.weight", (int64_t)4 * A * hid);
+    const auto* bd = find(h, "proposal_generator.rpn_head.anchor_deltas.bias", 4 * A);
+    const auto* wo = find(h, "proposal_generator.rpn_head.objectness_logits.weight", (int64_t)A * hid);
+    const auto* bo = find(h, "proposal_generator.rpn_head.objectness_logits.bias", A);
+    if (!wd || !bd || !wo || !bo) return -2;
+    LayerW& L = h->rpn_head;
+    L.cin = L.cin_pad = hid; L.cout = 5 * A; L.k = 1; L.ldw = round_up(5 * A, 4);
+    std::vector<float> kn((size_t)round_up(hid, 16) * L.ldw, 0.f), sh(L.ldw, 0.f);
+    for (int k = 0; k < hid; ++k) {
+      for (int o = 0; o < 4 * A; ++o) kn[(size_t)k * L.ldw + o] = (*wd)[(size_t)o * hid + k];
+      for (int o = 0; o < A; ++o) kn[(size_t)k * L.ldw + 4 * A + o] = (*wo)[(size_t)o * hid + k];
+    }
+    for (int o = 0; o < 4 * A; ++o) sh[o] = (*bd)[o];
+    for (int o = 0; o < A; ++o) sh[4 * A + o] = (*bo)[o];
+    if (upload(h, kn, &L.w_kn) || upload(h, sh, &L.shift)) return -1;
+  }
+  {
+    const auto* ca = find(h, "proposal_generator.anchor_generator.cell_anchors.0", 4 * A);
+    if (!ca) return -2;
+    if (upload(h, *ca, &h->cell)) return -1;
+  }
+  // predictor (frcnn.py:1726-1740): always fp32 — its argmaxes decide ids
+  const int NC = c.num_classes, NA = c.num_attrs, E = D / 8, HA = D / 4;
+  if (pack_layer(h, h->cls_score, "roi_heads.box_predictor.cls_score", D, NC + 1, 1, 1, 0, 1, 0, false, true, false, false)) return -1;
+  if (pack_layer(h, h->bbox_pred, "roi_heads.box_predictor.bbox_pred", D, NC * 4, 1, 1, 0, 1, 0, false, true, false, false)) return -1;
+  if (pack_layer(h, h->attr_score, "roi_heads.box_predictor.attr_score", HA, NA + 1, 1, 1, 0, 1, 0, false, true, false, false)) return -1;
+  {  // fc_attr(cat[x, emb[c]]) = W[:, :D] x + (W[:, D:] emb[c]) + b: the concat becomes a class-indexed bias
+    const auto* w = find(h, "roi_heads.box_predictor.fc_attr.weight", (int64_t)HA * (D + E));
+    const auto* b = find(h, "roi_heads.box_predictor.fc_attr.bias", HA);
+    const auto* emb = find(h, "roi_heads.box_predictor.cls_embedding.weight", (int64_t)(NC + 1) * E);
+    if (!w || !b || !emb) return -2;
+    LayerW& L = h->fc_attr;
+    L.cin = L.cin_pad = D; L.cout = HA; L.k = 1; L.ldw = HA; L.relu = 1;
+    std::vector<float> kn((size_t)D * HA), sh(b->begin(), b->end());
+    for (int o = 0; o < HA; ++o)
+      for (int k = 0; k < D; ++k) kn[(size_t)k * HA + o] = (*w)[(size_t)o * (D + E) + k];
+    std::vector<float> tab((size_t)(NC + 1) * HA);
+    for (int cidx = 0; cidx <= NC; ++cidx)
+      for (int o = 0; o < HA; ++o) {
+        double s = 0.0;
+        for (int e = 0; e < E; ++e) s += (double)(*w)[(size_t)o * (D + E) + D + e] * (double)(*emb)[(size_t)cidx * E + e];
+        tab[(size_t)cidx * HA + o] = (float)s;
+      }
+    if (upload(h, kn, &L.w_kn) || upload(h, sh, &L.shift) || upload(h, tab, &h->attr_table)) return -1;
+  }
+  h->host.clear();
+  h->finalized = true;
+  return 0;
+}
+
+static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void** ptrs);
+
+enum {
+  B_IN4, B_STEM, B_POOL, B_A, B_B, B_T1, B_T2, B_S, B_RPNH, B_HEAD, B_SIZES, B_SCALES, B_SBOX, B_SSCORE,
+  B_SIDX, B_SVALID, B_MASK, B_PROP, B_PSCORE, B_PIDX, B_COUNT, B_POOLED, B_R5A, B_R5B, B_R5T1, B_R5T2,
+  B_R5S, B_FEATS, B_CLS, B_BBOX, B_ARGMAX, B_TG, B_AH, B_ATTR, B_NUM
+};
+
+static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void** p) {
+  const vltk_frcnn_config& c = h->cfg;
+  const size_t e = esz(h->act);
+  Bump b(base, cap);
+  const int64_t N = s.N;
+  const int c2 = c.res2_out_channels, D = c2 * 8, NR = (int)(N * s.R), PP = s.P * s.P;
+  p[B_IN4] = b.take((size_t)N * s.H * s.W * 4 * 4);
+  p[B_STEM] = b.take((size_t)N * s.Hs * s.Ws * c.stem_out_channels * e);
+  p[B_POOL] = b.take((size_t)N * s.Hp * s.Wp * c.stem_out_channels * e);
+  // backbone ping-pong: largest block output / mid tensor over res2..res4
+  size_t big = std::max({(size_t)N * s.h2 * s.w2 * c2, (size_t)N * s.h3 * s.w3 * c2 * 2, (size_t)N * s.h4 * s.w4 * c2 * 4});
+  size_t midsz = std::max({(size_t)N * s.h2 * s.w2 * (c2 / 4), (size_t)N * s.h3 * s.w3 * (c2 / 2), (size_t)N * s.h4 * s.w4 * c2});
+  p[B_A] = b.take(big * e); p[B_B] = b.take(big * e); p[B_S] = b.take(big * e);
+  p[B_T1] = b.take(midsz * e); p[B_T2] = b.take(midsz * e);
+  p[B_RPNH] = b.take((size_t)N * s.h4 * s.w4 * c.rpn_hidden * e);
+  p[B_HEAD] = b.take((size_t)N * s.h4 * s.w4 * h->rpn_head.ldw * 4);
+  p[B_SIZES] = b.take((size_t)N * 2 * 4); p[B_SCALES] = b.take((size_t)N * 2 * 4);
+  p[B_SBOX] = b.take((size_t)N * s.K * 16); p[B_SSCORE] = b.take((size_t)N * s.K * 4);
+  p[B_SIDX] = b.take((size_t)N * s.K * 4); p[B_SVALID] = b.take((size_t)N * s.K);
+  p[B_MASK] = b.take(nms_mask_bytes((int)N, s.K));
+  p[B_PROP] = b.take((size_t)NR * 16); p[B_PSCORE] = b.take((size_t)NR * 4);
+  p[B_PIDX] = b.take((size_t)NR * 4); p[B_COUNT] = b.take((size_t)N * 4);
+  p[B_POOLED] = b.take((size_t)NR * PP * c2 * 4 * e);
+  p[B_R5A] = b.take((size_t)NR * PP * D * e); p[B_R5B] = b.take((size_t)NR * PP * D * e);
+  p[B_R5S] = b.take((size_t)NR * PP * D * e);
+  p[B_R5T1] = b.take((size_t)NR * PP * (D / 4) * e); p[B_R5T2] = b.take((size_t)NR * PP * (D / 4) * e);
+  p[B_FEATS] = b.take((size_t)NR * D * 4);
+  p[B_CLS] = b.take((size_t)NR * h->cls_score.ldw * 4);
+  p[B_BBOX] = b.take((size_t)NR * h->bbox_pred.ldw * 4);
+  p[B_ARGMAX] = b.take((size_t)NR * 4);
+  p[B_TG] = b.take((size_t)NR * (D / 4) * 4); p[B_AH] = b.take((size_t)NR * (D / 4) * 4);
+  p[B_ATTR] = b.take((size_t)NR * h->attr_score.ldw * 4);
+  return b.off + 256;
+}
+
+size_t vltk_frcnn_workspace_bytes(vltk_frcnn_t* h, int n, int height, int width) {
+  if (!h || !h->finalized || n < 0) return 0;
+  void* p[B_NUM];
+  return plan(h, make_shapes(h->cfg, n, height, width), nullptr, 0, p);
+}
+
+int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* sizes_hw, const float* scales_yx,
+                       int n, int height, int width, const vltk_frcnn_knobs* knobs, const vltk_frcnn_out* out,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  VLTK_CHECK(h && h->finalized, "forward: weights not finalized");
+  VLTK_CHECK(images && sizes_hw && knobs && out && workspace, "forward: null argument");
+  VLTK_CHECK(n >= 1, "forward: empty batch");
+  VLTK_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const vltk_frcnn_config& c = h->cfg;
+  const Shapes s = make_shapes(c, n, height, width);
+  VLTK_CHECK(s.h4 >= 1 && s.w4 >= 1, "forward: image %dx%d too small", height, width);
+  for (int i = 0; i < n; ++i)
+    VLTK_CHECK(sizes_hw[2 * i] >= 1 && sizes_hw[2 * i] <= height && sizes_hw[2 * i + 1] >= 1 && sizes_hw[2 * i + 1] <= width,
+               "forward: image_shapes[%d]=(%d,%d) outside the padded %dx%d batch", i, sizes_hw[2 * i], sizes_hw[2 * i + 1], height, width);
+  VLTK_CHECK(knobs->max_detections >= 1 && knobs->max_detections <= s.R, "forward: max_detections=%d must be in 1..%d", knobs->max_detections, s.R);
+  void* p[B_NUM];
+  size_t need = plan(h, s, workspace, workspace_bytes, p);
+  VLTK_CHECK(need <= workspace_bytes, "forward: workspace %zu < required %zu", workspace_bytes, need);
+  const DType d = h->act;
+  h->taps.clear();
+
+  VLTK_CUDA(cudaMemcpyAsync(p[B_SIZES], sizes_hw, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  if (scales_yx) VLTK_CUDA(cudaMemcpyAsync(p[B_SCALES], scales_yx, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+
+  // ---- backbone (frcnn.py:1076-1090)
+  if (nchw3_to_nhwc4(images, p[B_IN4], DT_F32, n, height, width, st)) return -1;
+  h->launches++;
+  if (run_conv(h, h->stem, p[B_IN4], DT_F32, n, height, width, p[B_STEM], d, h->stem.ldw, nullptr, 0, 1, st)) return -1;
+  if (maxpool3x3s2_ceil(p[B_STEM], p[B_POOL], d, n, s.Hs, s.Ws, c.stem_out_channels, s.Hp, s.Wp, st)) return -1;
+  h->launches++;
+  const void* x = p[B_POOL];
+  int ch = s.Hp, cw = s.Wp;
+  void* pp[2] = {p[B_A], p[B_B]};
+  int flip = 0;
+  for (auto& stage : h->stages)
+    for (auto& blk : stage) {
+      int oh, ow;
+      if (run_block(h, blk, x, n, ch, cw, pp[flip], p[B_T1], p[B_T2], p[B_S], st, &oh, &ow)) return -1;
+      x = pp[flip]; flip ^= 1; ch = oh; cw = ow;
+    }
+  VLTK_CHECK(ch == s.h4 && cw == s.w4, "internal: res4 shape mismatch");
+  const void* res4 = x;
+  const int C4 = c.res2_out_channels * 4, A = c.num_anchors;
+  tap(h, "res4", res4, (int64_t)n * s.h4 * s.w4 * C4, d);
+
+  // ---- RPN head + proposal selection (frcnn.py:1561-1572, 264-390)
+  if (run_conv(h, h->rpn_conv, res4, d, n, s.h4, s.w4, p[B_RPNH], d, h->rpn_conv.ldw, nullptr, 0, 1, st)) return -1;
+  if (run_conv(h, h->rpn_head, p[B_RPNH], d, n, s.h4, s.w4, p[B_HEAD], DT_F32, h->rpn_head.ldw, nullptr, 0, 0, st)) return -1;
+  tap(h, "rpn_head", p[B_HEAD], (int64_t)n * s.h4 * s.w4 * h->rpn_head.ldw, DT_F32);
+  RpnSelectArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  ra.head = (const float*)p[B_HEAD]; ra.ldh = h->rpn_head.ldw; ra.delta_off = 0; ra.logit_off = 4 * A;
+  ra.N = n; ra.H4 = s.h4; ra.W4 = s.w4; ra.A = A; ra.stride = c.anchor_stride; ra.cell = h->cell;
+  ra.sizes_hw = (const int*)p[B_SIZES]; ra.pre_topk = c.rpn_pre_nms_topk; ra.min_size = c.rpn_min_size;
+  ra.wx = c.rpn_bbox_weights[0]; ra.wy = c.rpn_bbox_weights[1]; ra.ww = c.rpn_bbox_weights[2]; ra.wh = c.rpn_bbox_weights[3];
+  ra.boxes = (float*)p[B_SBOX]; ra.scores = (float*)p[B_SSCORE]; ra.anchor_idx = (int*)p[B_SIDX];
+  ra.valid = (uint8_t*)p[B_SVALID]; ra.K = s.K;
+  if (rpn_select(ra, st)) return -1;
+  NmsArgs na;
+  memset(&na, 0, sizeof(na));
+  na.boxes = ra.boxes; na.scores = ra.scores; na.valid = ra.valid; na.N = n; na.K = s.K;
+  na.thresh = c.rpn_nms_thresh; na.max_keep = s.R; na.mask = (unsigned long long*)p[B_MASK];
+  na.out_boxes = (float*)p[B_PROP]; na.out_scores = (float*)p[B_PSCORE]; na.out_idx = (int*)p[B_PIDX];
+  na.out_count = (int*)p[B_COUNT];
+  if (nms_sorted(na, st)) return -1;
+  h->launches += 3;
+  tap(h, "topk_anchor_idx", p[B_SIDX], (int64_t)n * s.K, DT_F32);  // int32 payload, read raw
+  tap(h, "proposals", p[B_PROP], (int64_t)n * s.R * 4, DT_F32);
+  tap(h, "proposal_logits", p[B_PSCORE], (int64_t)n * s.R, DT_F32);
+  tap(h, "proposal_count", p[B_COUNT], n, DT_F32);
+
+  // ---- ROI head: RoIPool -> res5 -> mean (frcnn.py:1387-1403)
+  const int NR = n * s.R, PP = s.P * s.P, D = c.res2_out_channels * 8;
+  if (roi_pool(res4, d, n, s.h4, s.w4, C4, (const float*)p[B_PROP], (const int*)p[B_COUNT], s.R, s.P,
+               1.0f / (float)c.anchor_stride, p[B_POOLED], st)) return -1;
+  h->launches++;
+  x = p[B_POOLED];
+  void* r5[2] = {p[B_R5A], p[B_R5B]};
+  flip = 0;
+  for (auto& blk : h->res5) {
+    int oh, ow;
+    if (run_block(h, blk, x, NR, s.P, s.P, r5[flip], p[B_R5T1], p[B_R5T2], p[B_R5S], st, &oh, &ow)) return -1;
+    x = r5[flip]; flip ^= 1;
+  }
+  if (mean_rows(x, (float*)p[B_FEATS], d, NR, PP, D, st)) return -1;
+  h->launches++;
+  tap(h, "feats", p[B_FEATS], (int64_t)NR * D, DT_F32);
+
+  // ---- predictor (frcnn.py:1726-1740), fp32
+  if (run_conv(h, h->cls_score, p[B_FEATS], DT_F32, NR, 1, 1, p[B_CLS], DT_F32, h->cls_score.ldw, nullptr, 0, 0, st)) return -1;
+  if (run_conv(h, h->bbox_pred, p[B_FEATS], DT_F32, NR, 1, 1, p[B_BBOX], DT_F32, h->bbox_pred.ldw, nullptr, 0, 0, st)) return -1;
+  if (row_argmax((const float*)p[B_CLS], h->cls_score.ldw, NR, c.num_classes + 1, (int*)p[B_ARGMAX], st)) return -1;
+  if (gather_rows(h->attr_table, D / 4, (const int*)p[B_ARGMAX], NR, D / 4, (float*)p[B_TG], D / 4, st)) return -1;
+  if (run_conv(h, h->fc_attr, p[B_FEATS], DT_F32, NR, 1, 1, p[B_AH], DT_F32, D / 4, p[B_TG], D / 4, 1, st)) return -1;
+  if (run_conv(h, h->attr_score, p[B_AH], DT_F32, NR, 1, 1, p[B_ATTR], DT_F32, h->attr_score.ldw, nullptr, 0, 0, st)) return -1;
+  h->launches += 2;
+  tap(h, "cls_logits", p[B_CLS], (int64_t)NR * h->cls_score.ldw, DT_F32);
+  tap(h, "bbox_deltas", p[B_BBOX], (int64_t)NR * h->bbox_pred.ldw, DT_F32);
+  tap(h, "attr_logits", p[B_ATTR], (int64_t)NR * h->attr_score.ldw, DT_F32);
+
+  // ---- detection tail (frcnn.py:1262-1294)
+  TailArgs ta;
+  memset(&ta, 0, sizeof(ta));
+  ta.N = n; ta.R = s.R; ta.cls_logits = (const float*)p[B_CLS]; ta.ldc = h->cls_score.ldw;
+  ta.bbox_deltas = (const float*)p[B_BBOX]; ta.ldb = h->bbox_pred.ldw;
+  ta.attr_logits = (const float*)p[B_ATTR]; ta.lda = h->attr_score.ldw;
+  ta.feats = (const float*)p[B_FEATS]; ta.D = D; ta.proposals = (const float*)p[B_PROP];
+  ta.count = (const int*)p[B_COUNT]; ta.sizes_hw = (const int*)p[B_SIZES];
+  ta.scales_yx = scales_yx ? (const float*)p[B_SCALES] : nullptr;
+  ta.num_classes = c.num_classes; ta.num_attrs = c.num_attrs;
+  ta.wx = c.roi_bbox_weights[0]; ta.wy = c.roi_bbox_weights[1]; ta.ww = c.roi_bbox_weights[2]; ta.wh = c.roi_bbox_weights[3];
+  ta.nms_thresh = knobs->nms_thresh; ta.n_thresh = knobs->n_nms_thresh;
+  ta.min_det = knobs->min_detections; ta.max_det = knobs->max_detections; ta.pad_value = knobs->pad_value;
+  ta.boxes = out->boxes; ta.norm_boxes = out->normalized_boxes; ta.obj_ids = (long long*)out->obj_ids;
+  ta.obj_probs = out->obj_probs; ta.attr_ids = (long long*)out->attr_ids; ta.attr_probs = out->attr_probs;
+  ta.roi_features = out->roi_features; ta.preds_per_image = out->preds_per_image; ta.keep_idx = out->keep_idx;
+  if (roi_tail(ta, st)) return -1;
+  h->launches++;
+  return 0;
+}
+
+int vltk_frcnn_preprocess(const uint8_t* raw, int rh, int rw, int nh, int nw, const float mean[3], const float stdv[3],
+                          float pad_value, float* images, int index, int height, int width, void* stream) {
+  VLTK_CHECK(raw && images && mean && stdv, "preprocess: null argument");
+  VLTK_CHECK(nh <= height && nw <= width && nh >= 1 && nw >= 1, "preprocess: resized %dx%d exceeds canvas %dx%d", nh, nw, height, width);
+  return preprocess_image(raw, rh, rw, nh, nw, height, width, mean, stdv, pad_value,
+                          images + (int64_t)index * 3 * height * width, nullptr, DT_F32, (cudaStream_t)stream);
+}
+
+int64_t vltk_frcnn_debug_read(vltk_frcnn_t* h, const char* name, float* dst, int64_t cap) {
+  VLTK_CHECK(h && name && dst, "debug_read: null argument");
+  auto it = h->taps.find(name);
+  VLTK_CHECK(it != h->taps.end(), "debug_read: no tap '%s' (run forward first)", name);
+  const Tap& t = it->second;
+  VLTK_CHECK(t.n <= cap, "debug_read: '%s' has %lld elements, capacity %lld", name, (long long)t.n, (long long)cap);
+  VLTK_CUDA(cudaSetDevice(h->device));
+  VLTK_CUDA(cudaDeviceSynchronize());
+  if (t.dt == DT_F32) {
+    VLTK_CUDA(cudaMemcpy(dst, t.p, (size_t)t.n * 4, cudaMemcpyDeviceToHost));
+  } else {
+    float* tmp = nullptr;
+    VLTK_CUDA(cudaMalloc(&tmp, (size_t)t.n * 4));
+    widen_bf16_kernel<<<(unsigned)ceil_div64(t.n, 256), 256>>>((const bf16*)t.p, tmp, t.n);
+    cudaError_t e = cudaMemcpy(dst, tmp, (size_t)t.n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(tmp);
+    VLTK_CUDA(e);
+  }
+  return t.n;
+}
+
+int64_t vltk_frcnn_launch_count(vltk_frcnn_t* h) { return h ? h->launches : -1; }
+
+// ---------------------------------------------------------------------------- stage entries
+int vltk_conv2d_nhwc(const void* x, const float* weight, const float* scale, const float* shift, const void* residual,
+                     void* y, int n, int hh, int ww, int cin, int cout, int kh, int kw, int stride, int pad, int dil,
+                     int relu, int mode, int use_tc, void* stream) {
+  VLTK_CHECK(x && weight && y, "conv2d: null argument");
+  VLTK_CHECK(kh == kw, "conv2d: square kernels only");
+  VLTK_CHECK(cin % 4 == 0 && cout % 4 == 0, "conv2d: cin/cout must be multiples of 4 for the stage entry");
+  cudaStream_t st = (cudaStream_t)stream;
+  const DType d = mode == VLTK_MODE_BF16 ? DT_BF16 : DT_F32;
+  ConvProblem p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.ldx = cin; p.y = y; p.ldy = cout; p.residual = residual; p.ldr = cout;
+  p.N = n; p.H = hh; p.W = ww; p.Cin = cin; p.KH = kh; p.KW = kw; p.stride = stride; p.pad = pad; p.dil = dil;
+  p.OH = (hh + 2 * pad - (dil * (kh - 1) + 1)) / stride + 1;
+  p.OW = (ww + 2 * pad - (dil * (kw - 1) + 1)) / stride + 1;
+  p.Cout = cout; p.scale = scale; p.shift = shift; p.relu = relu; p.in_dtype = d; p.out_dtype = d;
+  const int K = kh * kw * cin, K_pad = round_up(K, 16);
+  int rc = 0;
+  if (use_tc) {
+    VLTK_CHECK(d == DT_BF16 && cin % 64 == 0, "conv2d: tensor-core path needs bf16 and cin %% 64 == 0");
+    const int cout_pad = round_up(cout, 64);
+    bf16* w_nk = nullptr;
+    float *sc = nullptr, *sh = nullptr;
+    VLTK_CUDA(cudaMalloc(&w_nk, (size_t)cout_pad * K * 2));
+    VLTK_CUDA(cudaMemsetAsync(w_nk, 0, (size_t)cout_pad * K * 2, st));
+    VLTK_CUDA(cudaMalloc(&sc, (size_t)cout_pad * 4));
+    VLTK_CUDA(cudaMalloc(&sh, (size_t)cout_pad * 4));
+    rc = pack_weight_nk(weight, w_nk, cout, cin, kh * kw, st);
+    if (!rc) rc = pad_vector(scale, sc, cout, cout_pad, 1.f, st);
+    if (!rc) rc = pad_vector(shift, sh, cout, cout_pad, 0.f, st);
+    p.scale = sc; p.shift = sh;
+    TensorMapCache cache;
+    if (!rc) rc = conv_tc_launch(p, w_nk, cout_pad, &cache, st);
+    cudaStreamSynchronize(st);
+    cudaFree(w_nk); cudaFree(sc); cudaFree(sh);
+  } else {
+    float* w_kn = nullptr;
+    VLTK_CUDA(cudaMalloc(&w_kn, (size_t)K_pad * cout * 4));
+    VLTK_CUDA(cudaMemsetAsync(w_kn, 0, (size_t)K_pad * cout * 4, st));
+    rc = pack_weight_kn(weight, w_kn, cout, cin, kh * kw, cout, d == DT_BF16, st);
+    if (!rc) rc = conv_simt_launch(p, w_kn, cout, st);
+    cudaStreamSynchronize(st);
+    cudaFree(w_kn);
+  }
+  return rc;
+}
+
+int vltk_rpn_proposals(const float* logits, const float* deltas, const float* cell_host, const int32_t* sizes_hw,
+                       int n, int a, int h4, int w4, int stride, int pre_topk, int post_topk, float nms_thresh,
+                       float min_size, const float weights[4], float* proposals, float* proposal_logits,
+                       int32_t* counts, void* stream) {
+  VLTK_CHECK(logits && deltas && cell_host && sizes_hw && proposals && counts, "rpn_proposals: null argument");
+  VLTK_CHECK(pre_topk >= 1 && pre_topk <= 8192 && post_topk >= 1 && post_topk <= 8192, "rpn_proposals: topk out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HW = h4 * w4, ldh = round_up(5 * a, 4), K = std::min(pre_topk, HW * a);
+  float *head = nullptr, *cell = nullptr, *sbox = nullptr, *ssc = nullptr, *psc = nullptr;
+  int *sizes = nullptr, *sidx = nullptr, *pidx = nullptr;
+  uint8_t* valid = nullptr;
+  unsigned long long* mask = nullptr;
+  VLTK_CUDA(cudaMalloc(&head, (size_t)n * HW * ldh * 4));
+  VLTK_CUDA(cudaMalloc(&cell, (size_t)a * 16));
+  VLTK_CUDA(cudaMalloc(&sizes, (size_t)n * 8));
+  VLTK_CUDA(cudaMalloc(&sbox, (size_t)n * K * 16));
+  VLTK_CUDA(cudaMalloc(&ssc, (size_t)n * K * 4));
+  VLTK_CUDA(cudaMalloc(&sidx, (size_t)n * K * 4));
+  VLTK_CUDA(cudaMalloc(&valid, (size_t)n * K));
+  VLTK_CUDA(cudaMalloc(&mask, nms_mask_bytes(n, K)));
+  VLTK_CUDA(cudaMalloc(&pidx, (size_t)n * post_topk * 4));
+  if (!proposal_logits) VLTK_CUDA(cudaMalloc(&psc, (size_t)n * post_topk * 4));
+  VLTK_CUDA(cudaMemcpyAsync(cell, cell_host, (size_t)a * 16, cudaMemcpyHostToDevice, st));
+  VLTK_CUDA(cudaMemcpyAsync(sizes, sizes_hw, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  int64_t t1 = (int64_t)n * 4 * a * HW, t2 = (int64_t)n * a * HW;
+  nchw_to_nhwc_kernel<<<(unsigned)ceil_div64(t1, 256), 256, 0, st>>>(deltas, head, 4 * a, HW, ldh, 0, t1);
+  nchw_to_nhwc_kernel<<<(unsigned)ceil_div64(t2, 256), 256, 0, st>>>(logits, head, a, HW, ldh, 4 * a, t2);
+  RpnSelectArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  ra.head = head; ra.ldh = ldh; ra.delta_off = 0; ra.logit_off = 4 * a; ra.N = n; ra.H4 = h4; ra.W4 = w4; ra.A = a;
+  ra.stride = stride; ra.cell = cell; ra.sizes_hw = sizes; ra.pre_topk = pre_topk; ra.min_size = min_size;
+  ra.wx = weights[0]; ra.wy = weights[1]; ra.ww = weights[2]; ra.wh = weights[3];
+  ra.boxes = sbox; ra.scores = ssc; ra.anchor_idx = sidx; ra.valid = valid; ra.K = K;
+  int rc = rpn_select(ra, st);
+  NmsArgs na;
+  memset(&na, 0, sizeof(na));
+  na.boxes = sbox; na.scores = ssc; na.valid = valid; na.N = n; na.K = K; na.thresh = nms_thresh; na.max_keep = post_topk;
+  na.mask = mask; na.out_boxes = proposals; na.out_scores = proposal_logits ? proposal_logits : psc; na.out_idx = pidx;
+  na.out_count = counts;
+  if (!rc) rc = nms_sorted(na, st);
+  cudaStreamSynchronize(st);
+  cudaFree(head); cudaFree(cell); cudaFree(sizes); cudaFree(sbox); cudaFree(ssc); cudaFree(sidx);
+  cudaFree(valid); cudaFree(mask); cudaFree(pidx); if (psc) cudaFree(psc);
+  return rc;
+}
+
+int vltk_nms(const float* boxes, const float* scores, int k, float thresh, int max_keep, int32_t* keep,
+             int32_t* count, void* stream) {
+  VLTK_CHECK(boxes && scores && keep && count, "nms: null argument");
+  VLTK_CHECK(k >= 0 && k <= 8192 && max_keep >= 1 && max_keep <= 8192, "nms: k must be <= 8192");
+  cudaStream_t st = (cudaStream_t)stream;
+  float *sbox = nullptr, *ssc = nullptr, *obox = nullptr;
+  int *order = nullptr, *oidx = nullptr;
+  unsigned long long* mask = nullptr;
+  VLTK_CUDA(cudaMalloc(&sbox, (size_t)std::max(k, 1) * 16));
+  VLTK_CUDA(cudaMalloc(&ssc, (size_t)std::max(k, 1) * 4));
+  VLTK_CUDA(cudaMalloc(&order, (size_t)std::max(k, 1) * 4));
+  VLTK_CUDA(cudaMalloc(&obox, (size_t)max_keep * 16));
+  VLTK_CUDA(cudaMalloc(&oidx, (size_t)max_keep * 4));
+  VLTK_CUDA(cudaMalloc(&mask, nms_mask_bytes(1, std::max(k, 1))));
+  int rc = sort_boxes_desc(boxes, scores, k, sbox, ssc, order, st);
+  NmsArgs na;
+  memset(&na, 0, sizeof(na));
+  na.boxes = sbox; na.scores = ssc; na.valid = nullptr; na.N = 1; na.K = k; na.thresh = thresh; na.max_keep = max_keep;
+  na.mask = mask; na.out_boxes = obox; na.out_scores = nullptr; na.out_idx = oidx; na.out_count = count;
+  if (!rc) rc = nms_sorted(na, st);
+  if (!rc) rc = remap_indices(oidx, order, max_keep, keep, st);
+  cudaStreamSynchronize(st);
+  cudaFree(sbox); cudaFree(ssc); cudaFree(order); cudaFree(obox); cudaFree(oidx); cudaFree(mask);
+  return rc;
+}
+
+int vltk_roi_pool_nchw(const float* feat, int n, int c, int hh, int ww, const float* rois5, int r, int pp, float scale,
+                       float* out, void* stream) {
+  VLTK_CHECK(feat && rois5 && out, "roi_pool: null argument");
+  VLTK_CHECK(c % 4 == 0, "roi_pool: C must be a multiple of 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  // the stage entry accepts arbitrary batch indices: pool each ROI as its own "image slot"
+  float *nhwc = nullptr, *boxes = nullptr, *tmp = nullptr;
+  int *bidx = nullptr, *ones = nullptr;
+  VLTK_CUDA(cudaMalloc(&nhwc, (size_t)n * hh * ww * c * 4));
+  VLTK_CUDA(cudaMalloc(&boxes, (size_t)std::max(r, 1) * 16));
+  VLTK_CUDA(cudaMalloc(&bidx, (size_t)std::max(r, 1) * 4));
+  VLTK_CUDA(cudaMalloc(&ones, (size_t)std::max(n, 1) * 4));
+  VLTK_CUDA(cudaMalloc(&tmp, (size_t)std::max(r, 1) * pp * pp * c * 4));
+  int64_t tot = (int64_t)n * c * hh * ww;
+  nchw_to_nhwc_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(feat, nhwc, c, hh * ww, c, 0, tot);
+  int rc = 0;
+  if (r > 0) {
+    rois5_split_kernel<<<ceil_div(r, 128), 128, 0, st>>>(rois5, r, boxes, bidx);
+    rc = roi_pool_indexed(nhwc, DT_F32, hh, ww, c, boxes, bidx, r, pp, scale, tmp, st);
+    int64_t to = (int64_t)r * c * pp * pp;
+    nhwc_to_nchw_kernel<<<(unsigned)ceil_div64(to, 256), 256, 0, st>>>(tmp, out, c, pp * pp, to);
+  }
+  cudaStreamSynchronize(st);
+  cudaFree(nhwc); cudaFree(boxes); cudaFree(bidx); cudaFree(ones); cudaFree(tmp);
+  VLTK_LAUNCH_CHECK();
+  return rc;
+}
+
+int vltk_roi_outputs(const float* obj_logits, const float* attr_logits, const float* box_deltas, const float* feats,
+                     const float* proposals, const int32_t* counts, const int32_t* sizes_hw, const float* scales_yx,
+                     int n, int r, int num_classes, int num_attrs, int d, const float weights[4],
+                     const vltk_frcnn_knobs* knobs, const vltk_frcnn_out* out, void* stream) {
+  VLTK_CHECK(obj_logits && attr_logits && box_deltas && feats && proposals && counts && sizes_hw && knobs && out,
+             "roi_outputs: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int* sizes = nullptr;
+  float* scales = nullptr;
+  VLTK_CUDA(cudaMalloc(&sizes, (size_t)n * 8));
+  VLTK_CUDA(cudaMalloc(&scales, (size_t)n * 8));
+  VLTK_CUDA(cudaMemcpyAsync(sizes, sizes_hw, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  if (scales_yx) VLTK_CUDA(cudaMemcpyAsync(scales, scales_yx, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  TailArgs ta;
+  memset(&ta, 0, sizeof(ta));
+  ta.N = n; ta.R = r; ta.cls_logits = obj_logits; ta.ldc = num_classes + 1; ta.bbox_deltas = box_deltas; ta.ldb = num_classes * 4;
+  ta.attr_logits = attr_logits; ta.lda = num_attrs + 1; ta.feats = feats; ta.D = d; ta.proposals = proposals;
+  ta.count = counts; ta.sizes_hw = sizes; ta.scales_yx = scales_yx ? scales : nullptr;
+  ta.num_classes = num_classes; ta.num_attrs = num_attrs;
+  ta.wx = weights[0]; ta.wy = weights[1]; ta.ww = weights[2]; ta.wh = weights[3];
+  ta.nms_thresh = knobs->nms_thresh; ta.n_thresh = knobs->n_nms_thresh; ta.min_det = knobs->min_detections;
+  ta.max_det = knobs->max_detections; ta.pad_value = knobs->pad_value;
+  ta.boxes = out->boxes; ta.norm_boxes = out->normalized_boxes; ta.obj_ids = (long long*)out->obj_ids;
+  ta.obj_probs = out->obj_probs; ta.attr_ids = (long long*)out->attr_ids; ta.attr_probs = out->attr_probs;
+  ta.roi_features = out->roi_features; ta.preds_per_image = out->preds_per_image; ta.keep_idx = out->keep_idx;
+  int rc = roi_tail(ta, st);
+  cudaStreamSynchronize(st);
+  cudaFree(sizes); cudaFree(scales);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,231 @@
+"""Drop-in for `vltk.modeling.frcnn.FRCNN` (reference: vltk/modeling/frcnn.py:1743-2004).
+
+Same constructor / `from_pretrained` / `forward(images, image_shapes, scales_yx=..., **kw)`
+contract and the same mutable `roi_outputs.{nms_thresh,min_detections,max_detections}`
+knobs (tests/frcnn_test.py:16-31), but everything below the call is the C-ABI library
+(include/vltk_frcnn.h): hand-written sm_100a kernels, no torch ops, no CPU fallback.
+torch is used only for device memory, streams and host<->device copies.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import FRCNNConfig
+
+
+class ROIOutputs:
+    """The knobs callers poke on `model.roi_outputs` (frcnn.py:1229-1240)."""
+
+    def __init__(self, cfg: FRCNNConfig):
+        nms = cfg.nms_thresh_test
+        self.nms_thresh = list(nms) if isinstance(nms, (list, tuple)) else [nms]
+        self.score_thresh = cfg.score_thresh_test  # accepted, never used — as in the reference
+        self.min_detections = cfg.min_detections
+        self.max_detections = cfg.max_detections
+
+
+class FRCNN:
+    def __init__(self, cfg: Optional[FRCNNConfig] = None, mode: str = "bf16", device: int = 0):
+        self.config = cfg or FRCNNConfig()
+        self.mode = mode
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.roi_outputs = ROIOutputs(self.config)
+        self.min_detections = self.config.min_detections
+        self.max_detections = self.config.max_detections
+        self.training = False
+        self._lib = _lib.lib()
+        self._h = C.c_void_p()
+        ccfg = _lib.make_config(self.config, mode)
+        _lib.check(self._lib.vltk_frcnn_create(C.byref(ccfg), self.device_index, C.byref(self._h)),
+                   "vltk_frcnn_create")
+        self._finalized = False
+        self._workspace = None
+        self._pinned: Dict[tuple, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ lifecycle
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                self._lib.vltk_frcnn_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def eval(self):
+        return self
+
+    def to(self, *_a, **_k):
+        return self
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path=None, *model_args, **kwargs):
+        """Reference: frcnn.py:1757-1922.  There is no hub access here: a `state_dict` (the
+        reference's 640-key layout) or a local checkpoint path must be
+        given; `config` may be an FRCNNConfig."""
+        config = kwargs.pop("config", None)
+        if config is None and model_args:
+            config = model_args[0]
+        state_dict = kwargs.pop("state_dict", None)
+        mode = kwargs.pop("mode", "bf16")
+        device = kwargs.pop("device", 0)
+        if state_dict is None:
+            if pretrained_model_name_or_path is None:
+                raise ValueError("from_pretrained needs state_dict= or a local checkpoint path")
+            state_dict = torch.load(pretrained_model_name_or_path, map_location="cpu")
+        model = cls(config if isinstance(config, FRCNNConfig) else None, mode=mode, device=device)
+        model.load_state_dict(state_dict)
+        return model
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        if self._finalized:
+            raise RuntimeError("weights already loaded into this engine")
+        for key, t in state_dict.items():
+            # old-format BN names, as the reference renames them (frcnn.py:1862-1872)
+            key = key.replace("gamma", "weight") if "gamma" in key else key
+            key = key.replace("beta", "bias") if "beta" in key else key
+            if key.endswith("num_batches_tracked"):
+                continue
+            a = np.ascontiguousarray(t.detach().cpu().float().numpy())
+            _lib.check(self._lib.vltk_frcnn_load_tensor(self._h, key.encode(), a.ctypes.data, a.size),
+                       f"load_tensor({key})")
+        _lib.check(self._lib.vltk_frcnn_finalize(self._h), "vltk_frcnn_finalize")
+        self._finalized = True
+        return self
+
+    # -------------------------------------------------------------------- forward
+    def _ws(self, n, h, w):
+        need = int(self._lib.vltk_frcnn_workspace_bytes(self._h, n, h, w))
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = None
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    def _alloc_out(self, n, md, d):
+        dev = self.device
+        t = OrderedDict(
+            boxes=torch.empty((n, md, 4), dtype=torch.float32, device=dev),
+            normalized_boxes=torch.empty((n, md, 4), dtype=torch.float32, device=dev),
+            obj_ids=torch.empty((n, md), dtype=torch.int64, device=dev),
+            obj_probs=torch.empty((n, md), dtype=torch.float32, device=dev),
+            attr_ids=torch.empty((n, md), dtype=torch.int64, device=dev),
+            attr_probs=torch.empty((n, md), dtype=torch.float32, device=dev),
+            roi_features=torch.empty((n, md, d), dtype=torch.float32, device=dev),
+            preds_per_image=torch.empty((n,), dtype=torch.int32, device=dev),
+            keep_idx=torch.empty((n, md), dtype=torch.int32, device=dev),
+        )
+        o = _lib.Out()
+        for k, v in t.items():
+            setattr(o, k, v.data_ptr())
+        return t, o
+
+    def run(self, images: torch.Tensor, sizes_hw: np.ndarray, scales_yx: Optional[np.ndarray],
+            max_detections: int, min_detections: int, nms_thresh, pad_value: float = 0.0):
+        """Enqueues one forward on the current stream; returns the dense device tensors."""
+        if not self._finalized:
+            raise RuntimeError("load_state_dict() has not been called")
+        assert images.is_cuda and images.dtype == torch.float32 and images.is_contiguous()
+        n, c, h, w = images.shape
+        assert c == 3
+        sizes_hw = np.ascontiguousarray(sizes_hw, dtype=np.int32).reshape(n, 2)
+        sc_ptr = None
+        if scales_yx is not None:
+            scales_yx = np.ascontiguousarray(scales_yx, dtype=np.float32).reshape(n, 2)
+            sc_ptr = scales_yx.ctypes.data
+        ws = self._ws(n, h, w)
+        d = self.config.res2_out_channels * 8
+        tensors, out = self._alloc_out(n, max_detections, d)
+        knobs = _lib.make_knobs(nms_thresh, min_detections, max_detections, pad_value)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self._lib.vltk_frcnn_forward(
+            self._h, images.data_ptr(), sizes_hw.ctypes.data, sc_ptr, n, h, w, C.byref(knobs),
+            C.byref(out), ws.data_ptr(), ws.numel(), stream), "vltk_frcnn_forward")
+        tensors["_keepalive"] = (images, sizes_hw, scales_yx)
+        return tensors
+
+    def forward(self, images, image_shapes, gt_boxes=None, proposals=None, scales_yx=None,
+                ignorey=None, **kwargs):
+        """kwargs (frcnn.py:1924-1929): max_detections, return_tensors in {"np","pt",None},
+        padding in {None,"max_detections"}, pad_value, location in {"cuda","cpu"}.
+
+        padding=None returns the live reference's ragged lists of per-image tensors;
+        padding="max_detections" returns the v1.0.0 dense layout [N,max_det,...] plus `sizes`
+        and `normalized_boxes`."""
+        if self.training:
+            raise NotImplementedError()
+        if gt_boxes is not None or proposals is not None or ignorey is not None:
+            raise NotImplementedError("gt_boxes / proposals / ignorey are not part of the extraction path")
+        padding = kwargs.get("padding", None)
+        return_tensors = kwargs.get("return_tensors", None)
+        pad_value = kwargs.get("pad_value", 0)
+        location = kwargs.get("location", None) or "cpu"
+        assert padding in (None, "max_detections"), padding
+        assert return_tensors in (None, "np", "pt"), return_tensors
+        ro = self.roi_outputs
+        max_det = int(kwargs.get("max_detections", None) or ro.max_detections)
+        min_det = min(int(ro.min_detections), max_det)
+
+        with torch.cuda.device(self.device):
+            x = torch.as_tensor(images)
+            if not x.is_cuda:
+                x = x.float().contiguous()
+                x = (x if x.is_pinned() else x.pin_memory()).to(self.device, non_blocking=True)
+            else:
+                x = x.to(self.device).float().contiguous()
+            sizes = np.asarray(torch.as_tensor(image_shapes).cpu().numpy(), dtype=np.int32)
+            scales = None if scales_yx is None else \
+                np.asarray(torch.as_tensor(scales_yx).cpu().numpy(), dtype=np.float32)
+            t = self.run(x, sizes, scales, max_det, min_det, ro.nms_thresh, float(pad_value))
+            t.pop("_keepalive")
+            keep = t.pop("keep_idx")
+            counts = t["preds_per_image"].cpu().to(torch.int64)  # the one sync; int64 like frcnn.py:1985
+
+        def place(v):
+            return v.cpu() if (location == "cpu" or return_tensors == "np") else v
+
+        keys = ("obj_ids", "obj_probs", "attr_ids", "attr_probs", "boxes", "roi_features")
+        if padding is None:
+            out = OrderedDict()
+            for k in keys[:5]:
+                out[k] = [place(t[k][i, : int(c)]) for i, c in enumerate(counts)]
+            out["preds_per_image"] = counts
+            out["roi_features"] = [place(t["roi_features"][i, : int(c)]) for i, c in enumerate(counts)]
+            out["keep_idx"] = [place(keep[i, : int(c)]).to(torch.int64) for i, c in enumerate(counts)]
+            return out
+        out = OrderedDict()
+        for k in keys:
+            out[k] = place(t[k])
+        out["preds_per_image"] = counts
+        out["sizes"] = torch.as_tensor(sizes.astype(np.int64))
+        out["normalized_boxes"] = place(t["normalized_boxes"])
+        out["keep_idx"] = place(keep)
+        if return_tensors == "np":
+            out = OrderedDict((k, v.numpy()) for k, v in out.items())
+        return out
+
+    __call__ = forward
+    inference = forward
+
+    # ------------------------------------------------------------------ test taps
+    def debug_read(self, name: str, dtype=np.float32) -> np.ndarray:
+        """Copies an intermediate of the last forward to the host (tests only)."""
+        cap = 1 << 20
+        while True:
+            buf = np.empty(cap, dtype=np.float32)
+            n = int(self._lib.vltk_frcnn_debug_read(self._h, name.encode(), buf.ctypes.data, cap))
+            if n >= 0:
+                return buf[:n].view(dtype).copy()
+            msg = self._lib.vltk_frcnn_last_error().decode()
+            if "capacity" in msg and cap < (1 << 33):
+                cap *= 8
+                continue
+            raise _lib.LibraryError(msg)
+
+    def launch_count(self) -> int:
+        return int(self._lib.vltk_frcnn_launch_count(self._h))

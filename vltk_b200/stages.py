@@ -1,0 +1,136 @@
+"""Torch-tensor wrappers over the stage entry points of include/vltk_frcnn.h — used by the
+teacher-forced parity tests and the config-4 microbenchmarks.  Each mirrors the reference
+call it replaces; all tensors must live on the CUDA device (no CPU fallback)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def conv2d_nhwc(x, weight, scale=None, shift=None, residual=None, stride=1, pad=0, dil=1, relu=False,
+                mode="fp32", tensor_cores=False):
+    """x [N,H,W,Cin] (f32 or bf16 per `mode`), weight [Cout,Cin,k,k] f32 (reference layout);
+    returns y [N,OH,OW,Cout] = act(conv(x,w)*scale + shift + residual)
+    (reference: Conv2d+BN+ReLU, frcnn.py:794-822; bottleneck add, :963-979)."""
+    L = _lib.lib()
+    dt = torch.float32 if mode == "fp32" else torch.bfloat16
+    assert x.is_cuda and x.dtype == dt and x.is_contiguous()
+    n, h, w, cin = x.shape
+    cout, cin2, kh, kw = weight.shape
+    assert cin2 == cin
+    oh = (h + 2 * pad - (dil * (kh - 1) + 1)) // stride + 1
+    ow = (w + 2 * pad - (dil * (kw - 1) + 1)) // stride + 1
+    y = torch.empty((n, oh, ow, cout), dtype=dt, device=x.device)
+    wt = weight.to(x.device, torch.float32).contiguous()
+    sc = None if scale is None else scale.to(x.device, torch.float32).contiguous()
+    sh = None if shift is None else shift.to(x.device, torch.float32).contiguous()
+    if residual is not None:
+        assert residual.dtype == dt and residual.shape == y.shape and residual.is_contiguous()
+    with torch.cuda.device(x.device):
+        _lib.check(L.vltk_conv2d_nhwc(x.data_ptr(), wt.data_ptr(), _ptr(sc), _ptr(sh), _ptr(residual),
+                                      y.data_ptr(), n, h, w, cin, cout, kh, kw, stride, pad, dil,
+                                      int(relu), _lib.MODES[mode], int(tensor_cores), _stream(x)),
+                   "vltk_conv2d_nhwc")
+    return y
+
+
+def rpn_proposals(logits, deltas, cell_anchors, image_shapes, cfg):
+    """find_top_rpn_proposals + RPN.inference (frcnn.py:264-390, 1615-1638) on NCHW head
+    outputs.  Returns (proposals [N,post,4], logits [N,post], counts [N])."""
+    L = _lib.lib()
+    assert logits.is_cuda and deltas.is_cuda
+    n, a, h4, w4 = logits.shape
+    post = cfg.rpn_post_nms_topk
+    props = torch.empty((n, post, 4), dtype=torch.float32, device=logits.device)
+    plog = torch.empty((n, post), dtype=torch.float32, device=logits.device)
+    counts = torch.empty((n,), dtype=torch.int32, device=logits.device)
+    cell = np.ascontiguousarray(cell_anchors.detach().cpu().numpy(), dtype=np.float32)
+    sizes = np.ascontiguousarray(np.asarray(image_shapes), dtype=np.int32).reshape(n, 2)
+    wts = (C.c_float * 4)(*cfg.rpn_bbox_weights)
+    lg = logits.float().contiguous()
+    dl = deltas.float().contiguous()
+    with torch.cuda.device(logits.device):
+        _lib.check(L.vltk_rpn_proposals(lg.data_ptr(), dl.data_ptr(), cell.ctypes.data, sizes.ctypes.data,
+                                        n, a, h4, w4, cfg.anchor_stride, cfg.rpn_pre_nms_topk, post,
+                                        cfg.rpn_nms_thresh, cfg.rpn_min_size, wts, props.data_ptr(),
+                                        plog.data_ptr(), counts.data_ptr(), _stream(logits)),
+                   "vltk_rpn_proposals")
+    return props, plog, counts
+
+
+def nms(boxes, scores, thresh, max_keep=None):
+    """torchvision.ops.nms(boxes, scores, thresh)[:max_keep] (frcnn.py:132-133, 383-384)."""
+    L = _lib.lib()
+    k = boxes.shape[0]
+    max_keep = max(1, min(max_keep or k, 8192))
+    keep = torch.empty((max_keep,), dtype=torch.int32, device=boxes.device)
+    count = torch.zeros((1,), dtype=torch.int32, device=boxes.device)
+    b = boxes.float().contiguous()
+    s = scores.float().contiguous()
+    with torch.cuda.device(boxes.device):
+        _lib.check(L.vltk_nms(b.data_ptr(), s.data_ptr(), k, float(thresh), max_keep, keep.data_ptr(),
+                              count.data_ptr(), _stream(boxes)), "vltk_nms")
+    return keep[: int(count.item())].to(torch.int64)
+
+
+def roi_pool(feat, rois, output_size, spatial_scale):
+    """torchvision.ops.RoIPool(output_size, spatial_scale)(feat, rois) (frcnn.py:1179, 1198)."""
+    L = _lib.lib()
+    n, c, h, w = feat.shape
+    r = rois.shape[0]
+    out = torch.empty((r, c, output_size, output_size), dtype=torch.float32, device=feat.device)
+    f = feat.float().contiguous()
+    rr = rois.float().contiguous()
+    with torch.cuda.device(feat.device):
+        _lib.check(L.vltk_roi_pool_nchw(f.data_ptr(), n, c, h, w, rr.data_ptr(), r, output_size,
+                                        float(spatial_scale), out.data_ptr(), _stream(feat)),
+                   "vltk_roi_pool_nchw")
+    return out
+
+
+def roi_outputs(obj_logits, attr_logits, box_deltas, feats, proposals, counts, image_shapes, scales_yx,
+                cfg, nms_thresh=None, min_det=None, max_det=None, pad_value=0.0):
+    """ROIOutputs.inference (frcnn.py:1262-1294) in the padded layout.  proposals [N,R,4]."""
+    L = _lib.lib()
+    dev = obj_logits.device
+    n, r = proposals.shape[0], proposals.shape[1]
+    d = feats.shape[1]
+    md = max_det or cfg.max_detections
+    t = dict(
+        boxes=torch.empty((n, md, 4), dtype=torch.float32, device=dev),
+        normalized_boxes=torch.empty((n, md, 4), dtype=torch.float32, device=dev),
+        obj_ids=torch.empty((n, md), dtype=torch.int64, device=dev),
+        obj_probs=torch.empty((n, md), dtype=torch.float32, device=dev),
+        attr_ids=torch.empty((n, md), dtype=torch.int64, device=dev),
+        attr_probs=torch.empty((n, md), dtype=torch.float32, device=dev),
+        roi_features=torch.empty((n, md, d), dtype=torch.float32, device=dev),
+        preds_per_image=torch.empty((n,), dtype=torch.int32, device=dev),
+        keep_idx=torch.empty((n, md), dtype=torch.int32, device=dev))
+    o = _lib.Out()
+    for k, v in t.items():
+        setattr(o, k, v.data_ptr())
+    knobs = _lib.make_knobs(nms_thresh or cfg.nms_thresh_test, min_det if min_det is not None else cfg.min_detections,
+                            md, pad_value)
+    sizes = np.ascontiguousarray(np.asarray(image_shapes), dtype=np.int32).reshape(n, 2)
+    sc = None if scales_yx is None else np.ascontiguousarray(np.asarray(scales_yx), dtype=np.float32).reshape(n, 2)
+    wts = (C.c_float * 4)(*cfg.roi_bbox_weights)
+    args = [x.float().contiguous() for x in (obj_logits, attr_logits, box_deltas, feats, proposals)]
+    cn = counts.to(dev, torch.int32).contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(L.vltk_roi_outputs(*[a.data_ptr() for a in args], cn.data_ptr(), sizes.ctypes.data,
+                                      None if sc is None else sc.ctypes.data, n, r, cfg.num_classes,
+                                      cfg.num_attrs, d, wts, C.byref(knobs), C.byref(o), _stream(obj_logits)),
+                   "vltk_roi_outputs")
+    return t
