@@ -1,0 +1,203 @@
+"""Teacher-forced per-stage parity (GPU, through the C ABI): every kernel is fed the ORACLE's
+inputs for its stage and must reproduce the oracle's outputs — indices exactly, floats to the
+stated tolerance — so that a selection kernel's exactness is tested independently of
+dense-kernel rounding."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import cases, frcnn_oracle as O
+from tests.util import oracle_run, weights
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch.device("cuda", 0)
+
+
+def _ref_conv(x_nhwc, w, scale, shift, res, stride, pad, dil, relu):
+    y = F.conv2d(x_nhwc.permute(0, 3, 1, 2).double().cpu(), w.double().cpu(), None, stride, pad, dil)
+    y = y * scale.double().cpu().view(1, -1, 1, 1) + shift.double().cpu().view(1, -1, 1, 1)
+    y = y.permute(0, 2, 3, 1)
+    if res is not None:
+        y = y + res.double().cpu()
+    return (F.relu(y) if relu else y).float()
+
+
+CONV_CASES = [
+    # n, h, w, cin, cout, k, stride, pad, dil, residual, relu
+    (1, 12, 16, 64, 64, 1, 1, 0, 1, False, True),       # res2 conv1
+    (2, 14, 14, 64, 128, 3, 1, 2, 2, False, True),      # dilated 3x3 (res5 conv2 pattern)
+    (1, 25, 33, 128, 256, 1, 2, 0, 1, False, False),    # stride-2 1x1 on odd extents (res3.0)
+    (3, 14, 14, 128, 256, 1, 1, 0, 1, True, True),      # conv3 + residual + relu
+    (1, 19, 23, 64, 64, 3, 1, 1, 1, False, True),       # 3x3 pad 1, ragged M tail
+    (2, 14, 14, 256, 512, 3, 1, 2, 2, True, True),
+    (1, 13, 17, 1024, 512, 3, 1, 1, 1, False, True),    # RPN conv pattern
+    (5, 14, 14, 512, 2048, 1, 1, 0, 1, True, True),     # res5 conv3
+    (300, 1, 1, 2048, 1604, 1, 1, 0, 1, False, False),  # predictor linear (M=300, odd N)
+]
+
+
+def _conv_inputs(case, dev, dt):
+    n, h, w, cin, cout, k, s, p, d, use_res, relu = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn(n, h, w, cin, generator=g).to(dev).to(dt)
+    wt = (torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5).to(dev)
+    sc = (torch.rand(cout, generator=g) + 0.5).to(dev)
+    sh = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    oh = (h + 2 * p - (d * (k - 1) + 1)) // s + 1
+    ow = (w + 2 * p - (d * (k - 1) + 1)) // s + 1
+    res = torch.randn(n, oh, ow, cout, generator=g).to(dev).to(dt) if use_res else None
+    return x, wt, sc, sh, res
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fp32_matches_reference_conv(dev, case):
+    from vltk_b200 import stages
+    n, h, w, cin, cout, k, s, p, d, use_res, relu = case
+    x, wt, sc, sh, res = _conv_inputs(case, dev, torch.float32)
+    y = stages.conv2d_nhwc(x, wt, sc, sh, res, s, p, d, relu, mode="fp32")
+    ref = _ref_conv(x, wt, sc, sh, res, s, p, d, relu)
+    # fp32 FMA accumulation vs an fp64 reference: K <= 9216 terms of O(1)
+    np.testing.assert_allclose(y.cpu().numpy(), ref.numpy(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[3] % 64 == 0 and c[4] % 64 == 0])
+def test_conv_tcgen05_matches_simt_and_reference(dev, case):
+    """tcgen05 path vs (a) the SIMT kernel on identical bf16 operands (both accumulate in fp32,
+    outputs round to bf16: may differ by one bf16 ulp) and (b) an fp64 conv of those operands."""
+    from vltk_b200 import stages
+    n, h, w, cin, cout, k, s, p, d, use_res, relu = case
+    x, wt, sc, sh, res = _conv_inputs(case, dev, torch.bfloat16)
+    wt = wt.bfloat16().float()
+    y_tc = stages.conv2d_nhwc(x, wt, sc, sh, res, s, p, d, relu, mode="bf16", tensor_cores=True).float().cpu()
+    y_si = stages.conv2d_nhwc(x, wt, sc, sh, res, s, p, d, relu, mode="bf16", tensor_cores=False).float().cpu()
+    ref = _ref_conv(x, wt, sc, sh, res, s, p, d, relu)
+    ulp = 2.0 ** -7  # bf16 relative spacing
+    assert ((y_tc - y_si).abs() <= ulp * (y_si.abs() + 1e-2)).all()
+    assert ((y_tc - ref).abs() <= ulp * (ref.abs() + 1e-2)).all()
+
+
+def test_preprocess_matches_oracle(dev):
+    from vltk_b200.preprocess import Preprocess
+    for name in ("mixed", "tiny"):
+        cfg, _, raws = cases.case_inputs(name)
+        ids, images, sizes, scales = Preprocess(cfg)(raws)
+        oi, osz, osc = O.preprocess(cfg, raws)
+        assert images.shape == oi.shape
+        assert torch.equal(sizes, osz)
+        assert torch.equal(scales, osc)
+        # bilinear weights are fp32 products of u8 pixels: round-off only
+        np.testing.assert_allclose(images.cpu().numpy(), oi.numpy(), rtol=0, atol=2e-4)
+
+
+@pytest.mark.parametrize("name", ["tiny", "mixed", "full36"])
+def test_rpn_selection_teacher_forced(dev, name):
+    """Oracle RPN-head outputs in -> top-k / decode / clip / NMS(0.7) / first-300 out."""
+    from vltk_b200 import stages
+    cfg, images, sizes, scales, out, st = oracle_run(name)
+    cell = weights()["proposal_generator.anchor_generator.cell_anchors.0"]
+    props, plog, counts = stages.rpn_proposals(st["rpn_logits"].to(dev), st["rpn_deltas"].to(dev), cell,
+                                               sizes.numpy(), cfg)
+    counts = counts.cpu().tolist()
+    assert counts == [len(p) for p in st["proposals"]]
+    for i, c in enumerate(counts):
+        # same anchors in the same order: logits are copied, never recomputed -> bit exact
+        assert torch.equal(plog[i, :c].cpu(), st["proposal_logits"][i])
+        # decode uses CUDA expf vs the host's: sub-pixel round-off only
+        np.testing.assert_allclose(props[i, :c].cpu().numpy(), st["proposals"][i].numpy(), rtol=0, atol=2e-3)
+
+
+def _rand_boxes(n, seed, span=400.0):
+    g = torch.Generator().manual_seed(seed)
+    xy = torch.rand(n, 2, generator=g) * span
+    wh = torch.rand(n, 2, generator=g) * 120 + 1
+    return torch.cat([xy, xy + wh], 1)
+
+
+@pytest.mark.parametrize("n,thr,seed", [(1, 0.5, 0), (37, 0.3, 1), (300, 0.3, 2), (1000, 0.7, 3), (6000, 0.7, 4)])
+def test_nms_matches_oracle_exactly(dev, n, thr, seed):
+    from vltk_b200 import stages
+    boxes = _rand_boxes(n, seed)
+    scores = torch.rand(n, generator=torch.Generator().manual_seed(100 + seed))
+    keep = stages.nms(boxes.to(dev), scores.to(dev), thr).cpu().numpy()
+    ref = O.nms_np(boxes.numpy(), scores.numpy(), thr)
+    assert np.array_equal(keep, ref)
+
+
+def test_nms_edge_cases(dev):
+    from vltk_b200 import stages
+    # duplicates with tied scores: the lower index survives (stable order); zero-area boxes give
+    # IoU = 0/0 = NaN against themselves and are never suppressed
+    boxes = torch.tensor([[0, 0, 10, 10], [0, 0, 10, 10], [5, 5, 5, 5], [5, 5, 5, 5], [0, 0, 10, 10.5]],
+                         dtype=torch.float32)
+    scores = torch.tensor([0.5, 0.5, 0.9, 0.9, 0.5])
+    keep = stages.nms(boxes.to(dev), scores.to(dev), 0.5).cpu().numpy()
+    assert np.array_equal(keep, O.nms_np(boxes.numpy(), scores.numpy(), 0.5))
+    assert keep.tolist() == [2, 3, 0]
+    # max_keep truncation == slicing the full result
+    b = _rand_boxes(500, 9)
+    s = torch.rand(500, generator=torch.Generator().manual_seed(9))
+    full = O.nms_np(b.numpy(), s.numpy(), 0.4)
+    assert np.array_equal(stages.nms(b.to(dev), s.to(dev), 0.4, max_keep=20).cpu().numpy(), full[:20])
+
+
+def test_roi_pool_matches_oracle_exactly(dev):
+    from vltk_b200 import stages
+    g = torch.Generator().manual_seed(5)
+    feat = torch.randn(2, 64, 23, 31, generator=g)
+    b = _rand_boxes(60, 6, span=420.0)
+    b[0] = torch.tensor([-50.0, -40.0, -10.0, -5.0])      # fully outside -> zeros
+    b[1] = torch.tensor([100.0, 100.0, 100.0, 100.0])     # degenerate -> 1x1 region
+    b[2] = torch.tensor([0.0, 0.0, 495.9, 367.9])         # whole map and beyond
+    b[3] = torch.tensor([7.99, 8.0, 24.0, 23.99])         # rounding at .5 cell boundaries
+    rois = torch.cat([torch.randint(0, 2, (60, 1), generator=g).float(), b], 1)
+    out = stages.roi_pool(feat.to(dev), rois.to(dev), 14, 1.0 / 16).cpu()
+    ref = O.roi_pool_np(feat, rois, 14, 1.0 / 16)
+    assert torch.equal(out, ref)  # max-pooling copies values: bit exact
+    try:
+        from torchvision.ops import RoIPool
+        assert torch.equal(out, RoIPool((14, 14), 1.0 / 16)(feat, rois))
+    except ImportError:
+        pass
+
+
+@pytest.mark.parametrize("name", ["tiny", "mixed", "full36"])
+def test_detection_tail_teacher_forced(dev, name):
+    """Oracle predictor outputs in -> softmax / decode / clip / NMS / top-k / gather out."""
+    from vltk_b200 import stages
+    cfg, images, sizes, scales, out, st = oracle_run(name)
+    n, r = len(st["proposals"]), cfg.rpn_post_nms_topk
+    props = torch.zeros(n, r, 4)
+    pad = lambda t, w: torch.cat([t, t.new_zeros((r - t.shape[0], w))], 0)  # noqa: E731
+    ol, al, bd, ft = [], [], [], []
+    s = 0
+    for i, p in enumerate(st["proposals"]):
+        c = len(p)
+        props[i, :c] = p
+        ol.append(pad(st["obj_logits"][s:s + c], st["obj_logits"].shape[1]))
+        al.append(pad(st["attr_logits"][s:s + c], st["attr_logits"].shape[1]))
+        bd.append(pad(st["box_deltas"][s:s + c], st["box_deltas"].shape[1]))
+        ft.append(pad(st["feats"][s:s + c], st["feats"].shape[1]))
+        s += c
+    counts = torch.tensor([len(p) for p in st["proposals"]], dtype=torch.int32)
+    t = stages.roi_outputs(torch.cat(ol).to(dev), torch.cat(al).to(dev), torch.cat(bd).to(dev),
+                           torch.cat(ft).to(dev), props.to(dev), counts, sizes.numpy(), scales.numpy(), cfg)
+    ppi = t["preds_per_image"].cpu().tolist()
+    assert ppi == out["preds_per_image"].tolist()
+    for i, c in enumerate(ppi):
+        assert torch.equal(t["keep_idx"][i, :c].cpu().long(), out["keep"][i])
+        assert torch.equal(t["obj_ids"][i, :c].cpu(), out["obj_ids"][i])
+        assert torch.equal(t["attr_ids"][i, :c].cpu(), out["attr_ids"][i])
+        np.testing.assert_allclose(t["boxes"][i, :c].cpu().numpy(), out["boxes"][i].numpy(), rtol=0, atol=2e-3)
+        np.testing.assert_allclose(t["obj_probs"][i, :c].cpu().numpy(), out["obj_probs"][i].numpy(), rtol=0, atol=1e-5)
+        np.testing.assert_allclose(t["attr_probs"][i, :c].cpu().numpy(), out["attr_probs"][i].numpy(), rtol=0, atol=1e-5)
+        assert torch.equal(t["roi_features"][i, :c].cpu(), out["roi_features"][i])  # gather: bit exact
+        assert (t["roi_features"][i, c:] == 0).all() and (t["obj_ids"][i, c:] == 0).all()
+    padded = O.pad_outputs(out, sizes, scales, cfg.max_detections)
+    np.testing.assert_allclose(t["normalized_boxes"].cpu().numpy(), padded["normalized_boxes"].numpy(), rtol=0, atol=1e-5)

@@ -64,6 +64,11 @@ struct vltk_frcnn {
   std::map<std::string, Tap> taps;
   int64_t launches = 0;
   TensorMapCache tmaps;
+  // optional per-launch event timing (bench roofline leg)
+  bool profiling = false;
+  struct ProfRec { int kind; double flops; int64_t M; int K, Cout; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> event_pool;
 };
 
 namespace vltk_eng {
@@ -201,9 +206,27 @@ int run_conv(vltk_frcnn* h, const LayerW& L, const void* x, DType xdt, int N, in
   if (oh_out) *oh_out = p.OH;
   if (ow_out) *ow_out = p.OW;
   h->launches++;
-  if (h->use_tc && L.w_nk && xdt == DT_BF16 && ydt == DT_BF16)
-    return conv_tc_launch(p, L.w_nk, L.cout_pad, &h->tmaps, st);
-  return conv_simt_launch(p, L.w_kn, L.ldw, st);
+  const bool tc = h->use_tc && L.w_nk && xdt == DT_BF16 && ydt == DT_BF16;
+  vltk_frcnn::ProfRec rec;
+  if (h->profiling) {
+    auto get_event = [&]() {
+      cudaEvent_t e;
+      if (!h->event_pool.empty()) { e = h->event_pool.back(); h->event_pool.pop_back(); }
+      else cudaEventCreate(&e);
+      return e;
+    };
+    rec.kind = tc ? 0 : 1;
+    rec.M = (int64_t)N * p.OH * p.OW; rec.K = L.k * L.k * L.cin; rec.Cout = L.cout;
+    rec.flops = 2.0 * (double)rec.M * rec.K * rec.Cout;  // algorithmic: unpadded cin/cout
+    rec.e0 = get_event(); rec.e1 = get_event();
+    cudaEventRecord(rec.e0, st);
+  }
+  int rc = tc ? conv_tc_launch(p, L.w_nk, L.cout_pad, &h->tmaps, st) : conv_simt_launch(p, L.w_kn, L.ldw, st);
+  if (h->profiling) {
+    cudaEventRecord(rec.e1, st);
+    h->prof.push_back(rec);
+  }
+  return rc;
 }
 
 struct StageBufs { void *a, *b, *t1, *t2, *s; };
@@ -300,6 +323,8 @@ void vltk_frcnn_destroy(vltk_frcnn_t* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (void* p : h->owned) cudaFree(p);
+  for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (auto e : h->event_pool) cudaEventDestroy(e);
   delete h;
 }
 
@@ -587,6 +612,31 @@ int64_t vltk_frcnn_debug_read(vltk_frcnn_t* h, const char* name, float* dst, int
 }
 
 int64_t vltk_frcnn_launch_count(vltk_frcnn_t* h) { return h ? h->launches : -1; }
+
+int vltk_frcnn_profile_enable(vltk_frcnn_t* h, int enable) {
+  VLTK_CHECK(h, "profile_enable: null handle");
+  h->profiling = enable != 0;
+  return 0;
+}
+
+int vltk_frcnn_profile_read(vltk_frcnn_t* h, double* agg, char* csv, size_t cap) {
+  VLTK_CHECK(h && agg, "profile_read: null argument");
+  VLTK_CUDA(cudaSetDevice(h->device));
+  VLTK_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < 6; ++i) agg[i] = 0.0;
+  size_t off = 0;
+  if (csv && cap) csv[0] = 0;
+  for (auto& r : h->prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    agg[3 * r.kind + 0] += ms; agg[3 * r.kind + 1] += r.flops; agg[3 * r.kind + 2] += 1.0;
+    if (csv && off + 96 < cap)
+      off += snprintf(csv + off, cap - off, "%s,%lld,%d,%d,%.5f\n", r.kind == 0 ? "tcgen05" : "simt", (long long)r.M, r.K, r.Cout, ms);
+    h->event_pool.push_back(r.e0); h->event_pool.push_back(r.e1);
+  }
+  h->prof.clear();
+  return 0;
+}
 
 // ---------------------------------------------------------------------------- stage entries
 int vltk_conv2d_nhwc(const void* x, const float* weight, const float* scale, const float* shift, const void* residual,

@@ -229,3 +229,15 @@ class FRCNN:
 
     def launch_count(self) -> int:
         return int(self._lib.vltk_frcnn_launch_count(self._h))
+
+    def profile(self, enable: bool):
+        _lib.check(self._lib.vltk_frcnn_profile_enable(self._h, int(enable)), "profile_enable")
+
+    def profile_read(self, want_csv: bool = False):
+        """-> ({'tcgen05': (ms, flops, launches), 'simt': (...)}, csv or None); clears the log."""
+        agg = (C.c_double * 6)()
+        buf = C.create_string_buffer(1 << 22) if want_csv else None
+        _lib.check(self._lib.vltk_frcnn_profile_read(self._h, agg, buf, (1 << 22) if want_csv else 0),
+                   "profile_read")
+        d = {"tcgen05": tuple(agg[0:3]), "simt": tuple(agg[3:6])}
+        return d, (buf.value.decode() if want_csv else None)
