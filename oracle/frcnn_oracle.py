@@ -269,7 +269,7 @@ def roi_outputs(cfg, obj_logits, attr_logits, box_deltas, proposals: Sequence[to
     probs_all = F.softmax(obj_logits, dim=-1)
     attr_p_all, attr_i_all = attr_logits[..., :-1].softmax(-1).max(-1)
     res = {k: [] for k in ("boxes", "obj_ids", "obj_probs", "attr_ids", "attr_probs",
-                           "roi_features", "keep")}
+                           "roi_features", "keep", "all_boxes", "all_scores")}
     s = 0
     for i, cnt in enumerate(counts):
         sl = slice(s, s + cnt)
@@ -297,8 +297,11 @@ def roi_outputs(cfg, obj_logits, attr_logits, box_deltas, proposals: Sequence[to
         res["attr_probs"].append(attr_p_all[sl][keep])
         res["roi_features"].append(feats[sl][keep])
         res["keep"].append(keep)
+        res["all_boxes"].append(boxes)      # every ROI's winning-class box (clipped) and score:
+        res["all_scores"].append(max_scores)  # what the final NMS ranked (margin analysis)
     if not return_keep:
-        res.pop("keep")
+        for k in ("keep", "all_boxes", "all_scores"):
+            res.pop(k)
     return res
 
 

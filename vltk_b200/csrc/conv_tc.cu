@@ -13,6 +13,9 @@
 //
 // Reference layers replaced: every Conv2d+BN(+ReLU) of res2-res5 and the RPN 3x3
 // (frcnn.py:794-822, 963-979, 1345-1355, 1569).
+#include <algorithm>
+#include <cstdlib>
+
 #include "conv_tc.cuh"
 
 namespace vltk {
@@ -110,6 +113,31 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// TMA store smem -> global (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// named barrier over the 4 epilogue warps only (id 1; id 0 is __syncthreads)
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 // UMMA shared-memory descriptor, K-major operand in 128B-swizzled rows (8-row atoms of 1024 B):
 //   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 = 1024>>4
@@ -267,6 +295,246 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 2) tmem_dealloc<BN>(tmem_acc);
 }
 
+// =========================================================================================
+// v2: persistent, fully warp-specialised, every global access through TMA.
+//
+//   warp 0   TMA producer     A (im2col) + W tiles -> STAGES-deep smem ring
+//   warp 1   MMA issuer       tcgen05.mma into one of TWO TMEM accumulators (2 x BN columns), so
+//                             tile i+1's MMAs overlap tile i's epilogue
+//   warp 2   TMEM allocator
+//   warp 3   residual producer  [128 x 64] bf16 slabs of the shortcut tensor -> RS-deep smem ring
+//   warps 4-7 epilogue        tcgen05.ld -> scale/shift (+residual from smem) (+ReLU) -> bf16 ->
+//                             128B-swizzled smem staging -> TMA store (double buffered)
+//
+// One CTA per SM loops over tiles t = blockIdx.x, +gridDim.x, ... with the cout tile fastest, so
+// the CTAs running concurrently share A tiles in L2.  Rows past M are zero-filled on load and
+// clipped on store by the TMA unit: no tail code.
+constexpr int SLAB = 64;                       // epilogue column slab: 64 bf16 = one 128 B swizzle row
+constexpr int SLAB_BYTES = BM * SLAB * 2;      // 16 KB
+constexpr int RS = 3;                          // residual ring depth
+
+struct TcParams2 {
+  const float* scale; const float* shift;
+  int64_t M;
+  int Cout, relu;
+  int OH, OW, stride, pad, dil, KW, taps, cblocks;
+  int n_tiles, num_tiles;                      // cout tiles, total tiles
+};
+
+template <int BN, int STAGES, bool HAS_RES>
+struct Smem2 {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
+  static constexpr int OFF_OUT = STAGES * STAGE_BYTES;
+  static constexpr int OFF_RES = OFF_OUT + 2 * SLAB_BYTES;
+  static constexpr int OFF_SCALE = OFF_RES + (HAS_RES ? RS * SLAB_BYTES : 0);
+  static constexpr int OFF_BARS = OFF_SCALE + 2 * BN * 4;
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * RS;
+  static constexpr int TOTAL = OFF_BARS + NUM_BARS * 8 + 16;
+  static_assert(TOTAL <= 232448, "exceeds the 227 KB shared memory of one sm_100 CTA");
+};
+
+template <int BN, int STAGES, bool HAS_RES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, TcParams2 p) {
+  using S = Smem2<BN, STAGES, HAS_RES>;
+  constexpr int NSLAB = BN / SLAB;
+  // no static smem in this kernel: the dynamic window starts at the CTA's (1024 B aligned) base
+  extern __shared__ __align__(1024) unsigned char smem_dyn2[];
+  const uint32_t base = smem_u32(smem_dyn2);
+  if (base & 1023u) {
+    if (threadIdx.x == 0) printf("conv_tc2: dynamic smem base %u is not 1024 B aligned\n", base);
+    __trap();
+  }
+  unsigned char* gbase = smem_dyn2;
+  const uint32_t sA = base, sB = base + S::OFF_B, sOut = base + S::OFF_OUT, sRes = base + S::OFF_RES;
+  float* s_scale = reinterpret_cast<float*>(gbase + S::OFF_SCALE);
+  float* s_shift = s_scale + BN;
+  const uint32_t bars = base + S::OFF_BARS;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+  auto rfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + 4 + s); };
+  auto rempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + 4 + RS + s); };
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + S::OFF_BARS + S::NUM_BARS * 8);
+  const uint32_t tmem_slot = bars + S::NUM_BARS * 8;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = p.taps * p.cblocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY);
+    if (HAS_RES) tma_prefetch_desc(&tmR);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int s = 0; s < RS; ++s) { mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0 && lane == 0) {
+    // ================= TMA producer =================
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const int n0 = (t % p.n_tiles) * BN;
+      const int64_t m0 = (int64_t)(t / p.n_tiles) * BM;
+      const int ow0 = (int)(m0 % p.OW);
+      const int64_t q = m0 / p.OW;
+      const int oh0 = (int)(q % p.OH), img0 = (int)(q / p.OH);
+      const int bw = ow0 * p.stride - p.pad, bh = oh0 * p.stride - p.pad;
+      for (int tap = 0; tap < p.taps; ++tap) {
+        const int kh = tap / p.KW, kw = tap - kh * p.KW;
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), S::STAGE_BYTES);
+          tma_load_im2col_4d(sA + stage * A_STAGE_BYTES, &tmA, full_bar(stage), cb * BK, bw, bh, img0,
+                             (uint16_t)(kw * p.dil), (uint16_t)(kh * p.dil));
+          tma_load_2d(sB + stage * S::B_STAGE_BYTES, &tmB, full_bar(stage), (tap * p.cblocks + cb) * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = make_idesc(BM, BN);
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), use ^ 1u);   // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t a = sA + stage * A_STAGE_BYTES, b = sB + stage * S::B_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k)
+          umma_bf16(d, make_smem_desc(a + k * UMMA_K * 2), make_smem_desc(b + k * UMMA_K * 2), idesc,
+                    (kb | k) ? 1u : 0u);
+        umma_commit(empty_bar(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tfull_bar(acc));
+    }
+  } else if (HAS_RES && warp == 3 && lane == 0) {
+    // ================= residual producer =================
+    int slot = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const int n0 = (t % p.n_tiles) * BN;
+      const int m0 = (t / p.n_tiles) * BM;
+      for (int s = 0; s < NSLAB; ++s) {
+        mbar_wait(rempty_bar(slot), phase ^ 1u);
+        mbar_expect_tx(rfull_bar(slot), SLAB_BYTES);
+        tma_load_2d(sRes + slot * SLAB_BYTES, &tmR, rfull_bar(slot), n0 + s * SLAB, m0);
+        if (++slot == RS) { slot = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int e = warp - 4;                   // TMEM lane quarter == warp id % 4
+    const int row = e * 32 + lane;            // row of the tile owned by this thread
+    const int et = threadIdx.x - 128;         // 0..127
+    const bool issuer = et == 0;
+    const uint32_t swz = (uint32_t)(row & 7);
+    int slot = 0; uint32_t rphase = 0;
+    int obuf = 0, it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int n0 = (t % p.n_tiles) * BN;
+      const int m0 = (t / p.n_tiles) * BM;
+      const int acc = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1) & 1u;
+      // per-tile BN scale/shift -> smem (previous tile's readers are past its last epi_barrier)
+      for (int i = et; i < BN; i += 128) {
+        s_scale[i] = p.scale ? p.scale[n0 + i] : 1.f;
+        s_shift[i] = p.shift ? p.shift[n0 + i] : 0.f;
+      }
+      mbar_wait(tfull_bar(acc), use);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int s = 0; s < NSLAB; ++s) {
+        uint32_t v[64];
+        {
+          uint32_t lo[32], hi[32];
+          tmem_ld32(tacc + (uint32_t)(s * SLAB), lo);
+          tmem_ld32(tacc + (uint32_t)(s * SLAB + 32), hi);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { v[j] = lo[j]; v[32 + j] = hi[j]; }
+        }
+        if (s == NSLAB - 1) {                 // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        if (HAS_RES) mbar_wait(rfull_bar(slot), rphase);
+        if (issuer) bulk_wait_read<1>();      // the store that last read sOut[obuf] has drained it
+        epi_barrier();                        // sOut[obuf] reusable; s_scale/s_shift visible
+        const uint32_t orow = sOut + obuf * SLAB_BYTES + (uint32_t)row * 128u;
+        const uint32_t rrow = sRes + slot * SLAB_BYTES + (uint32_t)row * 128u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {         // 8 channels = one 16 B chunk, stored at chunk q ^ (row % 8)
+          const uint32_t coff = ((uint32_t)q ^ swz) << 4;
+          const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + s * SLAB + q * 8);
+          const float4 sc1 = *reinterpret_cast<const float4*>(s_scale + s * SLAB + q * 8 + 4);
+          const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + s * SLAB + q * 8);
+          const float4 sh1 = *reinterpret_cast<const float4*>(s_shift + s * SLAB + q * 8 + 4);
+          float f[8];
+          f[0] = fmaf(__uint_as_float(v[q * 8 + 0]), sc0.x, sh0.x); f[1] = fmaf(__uint_as_float(v[q * 8 + 1]), sc0.y, sh0.y);
+          f[2] = fmaf(__uint_as_float(v[q * 8 + 2]), sc0.z, sh0.z); f[3] = fmaf(__uint_as_float(v[q * 8 + 3]), sc0.w, sh0.w);
+          f[4] = fmaf(__uint_as_float(v[q * 8 + 4]), sc1.x, sh1.x); f[5] = fmaf(__uint_as_float(v[q * 8 + 5]), sc1.y, sh1.y);
+          f[6] = fmaf(__uint_as_float(v[q * 8 + 6]), sc1.z, sh1.z); f[7] = fmaf(__uint_as_float(v[q * 8 + 7]), sc1.w, sh1.w);
+          if (HAS_RES) {
+            uint4 r = lds128(rrow + coff);
+            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 rf = __bfloat1622float2(rb[j]);
+              f[2 * j] += rf.x; f[2 * j + 1] += rf.y;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          uint4 o;
+          __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+          sts128(orow + coff, o);
+        }
+        if (HAS_RES) {                        // this warp is done with the residual slab
+          __syncwarp();
+          if (lane == 0) mbar_arrive(rempty_bar(slot));
+          if (++slot == RS) { slot = 0; rphase ^= 1u; }
+        }
+        fence_proxy_async_smem();             // generic-proxy smem writes -> visible to the TMA unit
+        epi_barrier();
+        if (issuer) {
+          tma_store_2d(&tmY, sOut + obuf * SLAB_BYTES, n0 + s * SLAB, m0);
+          bulk_commit();
+        }
+        obuf ^= 1;
+      }
+    }
+    if (issuer) bulk_wait_all();              // all output bytes are in global memory
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<2 * BN>(tmem_base);
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -324,6 +592,49 @@ int make_b_map(const bf16* w, int K, int cout_pad, int bn, CUtensorMap* out) {
   return 0;
 }
 
+// [rows, cols] bf16 row-major (row stride ld elements), box = one 128 x 64 epilogue slab
+int make_rowmajor_map(const void* ptr, int64_t rows, int cols, int ld, CUtensorMap* out) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)SLAB, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VLTK_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for [%lld,%d] ld %d", (int)r, (long long)rows, cols, ld);
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int STAGES, bool HAS_RES>
+int launch2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& y, const CUtensorMap& r, TcParams2 tp,
+            int cout_pad, cudaStream_t st) {
+  using S = Smem2<BN, STAGES, HAS_RES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VLTK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STAGES, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_set = true;
+  }
+  tp.n_tiles = cout_pad / BN;
+  const int64_t tiles = ceil_div64(tp.M, BM) * tp.n_tiles;
+  VLTK_CHECK(tiles < (1ll << 31), "conv_tc: too many tiles");
+  tp.num_tiles = (int)tiles;
+  const int grid = (int)std::min<int64_t>(tiles, num_sms());  // persistent: one CTA per SM
+  conv_tc2_kernel<BN, STAGES, HAS_RES><<<grid, TC_THREADS, S::TOTAL, st>>>(a, b, y, r, tp);
+  VLTK_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int BN, int STAGES>
 int launch(const CUtensorMap& a, const CUtensorMap& b, const TcParams& tp, int cout_pad, cudaStream_t st) {
   using S = Smem<BN, STAGES>;
@@ -366,6 +677,38 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
     cache->maps[kb] = tb;
   } else tb = ib->second;
 
+  static const bool use_v1 = [] { const char* e = getenv("VLTK_TC_V1"); return e && e[0] == '1'; }();
+  if (!use_v1) {
+    VLTK_CHECK(p.Cout % 64 == 0 && cout_pad == p.Cout, "conv_tc: Cout=%d must be a multiple of 64", p.Cout);
+    CUtensorMap ty, tr;
+    TensorMapCache::Key ky(p.y, (int)M, p.Cout, p.ldy, 0, 0, 0, 0, 0, 0, 2);
+    auto iy = cache->maps.find(ky);
+    if (iy == cache->maps.end()) {
+      if (make_rowmajor_map(p.y, M, p.Cout, p.ldy, &ty)) return -1;
+      cache->maps[ky] = ty;
+    } else ty = iy->second;
+    tr = ty;
+    if (p.residual) {
+      TensorMapCache::Key kr(p.residual, (int)M, p.Cout, p.ldr, 0, 0, 0, 0, 0, 0, 3);
+      auto ir = cache->maps.find(kr);
+      if (ir == cache->maps.end()) {
+        if (make_rowmajor_map(p.residual, M, p.Cout, p.ldr, &tr)) return -1;
+        cache->maps[kr] = tr;
+      } else tr = ir->second;
+    }
+    TcParams2 t2;
+    t2.scale = p.scale; t2.shift = p.shift; t2.M = M; t2.Cout = p.Cout; t2.relu = p.relu;
+    t2.OH = p.OH; t2.OW = p.OW; t2.stride = p.stride; t2.pad = p.pad; t2.dil = p.dil; t2.KW = p.KW;
+    t2.taps = p.KH * p.KW; t2.cblocks = p.Cin / BK; t2.n_tiles = 0; t2.num_tiles = 0;
+    if (p.residual) {
+      if (bn == 256) return launch2<256, 3, true>(ta, tb, ty, tr, t2, cout_pad, st);
+      if (bn == 128) return launch2<128, 4, true>(ta, tb, ty, tr, t2, cout_pad, st);
+      return launch2<64, 4, true>(ta, tb, ty, tr, t2, cout_pad, st);
+    }
+    if (bn == 256) return launch2<256, 4, false>(ta, tb, ty, tr, t2, cout_pad, st);
+    if (bn == 128) return launch2<128, 4, false>(ta, tb, ty, tr, t2, cout_pad, st);
+    return launch2<64, 4, false>(ta, tb, ty, tr, t2, cout_pad, st);
+  }
   TcParams tp;
   tp.y = (bf16*)p.y; tp.residual = (const bf16*)p.residual; tp.scale = p.scale; tp.shift = p.shift;
   tp.M = M; tp.ldy = p.ldy; tp.ldr = p.ldr; tp.Cout = p.Cout; tp.relu = p.relu;
