@@ -24,7 +24,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from oracle import cases, frcnn_oracle as O, ref_loader  # noqa: E402
+from oracle import cases, frcnn_oracle as O, margins, ref_loader  # noqa: E402
 from vltk_b200 import synthetic  # noqa: E402
 from vltk_b200.config import FRCNNConfig  # noqa: E402
 
@@ -106,7 +106,14 @@ def run_reference(name: str):
         g["obj_logits"] = obj_logits.numpy()
         g["attr_logits"] = attr_logits.numpy()
         g["box_deltas_f16"] = box_deltas.numpy().astype(np.float16)
-    meta = {"case": name, "overrides": cases.CASES[name][0], "weight_seed": wseed,
+    # decision margins of this case (computed with the oracle port on the same inputs)
+    ost = {}
+    oout = O.forward(sd, cfg, images, sizes, scales, stages=ost)
+    mg = margins.margins(cfg, ost, oout)
+    assert margins.certified(mg), f"{name}: seeds are not margin-certified: {mg}"
+    g["rpn_topk_anchor_idx"] = torch.stack([d["topk_idx"] for d in ost["rpn_debug"]]).numpy().astype(np.int32)
+    meta = {"case": name, "overrides": cases.CASES[name][0], "weight_seed": wseed, "margins": mg,
+            "margin_thresholds": margins.THRESHOLDS,
             "images": cases.CASES[name][2], "torch": torch.__version__,
             "reference_seconds": round(dt, 2), "threads": torch.get_num_threads()}
     os.makedirs(GOLD, exist_ok=True)

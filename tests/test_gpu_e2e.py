@@ -14,7 +14,7 @@ import pytest
 import torch
 
 from oracle import cases
-from tests.util import load_golden, oracle_run, weights
+from tests.util import load_golden, match_proposals, oracle_run, weights
 
 pytestmark = pytest.mark.gpu
 
@@ -59,24 +59,28 @@ def test_fp32_matches_reference_golden(case):
     h4, w4 = cfg.res4_hw(images.shape[2], images.shape[3])
     res4 = torch.from_numpy(model.debug_read("res4")).view(n, h4, w4, -1).permute(0, 3, 1, 2)
     np.testing.assert_allclose(res4[:, ::16].numpy(), g["res4_sub"], rtol=1e-3, atol=1e-3)
-    # proposals: same count, same anchors in the same order
+    # proposals: same count, same boxes; order equal up to near-tied logits (tests/util.py)
     cnt = model.debug_read("proposal_count", np.int32)
     assert cnt.tolist() == g["n_props"].tolist()
     props = torch.from_numpy(model.debug_read("proposals")).view(n, -1, 4)
-    mine = torch.cat([props[i, : int(cnt[i])] for i in range(n)]).numpy()
-    np.testing.assert_allclose(mine, g["proposals"], rtol=0, atol=1e-2)
     plog = torch.from_numpy(model.debug_read("proposal_logits")).view(n, -1)
-    mine = torch.cat([plog[i, : int(cnt[i])] for i in range(n)]).numpy()
-    np.testing.assert_allclose(mine, g["proposal_logits"], rtol=1e-4, atol=1e-4)
-    # pooled res5 features of every proposal + per-ROI class decisions
     feats = torch.from_numpy(model.debug_read("feats")).view(n, -1, 2048)
-    mine = torch.cat([feats[i, : int(cnt[i])] for i in range(n)]).numpy()
-    np.testing.assert_allclose(mine[:, ::8], g["feats_sub"], rtol=1e-3, atol=1e-3)
     ldc = -(-(cfg.num_classes + 1) // 4) * 4  # logits rows are padded to a multiple of 4
     cl = torch.from_numpy(model.debug_read("cls_logits")).view(n, -1, ldc)[:, :, : cfg.num_classes + 1]
-    mine = torch.cat([cl[i, : int(cnt[i])] for i in range(n)])
-    assert np.array_equal(mine.argmax(-1).numpy(), g["obj_argmax_all"])
-    assert np.array_equal(mine[:, :-1].argmax(-1).numpy(), g["obj_fg_argmax_all"])
+    s0 = 0
+    for i in range(n):
+        c = int(cnt[i])
+        gs = slice(s0, s0 + c)
+        s0 += c
+        perm = match_proposals(props[i, :c].numpy(), plog[i, :c].numpy(), g["proposals"][gs], g["proposal_logits"][gs])
+        # pooled res5 features of every proposal + per-ROI class decisions
+        np.testing.assert_allclose(feats[i, :c].numpy()[perm][:, ::8], g["feats_sub"][gs], rtol=1e-3, atol=1e-3)
+        assert np.array_equal(cl[i, :c].argmax(-1).numpy()[perm], g["obj_argmax_all"][gs])
+        assert np.array_equal(cl[i, :c, :-1].argmax(-1).numpy()[perm], g["obj_fg_argmax_all"][gs])
+    # the pre-NMS top-k anchor SET (order inside it is the same near-tie story)
+    tk = model.debug_read("topk_anchor_idx", np.int32).reshape(n, -1)
+    for i in range(n):
+        assert set(tk[i].tolist()) == set(g["rpn_topk_anchor_idx"][i].tolist())
     # final detections
     assert out["preds_per_image"].tolist() == g["preds_per_image"].tolist()
     assert np.array_equal(cat(out["obj_ids"]), g["obj_ids"])
