@@ -49,15 +49,24 @@ class ClockSampler(threading.Thread):
         self.index, self.samples, self.stop_flag = index, [], False
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.samples.append([x.strip() for x in o.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        try:  # one long-lived nvidia-smi sampling every 50 ms (spawning one per sample takes ~150 ms each)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for ln in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                parts = [x.strip() for x in ln.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        p = getattr(self, "proc", None)
+        if p is not None:  # the exact child this object started
+            p.terminate()
 
     def summary(self):
         if not self.samples:
@@ -199,6 +208,7 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+        time.sleep(0.3)  # let the sampler attach before the timed region
     model.profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -212,7 +222,7 @@ def main():
     prof, csv = model.profile_read(want_csv=bool(args.profile_csv))
     model.profile(False)
     if sampler:
-        sampler.stop_flag = True
+        sampler.stop()
         sampler.join(timeout=3)
     if world > 1:
         tt = torch.tensor([ms], device=dev)
@@ -251,6 +261,13 @@ def main():
         d_ms, d_fl, d_n = prof[dom]
         achieved = d_fl / (d_ms / 1e3) / 1e12 if d_ms else 0.0
         peak = pk["bf16_tflops_sustained"] if "bf16_tflops_sustained" in pk else pk["bf16_tflops"]
+        traffic, traffic_note = None, None
+        ncu_json = os.path.join(ROOT, "profiles", "r01_conv_tc2_ncu.json")
+        if dom == "tcgen05" and os.path.exists(ncu_json):  # dram bytes/launch from the committed ncu --set full capture
+            nj = json.load(open(ncu_json))
+            traffic = nj["traffic_bytes_per_launch"]
+            traffic_note = (f"dram__bytes_read+write per launch, avg of {len(nj['launches'])} res5 launches in {os.path.basename(ncu_json)} "
+                            f"(algorithmic {nj['algorithmic_bytes_per_launch']:.4g} B)")
         line = {
             "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
             "warmup": W_, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -267,7 +284,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM)" if dom == "tcgen05" else "conv_simt_kernel",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         "traffic": None, "peak_source": pk_src + (", sustained bf16" if "bf16_tflops_sustained" in pk else ""),
+                         "traffic": traffic, "traffic_source": traffic_note, "peak_source": pk_src + (", sustained bf16" if "bf16_tflops_sustained" in pk else ""),
                          "launches_per_step": d_n / args.steps, "ms_per_step": d_ms / args.steps,
                          "flops_per_step": d_fl / args.steps,
                          "share_of_step": (d_ms / args.steps) / (ms / args.steps),
