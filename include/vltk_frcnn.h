@@ -125,6 +125,12 @@ int vltk_conv2d_nhwc(const void* x, const float* weight, const float* scale, con
                      int kh, int kw, int stride, int pad, int dil, int relu, int mode,
                      int use_tensor_cores, void* stream);
 
+/* nn.Linear on the tensor pipe with fp32-faithful arithmetic (frcnn.py:1729-1737 in bf16 mode):
+ * y[m,n] = act(x[m,k] . weight[n,k]^T + bias), all DEVICE f32; operands are split into bf16
+ * hi+lo planes and accumulated as hi*hi + lo*hi + hi*lo in one fp32 TMEM tile.  k,n % 64 == 0. */
+int vltk_linear_tc3(const float* x, const float* weight, const float* bias, float* y, int m, int k,
+                    int n, int relu, void* stream);
+
 /* find_top_rpn_proposals + RPN.inference — frcnn.py:264-390, 1615-1638 — on the RPN head's
  * NCHW outputs (DEVICE): logits [N,A,H4,W4], deltas [N,4A,H4,W4]; cell anchors [A,4] (HOST).
  * Outputs (DEVICE): proposals [N,post,4], proposal_logits [N,post], counts [N]. */

@@ -83,6 +83,28 @@ def test_conv_tcgen05_matches_simt_and_reference(dev, case):
     assert ((y_tc - ref).abs() <= ulp * (ref.abs() + 1e-2)).all()
 
 
+@pytest.mark.parametrize("m,k,n", [(300, 2048, 1664), (37, 512, 448), (2400, 2048, 6400)])
+def test_split_bf16_tensor_core_linear_is_fp32_faithful(dev, m, k, n):
+    """The predictor linears in bf16 mode: operands split into bf16 hi+lo, hi*hi + lo*hi + hi*lo
+    accumulated in fp32 on tcgen05, fp32 logits out.  Each operand keeps ~16 mantissa bits, so the
+    result must sit within 2^-16 * sum|x||w| of an fp64 product — ~100x tighter than single-pass
+    bf16 (2^-9) and close to fp32's own summation error."""
+    from vltk_b200 import stages
+    g = torch.Generator().manual_seed(m + k + n)
+    x = (torch.randn(m, k, generator=g).abs() * 2.0).to(dev)        # post-ReLU-mean-like features
+    w = (torch.randn(n, k, generator=g) * 0.04).to(dev)
+    b = (torch.randn(n, generator=g) * 0.1).to(dev)
+    y = stages.linear_tc3(x, w, b).cpu().double()
+    ref = x.cpu().double() @ w.cpu().double().T + b.cpu().double()
+    mag = x.cpu().double().abs() @ w.cpu().double().abs().T
+    err = (y - ref).abs()
+    assert (err <= 2.0 ** -16 * mag + 1e-6).all(), float((err / mag).max())
+    fp32 = (F.linear(x.cpu(), w.cpu(), b.cpu()).double() - ref).abs().max().item()
+    print(f"[linear_tc3 {m}x{k}x{n}] max err {err.max().item():.2e} (fp32 CPU linear: {fp32:.2e}; "
+          f"single-pass bf16 would be ~{(2.0 ** -9 * mag).mean().item():.1e})")
+    assert torch.equal(stages.linear_tc3(x, w, b, relu=True).cpu(), torch.relu(stages.linear_tc3(x, w, b)).cpu())
+
+
 def test_preprocess_matches_oracle(dev):
     from vltk_b200.preprocess import Preprocess
     for name in ("mixed", "tiny"):

@@ -319,6 +319,10 @@ struct TcParams2 {
   int Cout, relu;
   int OH, OW, stride, pad, dil, KW, taps, cblocks;
   int n_tiles, num_tiles;                      // cout tiles, total tiles
+  // split-precision GEMM: the K loop runs `npass` times; pass i reads A from map pass_a[i] (0: tmA,
+  // 1: tmA2) and W from map pass_b[i] (0: tmB, 1: tmB2), all accumulating into the same TMEM tile.
+  // npass = 1 is the plain bf16 product; {hi*hi, lo*hi, hi*lo} gives an fp32-faithful product.
+  int npass, pass_a[3], pass_b[3];
 };
 
 template <int BN, int STAGES, bool HAS_RES>
@@ -335,12 +339,15 @@ struct Smem2 {
   static_assert(TOTAL <= 232448, "exceeds the 227 KB shared memory of one sm_100 CTA");
 };
 
-template <int BN, int STAGES, bool HAS_RES>
+template <int BN, int STAGES, bool HAS_RES, bool OUT_F32>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2,
                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, TcParams2 p) {
   using S = Smem2<BN, STAGES, HAS_RES>;
-  constexpr int NSLAB = BN / SLAB;
+  static_assert(!(HAS_RES && OUT_F32), "fp32 output has no residual path");
+  constexpr int SLABC = OUT_F32 ? 32 : SLAB;   // columns per 128 B staging row (fp32: 32, bf16: 64)
+  constexpr int NSLAB = BN / SLABC;
   // no static smem in this kernel: the dynamic window starts at the CTA's (1024 B aligned) base
   extern __shared__ __align__(1024) unsigned char smem_dyn2[];
   const uint32_t base = smem_u32(smem_dyn2);
@@ -363,10 +370,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_slot = bars + S::NUM_BARS * 8;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = p.taps * p.cblocks;
+  const int num_kb = p.npass * p.taps * p.cblocks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY);
+    if (p.npass > 1) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
     if (HAS_RES) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
@@ -391,15 +399,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int64_t q = m0 / p.OW;
       const int oh0 = (int)(q % p.OH), img0 = (int)(q / p.OH);
       const int bw = ow0 * p.stride - p.pad, bh = oh0 * p.stride - p.pad;
-      for (int tap = 0; tap < p.taps; ++tap) {
-        const int kh = tap / p.KW, kw = tap - kh * p.KW;
-        for (int cb = 0; cb < p.cblocks; ++cb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), S::STAGE_BYTES);
-          tma_load_im2col_4d(sA + stage * A_STAGE_BYTES, &tmA, full_bar(stage), cb * BK, bw, bh, img0,
-                             (uint16_t)(kw * p.dil), (uint16_t)(kh * p.dil));
-          tma_load_2d(sB + stage * S::B_STAGE_BYTES, &tmB, full_bar(stage), (tap * p.cblocks + cb) * BK, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      for (int ps = 0; ps < p.npass; ++ps) {
+        const CUtensorMap* ma = p.pass_a[ps] ? &tmA2 : &tmA;
+        const CUtensorMap* mb = p.pass_b[ps] ? &tmB2 : &tmB;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int kh = tap / p.KW, kw = tap - kh * p.KW;
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), S::STAGE_BYTES);
+            tma_load_im2col_4d(sA + stage * A_STAGE_BYTES, ma, full_bar(stage), cb * BK, bw, bh, img0,
+                               (uint16_t)(kw * p.dil), (uint16_t)(kh * p.dil));
+            tma_load_2d(sB + stage * S::B_STAGE_BYTES, mb, full_bar(stage), (tap * p.cblocks + cb) * BK, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
         }
       }
     }
@@ -464,11 +476,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t tacc = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int s = 0; s < NSLAB; ++s) {
-        uint32_t v[64];
-        {
+        uint32_t v[SLABC];
+        if constexpr (OUT_F32) {
+          tmem_ld32(tacc + (uint32_t)(s * SLABC), v);
+          tmem_ld_wait();
+        } else {
           uint32_t lo[32], hi[32];
-          tmem_ld32(tacc + (uint32_t)(s * SLAB), lo);
-          tmem_ld32(tacc + (uint32_t)(s * SLAB + 32), hi);
+          tmem_ld32(tacc + (uint32_t)(s * SLABC), lo);
+          tmem_ld32(tacc + (uint32_t)(s * SLABC + 32), hi);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) { v[j] = lo[j]; v[32 + j] = hi[j]; }
@@ -483,36 +498,49 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         epi_barrier();                        // sOut[obuf] reusable; s_scale/s_shift visible
         const uint32_t orow = sOut + obuf * SLAB_BYTES + (uint32_t)row * 128u;
         const uint32_t rrow = sRes + slot * SLAB_BYTES + (uint32_t)row * 128u;
+        if constexpr (OUT_F32) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {         // 8 channels = one 16 B chunk, stored at chunk q ^ (row % 8)
-          const uint32_t coff = ((uint32_t)q ^ swz) << 4;
-          const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + s * SLAB + q * 8);
-          const float4 sc1 = *reinterpret_cast<const float4*>(s_scale + s * SLAB + q * 8 + 4);
-          const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + s * SLAB + q * 8);
-          const float4 sh1 = *reinterpret_cast<const float4*>(s_shift + s * SLAB + q * 8 + 4);
-          float f[8];
-          f[0] = fmaf(__uint_as_float(v[q * 8 + 0]), sc0.x, sh0.x); f[1] = fmaf(__uint_as_float(v[q * 8 + 1]), sc0.y, sh0.y);
-          f[2] = fmaf(__uint_as_float(v[q * 8 + 2]), sc0.z, sh0.z); f[3] = fmaf(__uint_as_float(v[q * 8 + 3]), sc0.w, sh0.w);
-          f[4] = fmaf(__uint_as_float(v[q * 8 + 4]), sc1.x, sh1.x); f[5] = fmaf(__uint_as_float(v[q * 8 + 5]), sc1.y, sh1.y);
-          f[6] = fmaf(__uint_as_float(v[q * 8 + 6]), sc1.z, sh1.z); f[7] = fmaf(__uint_as_float(v[q * 8 + 7]), sc1.w, sh1.w);
-          if (HAS_RES) {
-            uint4 r = lds128(rrow + coff);
-            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&r);
+          for (int q = 0; q < 8; ++q) {       // 4 fp32 channels = one 16 B chunk
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + s * SLABC + q * 4);
+            const float4 sh = *reinterpret_cast<const float4*>(s_shift + s * SLABC + q * 4);
+            float f0 = fmaf(__uint_as_float(v[q * 4 + 0]), sc.x, sh.x), f1 = fmaf(__uint_as_float(v[q * 4 + 1]), sc.y, sh.y);
+            float f2 = fmaf(__uint_as_float(v[q * 4 + 2]), sc.z, sh.z), f3 = fmaf(__uint_as_float(v[q * 4 + 3]), sc.w, sh.w);
+            if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
+            sts128(orow + (((uint32_t)q ^ swz) << 4),
+                   make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3)));
+          }
+        } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float2 rf = __bfloat1622float2(rb[j]);
-              f[2 * j] += rf.x; f[2 * j + 1] += rf.y;
+          for (int q = 0; q < 8; ++q) {       // 8 bf16 channels = one 16 B chunk, stored at chunk q ^ (row % 8)
+            const uint32_t coff = ((uint32_t)q ^ swz) << 4;
+            const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + s * SLABC + q * 8);
+            const float4 sc1 = *reinterpret_cast<const float4*>(s_scale + s * SLABC + q * 8 + 4);
+            const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + s * SLABC + q * 8);
+            const float4 sh1 = *reinterpret_cast<const float4*>(s_shift + s * SLABC + q * 8 + 4);
+            float f[8];
+            f[0] = fmaf(__uint_as_float(v[q * 8 + 0]), sc0.x, sh0.x); f[1] = fmaf(__uint_as_float(v[q * 8 + 1]), sc0.y, sh0.y);
+            f[2] = fmaf(__uint_as_float(v[q * 8 + 2]), sc0.z, sh0.z); f[3] = fmaf(__uint_as_float(v[q * 8 + 3]), sc0.w, sh0.w);
+            f[4] = fmaf(__uint_as_float(v[q * 8 + 4]), sc1.x, sh1.x); f[5] = fmaf(__uint_as_float(v[q * 8 + 5]), sc1.y, sh1.y);
+            f[6] = fmaf(__uint_as_float(v[q * 8 + 6]), sc1.z, sh1.z); f[7] = fmaf(__uint_as_float(v[q * 8 + 7]), sc1.w, sh1.w);
+            if (HAS_RES) {
+              uint4 r = lds128(rrow + coff);
+              const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 rf = __bfloat1622float2(rb[j]);
+                f[2 * j] += rf.x; f[2 * j + 1] += rf.y;
+              }
             }
-          }
-          if (p.relu) {
+            if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          uint4 o;
-          __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            uint4 o;
+            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-          sts128(orow + coff, o);
+            for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            sts128(orow + coff, o);
+          }
         }
         if (HAS_RES) {                        // this warp is done with the residual slab
           __syncwarp();
@@ -522,7 +550,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         fence_proxy_async_smem();             // generic-proxy smem writes -> visible to the TMA unit
         epi_barrier();
         if (issuer) {
-          tma_store_2d(&tmY, sOut + obuf * SLAB_BYTES, n0 + s * SLAB, m0);
+          tma_store_2d(&tmY, sOut + obuf * SLAB_BYTES, n0 + s * SLABC, m0);
           bulk_commit();
         }
         obuf ^= 1;
@@ -593,12 +621,13 @@ int make_b_map(const bf16* w, int K, int cout_pad, int bn, CUtensorMap* out) {
 }
 
 // [rows, cols] bf16 row-major (row stride ld elements), box = one 128 x 64 epilogue slab
-int make_rowmajor_map(const void* ptr, int64_t rows, int cols, int ld, CUtensorMap* out) {
+int make_rowmajor_map(const void* ptr, int64_t rows, int cols, int ld, bool f32, CUtensorMap* out) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)SLAB, (cuuint32_t)BM};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {(cuuint32_t)(f32 ? 32 : SLAB), (cuuint32_t)BM};   // 128 B rows either way
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = g_encode_tiled(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                              const_cast<void*>(ptr), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VLTK_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for [%lld,%d] ld %d", (int)r, (long long)rows, cols, ld);
@@ -616,13 +645,14 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES, bool HAS_RES>
-int launch2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& y, const CUtensorMap& r, TcParams2 tp,
-            int cout_pad, cudaStream_t st) {
+struct Maps { CUtensorMap a, a2, b, b2, y, r; };
+
+template <int BN, int STAGES, bool HAS_RES, bool OUT_F32>
+int launch2(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
   using S = Smem2<BN, STAGES, HAS_RES>;
   static bool attr_set = false;
   if (!attr_set) {
-    VLTK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STAGES, HAS_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    VLTK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STAGES, HAS_RES, OUT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
   tp.n_tiles = cout_pad / BN;
@@ -630,7 +660,7 @@ int launch2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& y, co
   VLTK_CHECK(tiles < (1ll << 31), "conv_tc: too many tiles");
   tp.num_tiles = (int)tiles;
   const int grid = (int)std::min<int64_t>(tiles, num_sms());  // persistent: one CTA per SM
-  conv_tc2_kernel<BN, STAGES, HAS_RES><<<grid, TC_THREADS, S::TOTAL, st>>>(a, b, y, r, tp);
+  conv_tc2_kernel<BN, STAGES, HAS_RES, OUT_F32><<<grid, TC_THREADS, S::TOTAL, st>>>(m.a, m.a2, m.b, m.b2, m.y, m.r, tp);
   VLTK_LAUNCH_CHECK();
   return 0;
 }
@@ -651,11 +681,15 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const TcParams& tp, int c
 
 }  // namespace
 
-int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorMapCache* cache, cudaStream_t st) {
-  VLTK_CHECK(p.in_dtype == DT_BF16 && p.out_dtype == DT_BF16, "conv_tc: bf16 activations only");
+int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorMapCache* cache, cudaStream_t st,
+                   const TcSplit* split) {
+  const bool out_f32 = p.out_dtype == DT_F32;
+  const bool is_split = split && split->x_lo && split->w_lo;
+  VLTK_CHECK(p.in_dtype == DT_BF16, "conv_tc: bf16 operands only");
+  VLTK_CHECK(!(out_f32 && p.residual), "conv_tc: fp32 output has no residual path");
   VLTK_CHECK(p.Cin % BK == 0, "conv_tc: Cin=%d must be a multiple of %d", p.Cin, BK);
   VLTK_CHECK(cout_pad % 64 == 0 && p.Cout <= cout_pad, "conv_tc: bad cout_pad");
-  VLTK_CHECK(p.ldy % 8 == 0 && p.ldx % 8 == 0 && (!p.residual || p.ldr % 8 == 0), "conv_tc: rows must be 16-byte aligned");
+  VLTK_CHECK(p.ldy % (out_f32 ? 4 : 8) == 0 && p.ldx % 8 == 0 && (!p.residual || p.ldr % 8 == 0), "conv_tc: rows must be 16-byte aligned");
   VLTK_CHECK(p.Cout % 32 == 0, "conv_tc: Cout=%d must be a multiple of 32", p.Cout);
   if (load_driver_entry_points()) return -1;
   const int64_t M = (int64_t)p.N * p.OH * p.OW;
@@ -678,36 +712,52 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
   } else tb = ib->second;
 
   static const bool use_v1 = [] { const char* e = getenv("VLTK_TC_V1"); return e && e[0] == '1'; }();
-  if (!use_v1) {
+  if (!use_v1 || out_f32 || is_split) {
     VLTK_CHECK(p.Cout % 64 == 0 && cout_pad == p.Cout, "conv_tc: Cout=%d must be a multiple of 64", p.Cout);
-    CUtensorMap ty, tr;
-    TensorMapCache::Key ky(p.y, (int)M, p.Cout, p.ldy, 0, 0, 0, 0, 0, 0, 2);
-    auto iy = cache->maps.find(ky);
-    if (iy == cache->maps.end()) {
-      if (make_rowmajor_map(p.y, M, p.Cout, p.ldy, &ty)) return -1;
-      cache->maps[ky] = ty;
-    } else ty = iy->second;
-    tr = ty;
-    if (p.residual) {
-      TensorMapCache::Key kr(p.residual, (int)M, p.Cout, p.ldr, 0, 0, 0, 0, 0, 0, 3);
-      auto ir = cache->maps.find(kr);
-      if (ir == cache->maps.end()) {
-        if (make_rowmajor_map(p.residual, M, p.Cout, p.ldr, &tr)) return -1;
-        cache->maps[kr] = tr;
-      } else tr = ir->second;
+    Maps m;
+    m.a = ta; m.b = tb; m.a2 = ta; m.b2 = tb;
+    auto cached = [&](const TensorMapCache::Key& k, CUtensorMap* dst, auto make) -> int {
+      auto it = cache->maps.find(k);
+      if (it == cache->maps.end()) {
+        if (make(dst)) return -1;
+        cache->maps[k] = *dst;
+      } else *dst = it->second;
+      return 0;
+    };
+    if (cached(TensorMapCache::Key(p.y, (int)M, p.Cout, p.ldy, out_f32 ? 1 : 0, 0, 0, 0, 0, 0, 2), &m.y,
+               [&](CUtensorMap* d) { return make_rowmajor_map(p.y, M, p.Cout, p.ldy, out_f32, d); })) return -1;
+    m.r = m.y;
+    if (p.residual &&
+        cached(TensorMapCache::Key(p.residual, (int)M, p.Cout, p.ldr, 0, 0, 0, 0, 0, 0, 3), &m.r,
+               [&](CUtensorMap* d) { return make_rowmajor_map(p.residual, M, p.Cout, p.ldr, false, d); })) return -1;
+    if (is_split) {
+      ConvProblem plo = p;
+      plo.x = split->x_lo;
+      if (cached(TensorMapCache::Key(plo.x, p.N, p.H, p.W, p.Cin, p.ldx, p.KH, p.stride, p.pad, p.dil, 0), &m.a2,
+                 [&](CUtensorMap* d) { return make_a_map(plo, d); })) return -1;
+      if (cached(TensorMapCache::Key(split->w_lo, K, cout_pad, bn, 0, 0, 0, 0, 0, 0, 1), &m.b2,
+                 [&](CUtensorMap* d) { return make_b_map(split->w_lo, K, cout_pad, bn, d); })) return -1;
     }
     TcParams2 t2;
     t2.scale = p.scale; t2.shift = p.shift; t2.M = M; t2.Cout = p.Cout; t2.relu = p.relu;
     t2.OH = p.OH; t2.OW = p.OW; t2.stride = p.stride; t2.pad = p.pad; t2.dil = p.dil; t2.KW = p.KW;
     t2.taps = p.KH * p.KW; t2.cblocks = p.Cin / BK; t2.n_tiles = 0; t2.num_tiles = 0;
-    if (p.residual) {
-      if (bn == 256) return launch2<256, 3, true>(ta, tb, ty, tr, t2, cout_pad, st);
-      if (bn == 128) return launch2<128, 4, true>(ta, tb, ty, tr, t2, cout_pad, st);
-      return launch2<64, 4, true>(ta, tb, ty, tr, t2, cout_pad, st);
+    t2.npass = is_split ? 3 : 1;                       // hi*hi, lo*hi, hi*lo
+    t2.pass_a[0] = 0; t2.pass_a[1] = 1; t2.pass_a[2] = 0;
+    t2.pass_b[0] = 0; t2.pass_b[1] = 0; t2.pass_b[2] = 1;
+    if (out_f32) {
+      if (bn == 256) return launch2<256, 4, false, true>(m, t2, cout_pad, st);
+      if (bn == 128) return launch2<128, 4, false, true>(m, t2, cout_pad, st);
+      return launch2<64, 4, false, true>(m, t2, cout_pad, st);
     }
-    if (bn == 256) return launch2<256, 4, false>(ta, tb, ty, tr, t2, cout_pad, st);
-    if (bn == 128) return launch2<128, 4, false>(ta, tb, ty, tr, t2, cout_pad, st);
-    return launch2<64, 4, false>(ta, tb, ty, tr, t2, cout_pad, st);
+    if (p.residual) {
+      if (bn == 256) return launch2<256, 3, true, false>(m, t2, cout_pad, st);
+      if (bn == 128) return launch2<128, 4, true, false>(m, t2, cout_pad, st);
+      return launch2<64, 4, true, false>(m, t2, cout_pad, st);
+    }
+    if (bn == 256) return launch2<256, 4, false, false>(m, t2, cout_pad, st);
+    if (bn == 128) return launch2<128, 4, false, false>(m, t2, cout_pad, st);
+    return launch2<64, 4, false, false>(m, t2, cout_pad, st);
   }
   TcParams tp;
   tp.y = (bf16*)p.y; tp.residual = (const bf16*)p.residual; tp.scale = p.scale; tp.shift = p.shift;

@@ -19,13 +19,22 @@ struct TensorMapCache {
 // y = act((x (*) w) * scale + shift + residual) on the tensor pipe.
 //   x, y, residual: bf16 NHWC;  w_nk: bf16 [cout_pad][KH*KW*Cin] (cin fastest), cout_pad % 64 == 0
 //   requires Cin % 64 == 0; scale/shift must hold cout_pad entries.
+// Optional split-precision operands: x = x_hi + x_lo, w = w_hi + w_lo (bf16 pairs).  When given, the
+// kernel accumulates x_hi*w_hi + x_lo*w_hi + x_hi*w_lo in one TMEM tile (fp32-faithful, ~2^-17 rel).
+struct TcSplit {
+  const void* x_lo = nullptr;   // same geometry as p.x
+  const bf16* w_lo = nullptr;   // same geometry as w_nk
+};
+// out_dtype may be DT_F32 (no residual) or DT_BF16.
 int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorMapCache* cache,
-                   cudaStream_t st);
+                   cudaStream_t st, const TcSplit* split = nullptr);
 
 // ---- pack.cu: reference-layout weights [cout][cin][taps] (DEVICE f32) -> kernel layouts
 int pack_weight_kn(const float* w, float* w_kn, int cout, int cin, int taps, int ldw, bool round_bf16,
                    cudaStream_t st);
 int pack_weight_nk(const float* w, bf16* w_nk, int cout, int cin, int taps, cudaStream_t st);
 int pad_vector(const float* src, float* dst, int n, int n_pad, float fill, cudaStream_t st);
+// hi = bf16(v), lo = bf16(v - hi) with v = relu?(x + add?) elementwise (add may be nullptr)
+int split_f32(const float* x, const float* add, int relu, bf16* hi, bf16* lo, int64_t n, cudaStream_t st);
 
 }  // namespace vltk

@@ -33,6 +33,7 @@ struct LayerW {           // one conv / linear layer, packed for the kernels
   int ldw = 0;            // round_up(cout, 4)
   float* w_kn = nullptr;  // SIMT: f32 [K_pad][ldw]
   bf16* w_nk = nullptr;   // tcgen05: bf16 [cout_pad][K]  (bf16 mode, Cin % 64 == 0 only)
+  bf16* w_lo = nullptr;   // split-precision layers: w = w_nk (hi) + w_lo
   int cout_pad = 0;
   float* scale = nullptr; // [ldw] or nullptr
   float* shift = nullptr; // [ldw]
@@ -146,6 +147,28 @@ int pack_layer(vltk_frcnn* h, LayerW& L, const std::string& name, int cin, int c
     for (int o = 0; o < cout; ++o) sh[o] = (*b)[o];
   }
   if (bn || bias) { if (upload(h, sh, &L.shift)) return -1; }
+  return 0;
+}
+
+// Predictor linears on the tensor pipe keep fp32-faithful logits: W[out][:k_used] is split into
+// bf16 hi + lo planes [cout_pad][k_used] (rows past `cout` are zero), bias padded to cout_pad.
+int pack_split_linear(vltk_frcnn* h, LayerW& L, const std::vector<float>& w, int cout, int k_full, int k_used,
+                      const std::vector<float>& bias) {
+  L.cout_pad = round_up(cout, 64);
+  std::vector<bf16> hi((size_t)L.cout_pad * k_used, __float2bfloat16_rn(0.f)), lo(hi);
+  for (int o = 0; o < cout; ++o)
+    for (int k = 0; k < k_used; ++k) {
+      float v = w[(size_t)o * k_full + k];
+      bf16 b = __float2bfloat16_rn(v);
+      hi[(size_t)o * k_used + k] = b;
+      lo[(size_t)o * k_used + k] = __float2bfloat16_rn(v - __bfloat162float(b));
+    }
+  if (dev_alloc(h, (void**)&L.w_nk, hi.size() * 2) || dev_alloc(h, (void**)&L.w_lo, lo.size() * 2)) return -1;
+  VLTK_CUDA(cudaMemcpy(L.w_nk, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
+  VLTK_CUDA(cudaMemcpy(L.w_lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+  std::vector<float> sh(L.cout_pad, 0.f);
+  for (int o = 0; o < cout; ++o) sh[o] = bias[o];
+  if (upload(h, sh, &L.shift)) return -1;   // replaces the SIMT-sized copy; both hold the same bias
   return 0;
 }
 
@@ -406,6 +429,19 @@ int vltk_frcnn_finalize(vltk_frcnn_t* h) {
         tab[(size_t)cidx * HA + o] = (float)s;
       }
     if (upload(h, kn, &L.w_kn) || upload(h, sh, &L.shift) || upload(h, tab, &h->attr_table)) return -1;
+    if (tc && pack_split_linear(h, L, *w, HA, D + E, D, *b)) return -1;
+  }
+  if (tc) {
+    const auto* wc = find(h, "roi_heads.box_predictor.cls_score.weight", (int64_t)(NC + 1) * D);
+    const auto* bc = find(h, "roi_heads.box_predictor.cls_score.bias", NC + 1);
+    const auto* wb = find(h, "roi_heads.box_predictor.bbox_pred.weight", (int64_t)NC * 4 * D);
+    const auto* bb = find(h, "roi_heads.box_predictor.bbox_pred.bias", NC * 4);
+    const auto* wa = find(h, "roi_heads.box_predictor.attr_score.weight", (int64_t)(NA + 1) * HA);
+    const auto* ba = find(h, "roi_heads.box_predictor.attr_score.bias", NA + 1);
+    if (!wc || !bc || !wb || !bb || !wa || !ba) return -2;
+    if (pack_split_linear(h, h->cls_score, *wc, NC + 1, D, D, *bc)) return -1;
+    if (pack_split_linear(h, h->bbox_pred, *wb, NC * 4, D, D, *bb)) return -1;
+    if (pack_split_linear(h, h->attr_score, *wa, NA + 1, HA, HA, *ba)) return -1;
   }
   h->host.clear();
   h->finalized = true;
@@ -417,7 +453,7 @@ static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void*
 enum {
   B_IN4, B_STEM, B_POOL, B_A, B_B, B_T1, B_T2, B_S, B_RPNH, B_HEAD, B_SIZES, B_SCALES, B_SBOX, B_SSCORE,
   B_SIDX, B_SVALID, B_MASK, B_PROP, B_PSCORE, B_PIDX, B_COUNT, B_POOLED, B_R5A, B_R5B, B_R5T1, B_R5T2,
-  B_R5S, B_FEATS, B_CLS, B_BBOX, B_ARGMAX, B_TG, B_AH, B_ATTR, B_NUM
+  B_R5S, B_FEATS, B_CLS, B_BBOX, B_ARGMAX, B_TG, B_AH, B_ATTR, B_FHI, B_FLO, B_AHHI, B_AHLO, B_NUM
 };
 
 static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void** p) {
@@ -447,11 +483,14 @@ static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void*
   p[B_R5S] = b.take((size_t)NR * PP * D * e);
   p[B_R5T1] = b.take((size_t)NR * PP * (D / 4) * e); p[B_R5T2] = b.take((size_t)NR * PP * (D / 4) * e);
   p[B_FEATS] = b.take((size_t)NR * D * 4);
-  p[B_CLS] = b.take((size_t)NR * h->cls_score.ldw * 4);
-  p[B_BBOX] = b.take((size_t)NR * h->bbox_pred.ldw * 4);
+  auto ld = [](const LayerW& L) { return (size_t)std::max(L.ldw, L.cout_pad); };  // split layers pad to 64
+  p[B_CLS] = b.take((size_t)NR * ld(h->cls_score) * 4);
+  p[B_BBOX] = b.take((size_t)NR * ld(h->bbox_pred) * 4);
   p[B_ARGMAX] = b.take((size_t)NR * 4);
   p[B_TG] = b.take((size_t)NR * (D / 4) * 4); p[B_AH] = b.take((size_t)NR * (D / 4) * 4);
-  p[B_ATTR] = b.take((size_t)NR * h->attr_score.ldw * 4);
+  p[B_ATTR] = b.take((size_t)NR * ld(h->attr_score) * 4);
+  p[B_FHI] = b.take((size_t)NR * D * 2); p[B_FLO] = b.take((size_t)NR * D * 2);
+  p[B_AHHI] = b.take((size_t)NR * (D / 4) * 2); p[B_AHLO] = b.take((size_t)NR * (D / 4) * 2);
   return b.off + 256;
 }
 
@@ -549,24 +588,59 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   h->launches++;
   tap(h, "feats", p[B_FEATS], (int64_t)NR * D, DT_F32);
 
-  // ---- predictor (frcnn.py:1726-1740), fp32
-  if (run_conv(h, h->cls_score, p[B_FEATS], DT_F32, NR, 1, 1, p[B_CLS], DT_F32, h->cls_score.ldw, nullptr, 0, 0, st)) return -1;
-  if (run_conv(h, h->bbox_pred, p[B_FEATS], DT_F32, NR, 1, 1, p[B_BBOX], DT_F32, h->bbox_pred.ldw, nullptr, 0, 0, st)) return -1;
-  if (row_argmax((const float*)p[B_CLS], h->cls_score.ldw, NR, c.num_classes + 1, (int*)p[B_ARGMAX], st)) return -1;
-  if (gather_rows(h->attr_table, D / 4, (const int*)p[B_ARGMAX], NR, D / 4, (float*)p[B_TG], D / 4, st)) return -1;
-  if (run_conv(h, h->fc_attr, p[B_FEATS], DT_F32, NR, 1, 1, p[B_AH], DT_F32, D / 4, p[B_TG], D / 4, 1, st)) return -1;
-  if (run_conv(h, h->attr_score, p[B_AH], DT_F32, NR, 1, 1, p[B_ATTR], DT_F32, h->attr_score.ldw, nullptr, 0, 0, st)) return -1;
-  h->launches += 2;
-  tap(h, "cls_logits", p[B_CLS], (int64_t)NR * h->cls_score.ldw, DT_F32);
-  tap(h, "bbox_deltas", p[B_BBOX], (int64_t)NR * h->bbox_pred.ldw, DT_F32);
-  tap(h, "attr_logits", p[B_ATTR], (int64_t)NR * h->attr_score.ldw, DT_F32);
+  // ---- predictor (frcnn.py:1726-1740): fp32 on the CUDA cores, or fp32-faithful split-bf16 (hi*hi +
+  //      lo*hi + hi*lo, fp32 accumulate and fp32 logits) on the tensor pipe
+  const bool ptc = h->use_tc && h->cls_score.w_lo;
+  const int ldc = ptc ? h->cls_score.cout_pad : h->cls_score.ldw;
+  const int ldb = ptc ? h->bbox_pred.cout_pad : h->bbox_pred.ldw;
+  const int lda = ptc ? h->attr_score.cout_pad : h->attr_score.ldw;
+  if (ptc) {
+    auto split_gemm = [&](const LayerW& L, const void* xhi, const void* xlo, int K, void* y, int relu) -> int {
+      ConvProblem q;
+      memset(&q, 0, sizeof(q));
+      q.x = xhi; q.ldx = K; q.y = y; q.ldy = L.cout_pad; q.N = NR; q.H = q.W = q.OH = q.OW = 1; q.Cin = K;
+      q.Cout = L.cout_pad; q.KH = q.KW = 1; q.stride = 1; q.dil = 1; q.shift = L.shift; q.relu = relu;
+      q.in_dtype = DT_BF16; q.out_dtype = DT_F32;
+      TcSplit sp; sp.x_lo = xlo; sp.w_lo = L.w_lo;
+      h->launches++;
+      vltk_frcnn::ProfRec rec;
+      if (h->profiling) {
+        rec.kind = 0; rec.M = NR; rec.K = K; rec.Cout = L.cout; rec.flops = 2.0 * NR * (double)K * L.cout;  // algorithmic (1 pass)
+        cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1); cudaEventRecord(rec.e0, st);
+      }
+      int rc = conv_tc_launch(q, L.w_nk, L.cout_pad, &h->tmaps, st, &sp);
+      if (h->profiling) { cudaEventRecord(rec.e1, st); h->prof.push_back(rec); }
+      return rc;
+    };
+    if (split_f32((const float*)p[B_FEATS], nullptr, 0, (bf16*)p[B_FHI], (bf16*)p[B_FLO], (int64_t)NR * D, st)) return -1;
+    if (split_gemm(h->cls_score, p[B_FHI], p[B_FLO], D, p[B_CLS], 0)) return -1;
+    if (split_gemm(h->bbox_pred, p[B_FHI], p[B_FLO], D, p[B_BBOX], 0)) return -1;
+    if (row_argmax((const float*)p[B_CLS], ldc, NR, c.num_classes + 1, (int*)p[B_ARGMAX], st)) return -1;
+    if (gather_rows(h->attr_table, D / 4, (const int*)p[B_ARGMAX], NR, D / 4, (float*)p[B_TG], D / 4, st)) return -1;
+    if (split_gemm(h->fc_attr, p[B_FHI], p[B_FLO], D, p[B_AH], 0)) return -1;   // W[:, :D] x + b
+    // + T[argmax class], ReLU, and the hi/lo split of the hidden vector, in one pass
+    if (split_f32((const float*)p[B_AH], (const float*)p[B_TG], 1, (bf16*)p[B_AHHI], (bf16*)p[B_AHLO], (int64_t)NR * (D / 4), st)) return -1;
+    if (split_gemm(h->attr_score, p[B_AHHI], p[B_AHLO], D / 4, p[B_ATTR], 0)) return -1;
+    h->launches += 4;
+  } else {
+    if (run_conv(h, h->cls_score, p[B_FEATS], DT_F32, NR, 1, 1, p[B_CLS], DT_F32, ldc, nullptr, 0, 0, st)) return -1;
+    if (run_conv(h, h->bbox_pred, p[B_FEATS], DT_F32, NR, 1, 1, p[B_BBOX], DT_F32, ldb, nullptr, 0, 0, st)) return -1;
+    if (row_argmax((const float*)p[B_CLS], ldc, NR, c.num_classes + 1, (int*)p[B_ARGMAX], st)) return -1;
+    if (gather_rows(h->attr_table, D / 4, (const int*)p[B_ARGMAX], NR, D / 4, (float*)p[B_TG], D / 4, st)) return -1;
+    if (run_conv(h, h->fc_attr, p[B_FEATS], DT_F32, NR, 1, 1, p[B_AH], DT_F32, D / 4, p[B_TG], D / 4, 1, st)) return -1;
+    if (run_conv(h, h->attr_score, p[B_AH], DT_F32, NR, 1, 1, p[B_ATTR], DT_F32, lda, nullptr, 0, 0, st)) return -1;
+    h->launches += 2;
+  }
+  tap(h, "cls_logits", p[B_CLS], (int64_t)NR * ldc, DT_F32);
+  tap(h, "bbox_deltas", p[B_BBOX], (int64_t)NR * ldb, DT_F32);
+  tap(h, "attr_logits", p[B_ATTR], (int64_t)NR * lda, DT_F32);
 
   // ---- detection tail (frcnn.py:1262-1294)
   TailArgs ta;
   memset(&ta, 0, sizeof(ta));
-  ta.N = n; ta.R = s.R; ta.cls_logits = (const float*)p[B_CLS]; ta.ldc = h->cls_score.ldw;
-  ta.bbox_deltas = (const float*)p[B_BBOX]; ta.ldb = h->bbox_pred.ldw;
-  ta.attr_logits = (const float*)p[B_ATTR]; ta.lda = h->attr_score.ldw;
+  ta.N = n; ta.R = s.R; ta.cls_logits = (const float*)p[B_CLS]; ta.ldc = ldc;
+  ta.bbox_deltas = (const float*)p[B_BBOX]; ta.ldb = ldb;
+  ta.attr_logits = (const float*)p[B_ATTR]; ta.lda = lda;
   ta.feats = (const float*)p[B_FEATS]; ta.D = D; ta.proposals = (const float*)p[B_PROP];
   ta.count = (const int*)p[B_COUNT]; ta.sizes_hw = (const int*)p[B_SIZES];
   ta.scales_yx = scales_yx ? (const float*)p[B_SCALES] : nullptr;
@@ -682,6 +756,31 @@ int vltk_conv2d_nhwc(const void* x, const float* weight, const float* scale, con
     cudaStreamSynchronize(st);
     cudaFree(w_kn);
   }
+  return rc;
+}
+
+int vltk_linear_tc3(const float* x, const float* weight, const float* bias, float* y, int m, int k, int n, int relu,
+                    void* stream) {
+  VLTK_CHECK(x && weight && y, "linear_tc3: null argument");
+  VLTK_CHECK(k % 64 == 0 && n % 64 == 0, "linear_tc3: k and n must be multiples of 64");
+  cudaStream_t st = (cudaStream_t)stream;
+  bf16 *xhi = nullptr, *xlo = nullptr, *whi = nullptr, *wlo = nullptr;
+  float* sh = nullptr;
+  VLTK_CUDA(cudaMalloc(&xhi, (size_t)m * k * 2)); VLTK_CUDA(cudaMalloc(&xlo, (size_t)m * k * 2));
+  VLTK_CUDA(cudaMalloc(&whi, (size_t)n * k * 2)); VLTK_CUDA(cudaMalloc(&wlo, (size_t)n * k * 2));
+  VLTK_CUDA(cudaMalloc(&sh, (size_t)n * 4));
+  int rc = split_f32(x, nullptr, 0, xhi, xlo, (int64_t)m * k, st);
+  if (!rc) rc = split_f32(weight, nullptr, 0, whi, wlo, (int64_t)n * k, st);   // [n][k] is already the B layout
+  if (!rc) rc = pad_vector(bias, sh, n, n, 0.f, st);
+  ConvProblem q;
+  memset(&q, 0, sizeof(q));
+  q.x = xhi; q.ldx = k; q.y = y; q.ldy = n; q.N = m; q.H = q.W = q.OH = q.OW = 1; q.Cin = k; q.Cout = n;
+  q.KH = q.KW = 1; q.stride = 1; q.dil = 1; q.shift = sh; q.relu = relu; q.in_dtype = DT_BF16; q.out_dtype = DT_F32;
+  TcSplit sp; sp.x_lo = xlo; sp.w_lo = wlo;
+  TensorMapCache cache;
+  if (!rc) rc = conv_tc_launch(q, whi, n, &cache, st, &sp);
+  cudaStreamSynchronize(st);
+  cudaFree(xhi); cudaFree(xlo); cudaFree(whi); cudaFree(wlo); cudaFree(sh);
   return rc;
 }
 

@@ -35,7 +35,31 @@ __global__ void pad_vector_kernel(const float* __restrict__ src, float* __restri
   if (i < n_pad) dst[i] = (src && i < n) ? src[i] : fill;
 }
 
+__global__ void split_f32_kernel(const float* __restrict__ x, const float* __restrict__ add, int relu,
+                                 bf16* __restrict__ hi, bf16* __restrict__ lo, int64_t n4) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = load4(x + i * 4);
+  if (add) {
+    float4 a = load4(add + i * 4);
+    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+  }
+  if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+  float4 h = make_float4(__bfloat162float(__float2bfloat16_rn(v.x)), __bfloat162float(__float2bfloat16_rn(v.y)),
+                         __bfloat162float(__float2bfloat16_rn(v.z)), __bfloat162float(__float2bfloat16_rn(v.w)));
+  store4(hi + i * 4, h);  // exact: h is already bf16-representable
+  store4(lo + i * 4, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
+}
+
 }  // namespace
+
+int split_f32(const float* x, const float* add, int relu, bf16* hi, bf16* lo, int64_t n, cudaStream_t st) {
+  VLTK_CHECK(n % 4 == 0, "split_f32: n must be a multiple of 4");
+  if (n == 0) return 0;
+  split_f32_kernel<<<(unsigned)ceil_div64(n / 4, 256), 256, 0, st>>>(x, add, relu, hi, lo, n / 4);
+  VLTK_LAUNCH_CHECK();
+  return 0;
+}
 
 int pack_weight_kn(const float* w, float* w_kn, int cout, int cin, int taps, int ldw, bool round_bf16, cudaStream_t st) {
   int64_t tot = (int64_t)cout * cin * taps;

@@ -46,6 +46,21 @@ def conv2d_nhwc(x, weight, scale=None, shift=None, residual=None, stride=1, pad=
     return y
 
 
+def linear_tc3(x, weight, bias=None, relu=False):
+    """F.linear(x, weight, bias) on the tensor pipe with split-bf16 (hi*hi + lo*hi + hi*lo) operands
+    and fp32 accumulate/output — how the predictor linears (frcnn.py:1729-1737) run in bf16 mode."""
+    L = _lib.lib()
+    m, k = x.shape
+    n = weight.shape[0]
+    y = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    xx, ww = x.float().contiguous(), weight.float().contiguous()
+    bb = None if bias is None else bias.float().contiguous()
+    with torch.cuda.device(x.device):
+        _lib.check(L.vltk_linear_tc3(xx.data_ptr(), ww.data_ptr(), _ptr(bb), y.data_ptr(), m, k, n, int(relu),
+                                     _stream(x)), "vltk_linear_tc3")
+    return y
+
+
 def rpn_proposals(logits, deltas, cell_anchors, image_shapes, cfg):
     """find_top_rpn_proposals + RPN.inference (frcnn.py:264-390, 1615-1638) on NCHW head
     outputs.  Returns (proposals [N,post,4], logits [N,post], counts [N])."""
