@@ -219,7 +219,13 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = model.launch_count() - l0
-    prof, csv = model.profile_read(want_csv=bool(args.profile_csv))
+    prof, csv = model.profile_read(want_csv=True)
+    stage_ms, stage_bytes = {}, {}
+    for ln in (csv or "").splitlines():   # live per-kernel-class breakdown of the timed region
+        kind, m_, k_, c_, ms_ = ln.split(",")
+        stage_ms[kind] = stage_ms.get(kind, 0.0) + float(ms_) / args.steps
+        if int(k_) == 0:                  # non-GEMM kernels log their algorithmic bytes in column 2
+            stage_bytes[kind] = stage_bytes.get(kind, 0.0) + float(m_) / args.steps
     model.profile(False)
     if sampler:
         sampler.stop()
@@ -289,6 +295,10 @@ def main():
                          "flops_per_step": d_fl / args.steps,
                          "share_of_step": (d_ms / args.steps) / (ms / args.steps),
                          "other_dense_ms_per_step": (si_ms if dom == "tcgen05" else tc_ms) / args.steps},
+            "stage_ms_per_step": {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])},
+            "hbm_kernels": {k: {"ms_per_step": round(stage_ms[k], 4), "algorithmic_bytes_per_step": b,
+                                "gbs": b / (stage_ms[k] / 1e3) / 1e9, "frac_of_hbm_peak": b / (stage_ms[k] / 1e3) / 1e9 / pk["hbm_gbs"]}
+                            for k, b in stage_bytes.items() if stage_ms.get(k)},
             "flops_per_image": fl["total"], "step_tflops": BATCH * fl["total"] / (ms / args.steps / 1e3) / 1e12,
             "clocks": sampler.summary() if sampler else None,
         }

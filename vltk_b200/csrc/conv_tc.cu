@@ -695,8 +695,12 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
   const int64_t M = (int64_t)p.N * p.OH * p.OW;
   if (M == 0) return 0;
   const int K = p.KH * p.KW * p.Cin;
-  const int bn = (cout_pad % 256 == 0) ? 256 : (cout_pad % 128 == 0 ? 128 : 64);
-
+  // Cout tile.  Measured on B200 (profiles/r01_summary.md §5): layers with K >= 512 are MMA-bound and want
+  // the widest tile (N=128 MMAs read A 4 KB + B 4 KB per 64 cycles = the whole 128 B/clk smem port, so
+  // they do NOT run at half the cost of N=256); layers with K <= 256 are epilogue-bound (1-4 k-blocks
+  // per tile) and run 7-34 % faster with BN=128, whose finer tiles keep both TMEM accumulators busy.
+  int bn = (cout_pad % 256 == 0) ? 256 : (cout_pad % 128 == 0 ? 128 : 64);
+  if (K <= 256 && cout_pad % 128 == 0) bn = 128;
   CUtensorMap ta, tb;
   TensorMapCache::Key ka(p.x, p.N, p.H, p.W, p.Cin, p.ldx, p.KH, p.stride, p.pad, p.dil, 0);
   TensorMapCache::Key kb(w_nk, K, cout_pad, bn, 0, 0, 0, 0, 0, 0, 1);

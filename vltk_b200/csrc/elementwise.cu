@@ -27,6 +27,50 @@ int nchw3_to_nhwc4(const float* x, void* y, DType dt, int N, int H, int W, cudaS
 }
 
 // ------------------------------------------------------------------------------------------
+// K2a (bf16 mode): im2col of the 7x7 s2 p3 stem (frcnn.py:860-868) so that the 3-channel conv becomes
+// a plain [M,192] x [64,192]^T tensor-core GEMM.  Row m = output pixel; k = (kh*7+kw)*3 + c for
+// k < 147, zero for k in [147,192).  One thread per 16-byte chunk (8 consecutive k) of a row.
+__global__ void stem_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ a, int H, int W, int OH, int OW,
+                                   int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int chunk = (int)(i % 24);
+  const int64_t m = i / 24;
+  const int ow = (int)(m % OW);
+  const int64_t t = m / OW;
+  const int oh = (int)(t % OH);
+  const int n = (int)(t / OH);
+  const float* xb = x + (int64_t)n * H * W * 4;
+  const int ih0 = oh * 2 - 3, iw0 = ow * 2 - 3;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = chunk * 8 + j;
+    float f = 0.f;
+    if (k < 147) {
+      const int tap = k / 3, c = k - tap * 3;
+      const int kh = tap / 7, kw = tap - kh * 7;
+      const int ih = ih0 + kh, iw = iw0 + kw;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) f = xb[((int64_t)ih * W + iw) * 4 + c];
+    }
+    v[j] = f;
+  }
+  uint4 o;
+  __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+  *reinterpret_cast<uint4*>(a + m * 192 + chunk * 8) = o;
+}
+
+int stem_im2col(const float* x_nhwc4, void* a, int N, int H, int W, int OH, int OW, cudaStream_t st) {
+  const int64_t total = (int64_t)N * OH * OW * 24;
+  if (total == 0) return 0;
+  stem_im2col_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(x_nhwc4, (bf16*)a, H, W, OH, OW, total);
+  VLTK_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // K2b: max_pool2d(k=3, s=2, p=0, ceil_mode=True) (frcnn.py:875-876) on NHWC, 4 channels/thread
 template <typename T>
 __global__ void maxpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W,

@@ -57,6 +57,7 @@ struct vltk_frcnn {
   std::map<std::string, std::vector<float>> host;
   std::vector<void*> owned;  // device allocations
   LayerW stem;
+  LayerW stem_tc;          // bf16 mode: stem as a [M,192] x [64,192]^T tensor-core GEMM over im2col rows
   std::vector<std::vector<Block>> stages;  // res2, res3, res4
   std::vector<Block> res5;
   LayerW rpn_conv, rpn_head, cls_score, bbox_pred, fc_attr, attr_score;
@@ -252,7 +253,25 @@ int run_conv(vltk_frcnn* h, const LayerW& L, const void* x, DType xdt, int N, in
   return rc;
 }
 
-struct StageBufs { void *a, *b, *t1, *t2, *s; };
+// Brackets a non-GEMM launch with events when profiling (kind >= 2; `bytes` = algorithmic bytes moved)
+struct StageTimer {
+  vltk_frcnn* h; cudaStream_t st; bool on;
+  vltk_frcnn::ProfRec rec;
+  StageTimer(vltk_frcnn* h_, int kind, double bytes, cudaStream_t s) : h(h_), st(s), on(h_->profiling) {
+    if (!on) return;
+    rec.kind = kind; rec.flops = 0.0; rec.M = (int64_t)bytes; rec.K = 0; rec.Cout = 0;
+    auto get = [&]() { cudaEvent_t e; if (!h->event_pool.empty()) { e = h->event_pool.back(); h->event_pool.pop_back(); } else cudaEventCreate(&e); return e; };
+    rec.e0 = get(); rec.e1 = get();
+    cudaEventRecord(rec.e0, st);
+  }
+  ~StageTimer() {
+    if (!on) return;
+    cudaEventRecord(rec.e1, st);
+    h->prof.push_back(rec);
+  }
+};
+enum { K_TC = 0, K_SIMT = 1, K_ROIPOOL = 2, K_SELECT = 3, K_NMS = 4, K_MEAN = 5, K_TAIL = 6, K_MAXPOOL = 7, K_LAYOUT = 8, K_GLUE = 9, K_NUM = 10 };
+static const char* kKindName[K_NUM] = {"tcgen05", "simt", "roi_pool", "rpn_select", "rpn_nms", "mean_rows", "roi_tail", "maxpool", "layout", "predictor_glue"};
 
 // bottleneck (frcnn.py:963-979): x -> conv1 -> conv2 -> conv3 (+shortcut(x) | x) -> relu
 int run_block(vltk_frcnn* h, const Block& B, const void* x, int N, int H, int W, void* out, void* t1,
@@ -365,6 +384,21 @@ int vltk_frcnn_finalize(vltk_frcnn_t* h) {
   const bool rb = h->act == DT_BF16, tc = h->use_tc;
   // stem consumes the fp32 NHWC4 image directly; its weights stay fp32 in both modes
   if (pack_layer(h, h->stem, "backbone.stem.conv1", 3, c.stem_out_channels, 7, 2, 3, 1, 1, true, false, false, false)) return -1;
+  if (tc && c.stem_out_channels % 64 == 0) {
+    const int so = c.stem_out_channels;
+    const auto* w = find(h, "backbone.stem.conv1.weight", (int64_t)so * 3 * 49);
+    if (!w) return -2;
+    LayerW& L = h->stem_tc;
+    L.cin = L.cin_pad = 192; L.cout = so; L.cout_pad = so; L.k = 1; L.ldw = so;
+    std::vector<bf16> nk((size_t)so * 192, __float2bfloat16_rn(0.f));
+    for (int o = 0; o < so; ++o)
+      for (int ci = 0; ci < 3; ++ci)
+        for (int t = 0; t < 49; ++t)   // k = tap*3 + c, matching stem_im2col
+          nk[(size_t)o * 192 + t * 3 + ci] = __float2bfloat16_rn((*w)[((size_t)o * 3 + ci) * 49 + t]);
+    if (dev_alloc(h, (void**)&L.w_nk, nk.size() * 2)) return -1;
+    VLTK_CUDA(cudaMemcpy(L.w_nk, nk.data(), nk.size() * 2, cudaMemcpyHostToDevice));
+    L.scale = h->stem.scale; L.shift = h->stem.shift;   // same folded BN (64 entries, so == ldw)
+  }
   int cin = c.stem_out_channels, cout = c.res2_out_channels, mid = c.res2_out_channels / 4;
   h->stages.resize(3);
   for (int s = 0; s < 3; ++s) {
@@ -453,7 +487,7 @@ static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void*
 enum {
   B_IN4, B_STEM, B_POOL, B_A, B_B, B_T1, B_T2, B_S, B_RPNH, B_HEAD, B_SIZES, B_SCALES, B_SBOX, B_SSCORE,
   B_SIDX, B_SVALID, B_MASK, B_PROP, B_PSCORE, B_PIDX, B_COUNT, B_POOLED, B_R5A, B_R5B, B_R5T1, B_R5T2,
-  B_R5S, B_FEATS, B_CLS, B_BBOX, B_ARGMAX, B_TG, B_AH, B_ATTR, B_FHI, B_FLO, B_AHHI, B_AHLO, B_NUM
+  B_R5S, B_FEATS, B_CLS, B_BBOX, B_ARGMAX, B_TG, B_AH, B_ATTR, B_FHI, B_FLO, B_AHHI, B_AHLO, B_STEMA, B_NUM
 };
 
 static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void** p) {
@@ -491,6 +525,7 @@ static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void*
   p[B_ATTR] = b.take((size_t)NR * ld(h->attr_score) * 4);
   p[B_FHI] = b.take((size_t)NR * D * 2); p[B_FLO] = b.take((size_t)NR * D * 2);
   p[B_AHHI] = b.take((size_t)NR * (D / 4) * 2); p[B_AHLO] = b.take((size_t)NR * (D / 4) * 2);
+  p[B_STEMA] = b.take(h->stem_tc.w_nk ? (size_t)N * s.Hs * s.Ws * 192 * 2 : 0);
   return b.off + 256;
 }
 
@@ -525,10 +560,31 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   if (scales_yx) VLTK_CUDA(cudaMemcpyAsync(p[B_SCALES], scales_yx, (size_t)n * 8, cudaMemcpyHostToDevice, st));
 
   // ---- backbone (frcnn.py:1076-1090)
-  if (nchw3_to_nhwc4(images, p[B_IN4], DT_F32, n, height, width, st)) return -1;
+  { StageTimer t(h, K_LAYOUT, (double)n * height * width * (12 + 16), st);
+    if (nchw3_to_nhwc4(images, p[B_IN4], DT_F32, n, height, width, st)) return -1; }
   h->launches++;
-  if (run_conv(h, h->stem, p[B_IN4], DT_F32, n, height, width, p[B_STEM], d, h->stem.ldw, nullptr, 0, 1, st)) return -1;
-  if (maxpool3x3s2_ceil(p[B_STEM], p[B_POOL], d, n, s.Hs, s.Ws, c.stem_out_channels, s.Hp, s.Wp, st)) return -1;
+  if (h->use_tc && h->stem_tc.w_nk) {
+    const int64_t Ms = (int64_t)n * s.Hs * s.Ws;
+    { StageTimer t(h, K_LAYOUT, (double)n * height * width * 16.0 + (double)Ms * 384.0, st);
+      if (stem_im2col((const float*)p[B_IN4], p[B_STEMA], n, height, width, s.Hs, s.Ws, st)) return -1; }
+    h->launches++;
+    ConvProblem q;
+    memset(&q, 0, sizeof(q));
+    const LayerW& L = h->stem_tc;
+    q.x = p[B_STEMA]; q.ldx = 192; q.y = p[B_STEM]; q.ldy = L.cout; q.N = (int)Ms; q.H = q.W = q.OH = q.OW = 1;
+    q.Cin = 192; q.Cout = L.cout; q.KH = q.KW = 1; q.stride = 1; q.dil = 1; q.scale = L.scale; q.shift = L.shift;
+    q.relu = 1; q.in_dtype = DT_BF16; q.out_dtype = DT_BF16;
+    vltk_frcnn::ProfRec rec;
+    if (h->profiling) {
+      rec.kind = 0; rec.M = Ms; rec.K = 147; rec.Cout = L.cout; rec.flops = 2.0 * (double)Ms * 147 * L.cout;
+      cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1); cudaEventRecord(rec.e0, st);
+    }
+    h->launches++;
+    if (conv_tc_launch(q, L.w_nk, L.cout_pad, &h->tmaps, st)) return -1;
+    if (h->profiling) { cudaEventRecord(rec.e1, st); h->prof.push_back(rec); }
+  } else if (run_conv(h, h->stem, p[B_IN4], DT_F32, n, height, width, p[B_STEM], d, h->stem.ldw, nullptr, 0, 1, st)) return -1;
+  { StageTimer t(h, K_MAXPOOL, ((double)n * s.Hs * s.Ws + (double)n * s.Hp * s.Wp) * c.stem_out_channels * esz(d), st);
+    if (maxpool3x3s2_ceil(p[B_STEM], p[B_POOL], d, n, s.Hs, s.Ws, c.stem_out_channels, s.Hp, s.Wp, st)) return -1; }
   h->launches++;
   const void* x = p[B_POOL];
   int ch = s.Hp, cw = s.Wp;
@@ -557,14 +613,16 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   ra.wx = c.rpn_bbox_weights[0]; ra.wy = c.rpn_bbox_weights[1]; ra.ww = c.rpn_bbox_weights[2]; ra.wh = c.rpn_bbox_weights[3];
   ra.boxes = (float*)p[B_SBOX]; ra.scores = (float*)p[B_SSCORE]; ra.anchor_idx = (int*)p[B_SIDX];
   ra.valid = (uint8_t*)p[B_SVALID]; ra.K = s.K;
-  if (rpn_select(ra, st)) return -1;
+  { StageTimer t(h, K_SELECT, (double)n * s.h4 * s.w4 * A * 20.0 + (double)n * s.K * 20.0, st);
+    if (rpn_select(ra, st)) return -1; }
   NmsArgs na;
   memset(&na, 0, sizeof(na));
   na.boxes = ra.boxes; na.scores = ra.scores; na.valid = ra.valid; na.N = n; na.K = s.K;
   na.thresh = c.rpn_nms_thresh; na.max_keep = s.R; na.mask = (unsigned long long*)p[B_MASK];
   na.out_boxes = (float*)p[B_PROP]; na.out_scores = (float*)p[B_PSCORE]; na.out_idx = (int*)p[B_PIDX];
   na.out_count = (int*)p[B_COUNT];
-  if (nms_sorted(na, st)) return -1;
+  { StageTimer t(h, K_NMS, (double)n * s.K * 20.0 + (double)n * s.R * 20.0, st);
+    if (nms_sorted(na, st)) return -1; }
   h->launches += 3;
   tap(h, "topk_anchor_idx", p[B_SIDX], (int64_t)n * s.K, DT_F32);  // int32 payload, read raw
   tap(h, "proposals", p[B_PROP], (int64_t)n * s.R * 4, DT_F32);
@@ -573,8 +631,9 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
 
   // ---- ROI head: RoIPool -> res5 -> mean (frcnn.py:1387-1403)
   const int NR = n * s.R, PP = s.P * s.P, D = c.res2_out_channels * 8;
-  if (roi_pool(res4, d, n, s.h4, s.w4, C4, (const float*)p[B_PROP], (const int*)p[B_COUNT], s.R, s.P,
-               1.0f / (float)c.anchor_stride, p[B_POOLED], st)) return -1;
+  { StageTimer t(h, K_ROIPOOL, ((double)n * s.h4 * s.w4 * C4 + (double)n * s.R * s.P * s.P * C4) * esz(d), st);
+    if (roi_pool(res4, d, n, s.h4, s.w4, C4, (const float*)p[B_PROP], (const int*)p[B_COUNT], s.R, s.P,
+                 1.0f / (float)c.anchor_stride, p[B_POOLED], st)) return -1; }
   h->launches++;
   x = p[B_POOLED];
   void* r5[2] = {p[B_R5A], p[B_R5B]};
@@ -584,7 +643,8 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
     if (run_block(h, blk, x, NR, s.P, s.P, r5[flip], p[B_R5T1], p[B_R5T2], p[B_R5S], st, &oh, &ow)) return -1;
     x = r5[flip]; flip ^= 1;
   }
-  if (mean_rows(x, (float*)p[B_FEATS], d, NR, PP, D, st)) return -1;
+  { StageTimer t(h, K_MEAN, (double)NR * PP * D * esz(d) + (double)NR * D * 4, st);
+    if (mean_rows(x, (float*)p[B_FEATS], d, NR, PP, D, st)) return -1; }
   h->launches++;
   tap(h, "feats", p[B_FEATS], (int64_t)NR * D, DT_F32);
 
@@ -612,7 +672,8 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
       if (h->profiling) { cudaEventRecord(rec.e1, st); h->prof.push_back(rec); }
       return rc;
     };
-    if (split_f32((const float*)p[B_FEATS], nullptr, 0, (bf16*)p[B_FHI], (bf16*)p[B_FLO], (int64_t)NR * D, st)) return -1;
+    { StageTimer t(h, K_GLUE, (double)NR * D * 8.0, st);
+      if (split_f32((const float*)p[B_FEATS], nullptr, 0, (bf16*)p[B_FHI], (bf16*)p[B_FLO], (int64_t)NR * D, st)) return -1; }
     if (split_gemm(h->cls_score, p[B_FHI], p[B_FLO], D, p[B_CLS], 0)) return -1;
     if (split_gemm(h->bbox_pred, p[B_FHI], p[B_FLO], D, p[B_BBOX], 0)) return -1;
     if (row_argmax((const float*)p[B_CLS], ldc, NR, c.num_classes + 1, (int*)p[B_ARGMAX], st)) return -1;
@@ -651,7 +712,8 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   ta.boxes = out->boxes; ta.norm_boxes = out->normalized_boxes; ta.obj_ids = (long long*)out->obj_ids;
   ta.obj_probs = out->obj_probs; ta.attr_ids = (long long*)out->attr_ids; ta.attr_probs = out->attr_probs;
   ta.roi_features = out->roi_features; ta.preds_per_image = out->preds_per_image; ta.keep_idx = out->keep_idx;
-  if (roi_tail(ta, st)) return -1;
+  { StageTimer t(h, K_TAIL, (double)NR * (ldc + lda + 4 + 4) * 4.0 + (double)n * knobs->max_detections * (D + 12) * 4.0, st);
+    if (roi_tail(ta, st)) return -1; }
   h->launches++;
   return 0;
 }
@@ -703,9 +765,9 @@ int vltk_frcnn_profile_read(vltk_frcnn_t* h, double* agg, char* csv, size_t cap)
   for (auto& r : h->prof) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, r.e0, r.e1);
-    agg[3 * r.kind + 0] += ms; agg[3 * r.kind + 1] += r.flops; agg[3 * r.kind + 2] += 1.0;
+    if (r.kind < 2) { agg[3 * r.kind + 0] += ms; agg[3 * r.kind + 1] += r.flops; agg[3 * r.kind + 2] += 1.0; }
     if (csv && off + 96 < cap)
-      off += snprintf(csv + off, cap - off, "%s,%lld,%d,%d,%.5f\n", r.kind == 0 ? "tcgen05" : "simt", (long long)r.M, r.K, r.Cout, ms);
+      off += snprintf(csv + off, cap - off, "%s,%lld,%d,%d,%.5f\n", kKindName[r.kind < K_NUM ? r.kind : 0], (long long)r.M, r.K, r.Cout, ms);
     h->event_pool.push_back(r.e0); h->event_pool.push_back(r.e1);
   }
   h->prof.clear();
