@@ -25,6 +25,15 @@ CASES = {
                    rpn_post_nms_topk=48, min_detections=8, max_detections=20,
                    nms_thresh_test=[0.05, 0.3]),
               0, [(150, 200, 2), (240, 160, 3)]),
+    # degenerate inputs: a constant image yields FEWER detections than min_detections (the nms_thresh
+    # list is exhausted and the last attempt is kept, frcnn.py:1274-1278) -> zero-padded tail with
+    # preds_per_image < max_detections; hard-edged stripes exercise saturated activations
+    "constant": (dict(min_size_test=192, max_size_test=256, rpn_pre_nms_topk=600,
+                      rpn_post_nms_topk=40, min_detections=12, max_detections=12),
+                 0, [(192, 256, "const117")]),
+    "stripes": (dict(min_size_test=192, max_size_test=256, rpn_pre_nms_topk=600,
+                     rpn_post_nms_topk=40, min_detections=12, max_detections=12),
+                0, [(192, 256, "stripes16")]),
     # full proposal/detection counts on a mid-size image (6000 -> 300 -> 36)
     "full36": (dict(min_size_test=384, max_size_test=576), 0, [(384, 576, 4)]),
     # BASELINE.json configs[0]: 1 image 800x1333, 36 boxes
@@ -35,8 +44,8 @@ CASES = {
     "cfg3x2": (dict(min_detections=10, max_detections=100), 0, [(600, 800, 20), (1000, 750, 21)]),
 }
 
-CPU_CASES = ("tiny", "mixed")          # cheap enough for the no-GPU suite
-GPU_CASES = ("tiny", "mixed", "full36", "cfg1", "cfg2x2", "cfg3x2")
+CPU_CASES = ("tiny", "mixed", "constant", "stripes")          # cheap enough for the no-GPU suite
+GPU_CASES = ("tiny", "mixed", "constant", "stripes", "full36", "cfg1", "cfg2x2", "cfg3x2")
 
 
 def case_config(name: str) -> FRCNNConfig:
@@ -45,8 +54,22 @@ def case_config(name: str) -> FRCNNConfig:
 
 def case_inputs(name: str):
     """-> (cfg, weight_seed, [raw BGR u8 images])."""
-    from vltk_b200 import synthetic
     over, wseed, imgs = CASES[name]
     cfg = FRCNNConfig().replace(**over)
-    raws = [synthetic.make_raw_image(h, w, s) for (h, w, s) in imgs]
+    raws = [raw_image(h, w, s) for (h, w, s) in imgs]
     return cfg, wseed, raws
+
+
+def raw_image(h: int, w: int, spec):
+    """Raw BGR u8 [h,w,3]: an int spec is a seed of the SURVEY §8d noise recipe; a string names a
+    deterministic pattern."""
+    import torch
+    from vltk_b200 import synthetic
+    if isinstance(spec, int):
+        return synthetic.make_raw_image(h, w, spec)
+    if spec.startswith("const"):
+        return torch.full((h, w, 3), int(spec[5:]), dtype=torch.uint8)
+    if spec.startswith("stripes"):
+        p = int(spec[7:])
+        return ((torch.arange(h).view(-1, 1, 1) // p % 2) * 200).expand(h, w, 3).to(torch.uint8).contiguous()
+    raise ValueError(spec)

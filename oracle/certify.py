@@ -21,8 +21,8 @@ def main():
     cfg = FRCNNConfig().replace(**over)
     sd = synthetic.make_state_dict(cfg, wseed)
     for t in range(tries):
-        seeds = [(h, w, s + 1000 * t) for (h, w, s) in imgs]
-        raws = [synthetic.make_raw_image(h, w, s) for (h, w, s) in seeds]
+        seeds = [(h, w, s + 1000 * t if isinstance(s, int) else s) for (h, w, s) in imgs]
+        raws = [cases.raw_image(h, w, s) for (h, w, s) in seeds]
         images, sizes, scales = O.preprocess(cfg, raws)
         st = {}
         out = O.forward(sd, cfg, images, sizes, scales, stages=st)
