@@ -100,12 +100,16 @@ class FRCNN:
         return self
 
     # -------------------------------------------------------------------- forward
-    def _ws(self, n, h, w):
+    def _ws(self, n, h, w, slot=0):
+        """One scratch buffer per in-flight slot (forwards on different streams must not share one)."""
         need = int(self._lib.vltk_frcnn_workspace_bytes(self._h, n, h, w))
-        if self._workspace is None or self._workspace.numel() < need:
-            self._workspace = None
-            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return self._workspace
+        if self._workspace is None:
+            self._workspace = {}
+        cur = self._workspace.get(slot)
+        if cur is None or cur.numel() < need:
+            self._workspace[slot] = None
+            self._workspace[slot] = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._workspace[slot]
 
     def _alloc_out(self, n, md, d):
         dev = self.device
@@ -126,8 +130,10 @@ class FRCNN:
         return t, o
 
     def run(self, images: torch.Tensor, sizes_hw: np.ndarray, scales_yx: Optional[np.ndarray],
-            max_detections: int, min_detections: int, nms_thresh, pad_value: float = 0.0):
-        """Enqueues one forward on the current stream; returns the dense device tensors."""
+            max_detections: int, min_detections: int, nms_thresh, pad_value: float = 0.0, slot: int = 0):
+        """Enqueues one forward on the current stream; returns the dense device tensors.  The call
+        never synchronises, so forwards on different streams overlap if they use different `slot`s
+        (each slot owns a workspace)."""
         if not self._finalized:
             raise RuntimeError("load_state_dict() has not been called")
         assert images.is_cuda and images.dtype == torch.float32 and images.is_contiguous()
@@ -138,7 +144,7 @@ class FRCNN:
         if scales_yx is not None:
             scales_yx = np.ascontiguousarray(scales_yx, dtype=np.float32).reshape(n, 2)
             sc_ptr = scales_yx.ctypes.data
-        ws = self._ws(n, h, w)
+        ws = self._ws(n, h, w, slot)
         d = self.config.res2_out_channels * 8
         tensors, out = self._alloc_out(n, max_detections, d)
         knobs = _lib.make_knobs(nms_thresh, min_detections, max_detections, pad_value)
