@@ -34,6 +34,10 @@ CASES = {
     "stripes": (dict(min_size_test=192, max_size_test=256, rpn_pre_nms_topk=600,
                      rpn_post_nms_topk=40, min_detections=12, max_detections=12),
                 0, [(192, 256, "stripes16")]),
+    # FEWER survivors than the proposal budget: 6x8 res4 cells = 720 anchors -> top 600 -> NMS leaves
+    # < 300, so ROI slots past the count are zero-filled and masked all the way to the tail
+    "few": (dict(min_size_test=96, max_size_test=128, rpn_pre_nms_topk=600, rpn_post_nms_topk=300,
+                 min_detections=10, max_detections=36), 0, [(96, 128, 3005)]),
     # full proposal/detection counts on a mid-size image (6000 -> 300 -> 36)
     "full36": (dict(min_size_test=384, max_size_test=576), 0, [(384, 576, 4)]),
     # BASELINE.json configs[0]: 1 image 800x1333, 36 boxes
@@ -44,8 +48,8 @@ CASES = {
     "cfg3x2": (dict(min_detections=10, max_detections=100), 0, [(600, 800, 20), (1000, 750, 21)]),
 }
 
-CPU_CASES = ("tiny", "mixed", "constant", "stripes")          # cheap enough for the no-GPU suite
-GPU_CASES = ("tiny", "mixed", "constant", "stripes", "full36", "cfg1", "cfg2x2", "cfg3x2")
+CPU_CASES = ("tiny", "mixed", "constant", "stripes", "few")          # cheap enough for the no-GPU suite
+GPU_CASES = ("tiny", "mixed", "constant", "stripes", "few", "full36", "cfg1", "cfg2x2", "cfg3x2")
 
 
 def case_config(name: str) -> FRCNNConfig:
