@@ -161,7 +161,8 @@ int vltk_roi_outputs(const float* obj_logits, const float* attr_logits, const fl
 
 /* Debug taps: after a forward call, copies an intermediate to HOST memory (tests only).
  * name in {"res4" [N,H4,W4,1024], "rpn_head" [N,H4*W4,80], "proposals" [N,post,4],
- * "proposal_count" [N] (as f32), "feats" [N*post,2048], "cls_logits", "attr_logits",
+ * "proposal_count" [N] (int32 payload), "topk_anchor_idx" [N,K] / "proposal_pos" [N,post] (int32
+ * payload: anchor index of each sorted candidate / position of each kept proposal in that list), "feats" [N*post,2048], "cls_logits", "attr_logits",
  * "bbox_deltas"}; returns the number of floats written, or <0.  bf16 taps are widened. */
 int64_t vltk_frcnn_debug_read(vltk_frcnn_t* h, const char* name, float* host_dst, int64_t capacity);
 

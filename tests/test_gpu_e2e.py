@@ -121,23 +121,60 @@ def _iou(a, b):
     return inter / np.maximum(aa[:, None] + ab[None, :] - inter, 1e-9)
 
 
-@pytest.mark.parametrize("case", ["tiny", "full36", "cfg1"])
+def _proposal_view(model, n):
+    cnt = model.debug_read("proposal_count", np.int32)
+    topk = model.debug_read("topk_anchor_idx", np.int32).reshape(n, -1)
+    pos = model.debug_read("proposal_pos", np.int32).reshape(n, -1)
+    props = model.debug_read("proposals").reshape(n, -1, 4)
+    feats = model.debug_read("feats").reshape(n, -1, 2048)
+    out = []
+    for i in range(n):
+        c = int(cnt[i])
+        out.append(dict(anchor=topk[i][pos[i, :c]], box=props[i, :c], feat=feats[i, :c]))
+    return out
+
+
+@pytest.mark.parametrize("case", ["tiny", "full36", "cfg1", "cfg2x2"])
 def test_bf16_tensor_core_mode_agrees_statistically(case):
+    """bf16 mode vs fp32 mode (which the golden tests pin to the reference, ids exact), compared BY ANCHOR
+    IDENTITY so that 'the same proposal' is a fact, not an IoU guess.  Stated bf16 tolerances:
+      * res4 mean relative error < 2e-2 after ~100 bf16 layers
+      * >= 85 % of the reference's proposals (same anchors) are selected, their boxes at IoU >= 0.8 on average
+        (RPN deltas have std ~0.7 with these weights, so a bf16 error of ~1e-2 moves a box by ~1 %)
+      * pooled 2048-d features of same-anchor proposals: median cosine >= 0.995 and >= 90 % above 0.98.  The
+        tail is RoIPool's quantisation, not arithmetic: a 0.1 px shift across a half-cell rounding boundary
+        moves the pooled window by a whole 16 px cell (torchvision semantics, reproduced bit-exactly).
+    Final detections are reported, not asserted beyond their count: SURVEY.md Appendix E shows bf16 operand
+    rounding re-ranks the near-uniform class scores of random-init weights."""
     g = load_golden(case)
-    model, cfg, images, sizes, scales, out = run_case(case, "bf16")
+    mf, cfg, images, sizes, scales, out_f = run_case(case, "fp32")
     n = images.shape[0]
+    ref = _proposal_view(mf, n)
     h4, w4 = cfg.res4_hw(images.shape[2], images.shape[3])
-    res4 = torch.from_numpy(model.debug_read("res4")).view(n, h4, w4, -1).permute(0, 3, 1, 2)[:, ::16].numpy()
-    ref = g["res4_sub"]
-    # 100 bf16 layers deep: error relative to the activation scale stays at the bf16 level
-    rel = np.abs(res4 - ref).mean() / np.abs(ref).mean()
+    res4_f = mf.debug_read("res4")
+    mb, _, _, _, _, out = run_case(case, "bf16")
+    got = _proposal_view(mb, n)
+    rel = np.abs(mb.debug_read("res4") - res4_f).mean() / np.abs(res4_f).mean()
     assert rel < 2e-2, rel
     assert out["preds_per_image"].tolist() == g["preds_per_image"].tolist()
-    iou = _iou(cat(out["boxes"]), g["boxes"])
-    refound = (iou.max(0) >= 0.7).mean()
-    assert refound >= 0.5, refound
-    print(f"[{case}] bf16: res4 rel err {rel:.2e}, reference boxes re-found (IoU>=0.7) {refound:.2f}, "
-          f"obj_ids equal at rank {(cat(out['obj_ids']) == g['obj_ids']).mean():.2f}")
+    shared, ious, coss = [], [], []
+    for r, b in zip(ref, got):
+        idx_b = {a: k for k, a in enumerate(b["anchor"].tolist())}
+        pairs = [(k, idx_b[a]) for k, a in enumerate(r["anchor"].tolist()) if a in idx_b]
+        shared.append(len(pairs) / max(len(r["anchor"]), 1))
+        ka = np.array([p[0] for p in pairs]); kb = np.array([p[1] for p in pairs])
+        ious.append(np.diag(_iou(r["box"][ka], b["box"][kb])))
+        fa, fb = r["feat"][ka], b["feat"][kb]
+        coss.append((fa * fb).sum(1) / (np.linalg.norm(fa, axis=1) * np.linalg.norm(fb, axis=1) + 1e-12))
+    ious, coss = np.concatenate(ious), np.concatenate(coss)
+    iou_final = _iou(cat(out["boxes"]), cat(out_f["boxes"]))
+    print(f"[{case}] bf16 vs reference-exact fp32: res4 rel err {rel:.2e}; same-anchor proposals {np.mean(shared):.2f}, their box IoU "
+          f"mean {ious.mean():.3f} min {ious.min():.3f}, pooled-feature cosine median {np.median(coss):.4f} mean {coss.mean():.4f} "
+          f">=0.98: {(coss >= 0.98).mean():.2f} min {coss.min():.3f}; final boxes re-found (IoU>=0.7) {(iou_final.max(0) >= 0.7).mean():.2f}, "
+          f"obj_ids equal at rank {(cat(out['obj_ids']) == cat(out_f['obj_ids'])).mean():.2f}")
+    assert np.mean(shared) >= 0.85, shared
+    assert ious.mean() >= 0.8, ious.mean()
+    assert np.median(coss) >= 0.995 and (coss >= 0.98).mean() >= 0.9, (np.median(coss), (coss >= 0.98).mean())
 
 
 def test_determinism_and_batch_invariance():

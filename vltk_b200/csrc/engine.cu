@@ -628,6 +628,7 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   tap(h, "proposals", p[B_PROP], (int64_t)n * s.R * 4, DT_F32);
   tap(h, "proposal_logits", p[B_PSCORE], (int64_t)n * s.R, DT_F32);
   tap(h, "proposal_count", p[B_COUNT], n, DT_F32);
+  tap(h, "proposal_pos", p[B_PIDX], (int64_t)n * s.R, DT_F32);  // int32: position in the sorted top-k list
 
   // ---- ROI head: RoIPool -> res5 -> mean (frcnn.py:1387-1403)
   const int NR = n * s.R, PP = s.P * s.P, D = c.res2_out_channels * 8;
