@@ -125,6 +125,14 @@ int vltk_conv2d_nhwc(const void* x, const float* weight, const float* scale, con
                      int kh, int kw, int stride, int pad, int dil, int relu, int mode,
                      int use_tensor_cores, void* stream);
 
+/* The res5 tail in bf16 mode (frcnn.py:1389, 1401): conv + BN + residual + ReLU on tcgen05 whose output tile
+ * is reduced instead of stored — pooled[g, c] = mean over the g-th group of `pool_rows` consecutive output
+ * pixels (one ROI = 14*14 = 196 rows).  x/residual bf16 NHWC (DEVICE), weight f32 [Cout,Cin,k,k], pooled f32
+ * [N*OH*OW/pool_rows, Cout].  cin % 64 == 0, cout % 256 == 0, pool_rows >= 128 and dividing N*OH*OW. */
+int vltk_conv2d_meanpool_nhwc(const void* x, const float* weight, const float* scale, const float* shift,
+                              const void* residual, float* pooled, int n, int h, int w, int cin, int cout,
+                              int k, int stride, int pad, int dil, int relu, int pool_rows, void* stream);
+
 /* nn.Linear on the tensor pipe with fp32-faithful arithmetic (frcnn.py:1729-1737 in bf16 mode):
  * y[m,n] = act(x[m,k] . weight[n,k]^T + bias), all DEVICE f32; operands are split into bf16
  * hi+lo planes and accumulated as hi*hi + lo*hi + hi*lo in one fp32 TMEM tile.  k,n % 64 == 0. */

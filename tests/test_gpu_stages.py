@@ -83,6 +83,26 @@ def test_conv_tcgen05_matches_simt_and_reference(dev, case):
     assert ((y_tc - ref).abs() <= ulp * (ref.abs() + 1e-2)).all()
 
 
+@pytest.mark.parametrize("rois,cin,cout", [(1, 512, 256), (5, 512, 2048), (37, 1024, 512)])
+def test_fused_meanpool_epilogue_matches_conv_then_mean(dev, rois, cin, cout):
+    """res5 tail: the last conv3's epilogue reduces each ROI's 14x14 = 196 rows to their mean (from the fp32
+    values, in a fixed order) instead of storing the tile.  Checked against an fp64 conv+BN+residual+ReLU+mean
+    of the same bf16 operands: only fp32 accumulation/reduction round-off remains (the unfused path would add
+    a bf16 rounding of every element first)."""
+    from vltk_b200 import stages
+    g = torch.Generator().manual_seed(rois * 7 + cin)
+    x = torch.randn(rois, 14, 14, cin, generator=g).to(dev).bfloat16()
+    wt = (torch.randn(cout, cin, 1, 1, generator=g) * (2.0 / cin) ** 0.5).bfloat16().float().to(dev)
+    sc = (torch.rand(cout, generator=g) * 0.2 + 0.1).to(dev)
+    sh = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    res = torch.randn(rois, 14, 14, cout, generator=g).abs().to(dev).bfloat16()
+    pooled = stages.conv2d_meanpool_nhwc(x, wt, sc, sh, res, 196).cpu()
+    ref = _ref_conv(x, wt, sc, sh, res, 1, 0, 1, True).double().reshape(rois, 196, cout).mean(1)
+    np.testing.assert_allclose(pooled.numpy(), ref.numpy(), rtol=2e-5, atol=2e-5)
+    again = stages.conv2d_meanpool_nhwc(x, wt, sc, sh, res, 196).cpu()
+    assert torch.equal(pooled, again)          # fixed reduction order: bit-reproducible, no atomics
+
+
 @pytest.mark.parametrize("m,k,n", [(300, 2048, 1664), (37, 512, 448), (2400, 2048, 6400)])
 def test_split_bf16_tensor_core_linear_is_fp32_faithful(dev, m, k, n):
     """The predictor linears in bf16 mode: operands split into bf16 hi+lo, hi*hi + lo*hi + hi*lo

@@ -130,6 +130,24 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // named barrier over the 4 epilogue warps only (id 1; id 0 is __syncthreads)
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// Sum 64 per-lane values (one per column) over the 32 lanes (rows) of a warp in 62 shuffles instead of
+// 64 x 5: at each step lanes exchange HALF of their live values with the partner lane, so the live set
+// halves (64 -> 32 -> ... -> 2).  On return lane L holds the totals of columns 2L (v[0]) and 2L+1 (v[1]).
+// The summation tree is fixed, so the result is bit-reproducible.
+__device__ __forceinline__ void warp_colsum64(float (&v)[64], int lane) {
+#pragma unroll
+  for (int step = 0; step < 5; ++step) {
+    const int half = 32 >> step;           // live values after this step
+    const int mask = 16 >> step;           // partner = lane ^ mask
+    const bool up = (lane & mask) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? v[i] : v[i + half];
+      const float keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+    }
+  }
+}
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
@@ -323,6 +341,11 @@ struct TcParams2 {
   // 1: tmA2) and W from map pass_b[i] (0: tmB, 1: tmB2), all accumulating into the same TMEM tile.
   // npass = 1 is the plain bf16 product; {hi*hi, lo*hi, hi*lo} gives an fp32-faithful product.
   int npass, pass_a[3], pass_b[3];
+  // POOL epilogue (res5 tail, frcnn.py:1401): rows are grouped in ROIs of `pool_rows` consecutive pixels;
+  // instead of storing the tile, each row tile writes fp32 column sums of its (at most two) ROI segments to
+  // pool_partial[(m_tile*2 + seg) * Cout + c]; pool_finish() adds the 2-3 partials per ROI in a fixed order.
+  float* pool_partial;
+  int pool_rows;
 };
 
 template <int BN, int STAGES, bool HAS_RES>
@@ -339,13 +362,14 @@ struct Smem2 {
   static_assert(TOTAL <= 232448, "exceeds the 227 KB shared memory of one sm_100 CTA");
 };
 
-template <int BN, int STAGES, bool HAS_RES, bool OUT_F32>
+template <int BN, int STAGES, bool HAS_RES, bool OUT_F32, bool POOL = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2,
                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, TcParams2 p) {
   using S = Smem2<BN, STAGES, HAS_RES>;
   static_assert(!(HAS_RES && OUT_F32), "fp32 output has no residual path");
+  static_assert(!POOL || !OUT_F32, "the pooled epilogue reduces the bf16-path tile");
   constexpr int SLABC = OUT_F32 ? 32 : SLAB;   // columns per 128 B staging row (fp32: 32, bf16: 64)
   constexpr int NSLAB = BN / SLABC;
   // no static smem in this kernel: the dynamic window starts at the CTA's (1024 B aligned) base
@@ -494,10 +518,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
         if (HAS_RES) mbar_wait(rfull_bar(slot), rphase);
-        if (issuer) bulk_wait_read<1>();      // the store that last read sOut[obuf] has drained it
-        epi_barrier();                        // sOut[obuf] reusable; s_scale/s_shift visible
+        if (!POOL && issuer) bulk_wait_read<1>();   // the store that last read sOut[obuf] has drained it
+        epi_barrier();                        // sOut[obuf] reusable (POOL: last slab's column readers done); scale/shift visible
         const uint32_t orow = sOut + obuf * SLAB_BYTES + (uint32_t)row * 128u;
         const uint32_t rrow = sRes + slot * SLAB_BYTES + (uint32_t)row * 128u;
+        float pv[POOL ? 64 : 1];              // POOL: this row's 64 fp32 epilogue values of the slab
+        (void)pv;
         if constexpr (OUT_F32) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {       // 4 fp32 channels = one 16 B chunk
@@ -535,11 +561,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
             }
-            uint4 o;
-            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+            if constexpr (POOL) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-            sts128(orow + coff, o);
+              for (int j = 0; j < 8; ++j) pv[q * 8 + j] = f[j];     // keep the fp32 row in registers
+            } else {
+              uint4 o;
+              __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              sts128(orow + coff, o);
+            }
           }
         }
         if (HAS_RES) {                        // this warp is done with the residual slab
@@ -547,16 +578,54 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (lane == 0) mbar_arrive(rempty_bar(slot));
           if (++slot == RS) { slot = 0; rphase ^= 1u; }
         }
-        fence_proxy_async_smem();             // generic-proxy smem writes -> visible to the TMA unit
-        epi_barrier();
-        if (issuer) {
-          tma_store_2d(&tmY, sOut + obuf * SLAB_BYTES, n0 + s * SLABC, m0);
-          bulk_commit();
+        if constexpr (POOL) {
+          // per-ROI column sums of this slab without staging the tile: rows of this warp that belong to the
+          // tile's first ROI (segment A) / second ROI (segment B) are reduced by a 62-shuffle butterfly
+          const int roi0 = m0 / p.pool_rows;
+          const int bnd = min(BM, (roi0 + 1) * p.pool_rows - m0);          // tile rows [0,bnd) belong to roi0
+          const int64_t left = p.M - (int64_t)m0;                          // rows past M do not exist
+          const int rmax = left < (int64_t)BM ? (int)left : BM;
+          const int w0 = e * 32;                                           // this warp's first tile row
+          const bool in_a = row < bnd && row < rmax, in_b = row >= bnd && row < rmax;
+          float* comb = reinterpret_cast<float*>(gbase + S::OFF_OUT) + (s & 1) * 512;   // [seg][warp][64], double buffered
+          const bool warp_has_a = w0 < bnd && w0 < rmax, warp_has_b = w0 + 31 >= bnd && bnd < rmax;
+          float2 ta = make_float2(0.f, 0.f), tb = make_float2(0.f, 0.f);
+          if (warp_has_a) {                                                // warp-uniform branches
+            float va[64];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) va[j] = in_a ? pv[j] : 0.f;
+            warp_colsum64(va, lane);
+            ta = make_float2(va[0], va[1]);
+          }
+          if (warp_has_b) {
+            float vb[64];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) vb[j] = in_b ? pv[j] : 0.f;
+            warp_colsum64(vb, lane);
+            tb = make_float2(vb[0], vb[1]);
+          }
+          *reinterpret_cast<float2*>(comb + (0 * 4 + e) * 64 + 2 * lane) = ta;   // lane L owns columns 2L, 2L+1
+          *reinterpret_cast<float2*>(comb + (1 * 4 + e) * 64 + 2 * lane) = tb;
+          epi_barrier();
+          {                                                                // 128 threads = 2 segments x 64 columns
+            const int col = et & 63, seg = et >> 6;
+            const float* c4 = comb + seg * 256 + col;
+            const float tot = ((c4[0] + c4[64]) + c4[128]) + c4[192];      // fixed warp order
+            const int64_t mt = m0 / BM;
+            p.pool_partial[(mt * 2 + seg) * (int64_t)p.Cout + n0 + s * SLABC + col] = tot;
+          }
+        } else {
+          fence_proxy_async_smem();           // generic-proxy smem writes -> visible to the TMA unit
+          epi_barrier();
+          if (issuer) {
+            tma_store_2d(&tmY, sOut + obuf * SLAB_BYTES, n0 + s * SLABC, m0);
+            bulk_commit();
+          }
+          obuf ^= 1;
         }
-        obuf ^= 1;
       }
     }
-    if (issuer) bulk_wait_all();              // all output bytes are in global memory
+    if (!POOL && issuer) bulk_wait_all();     // all output bytes are in global memory
   }
   tc_fence_before();
   __syncthreads();
@@ -645,14 +714,31 @@ int num_sms() {
   return n;
 }
 
+// feats[roi][c] = (sum of the row tiles' partial sums for that ROI, ascending tile order) / rows
+__global__ void pool_finish_kernel(const float* __restrict__ partial, float* __restrict__ out, int rois, int rows, int C) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c4n = C / 4;
+  if (i >= (int64_t)rois * c4n) return;
+  const int c = (int)(i % c4n) * 4, r = (int)(i / c4n);
+  const int t0 = (int)(((int64_t)r * rows) / BM), t1 = (int)(((int64_t)r * rows + rows - 1) / BM);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = t0; t <= t1; ++t) {
+    const int seg = r - (int)(((int64_t)t * BM) / rows);   // 0: the tile's first ROI, 1: its second
+    const float4 v = *reinterpret_cast<const float4*>(partial + ((int64_t)t * 2 + seg) * C + c);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  const float d = (float)rows;
+  *reinterpret_cast<float4*>(out + (int64_t)r * C + c) = make_float4(s.x / d, s.y / d, s.z / d, s.w / d);
+}
+
 struct Maps { CUtensorMap a, a2, b, b2, y, r; };
 
-template <int BN, int STAGES, bool HAS_RES, bool OUT_F32>
+template <int BN, int STAGES, bool HAS_RES, bool OUT_F32, bool POOL = false>
 int launch2(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
   using S = Smem2<BN, STAGES, HAS_RES>;
   static bool attr_set = false;
   if (!attr_set) {
-    VLTK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STAGES, HAS_RES, OUT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    VLTK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STAGES, HAS_RES, OUT_F32, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
   tp.n_tiles = cout_pad / BN;
@@ -660,7 +746,7 @@ int launch2(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
   VLTK_CHECK(tiles < (1ll << 31), "conv_tc: too many tiles");
   tp.num_tiles = (int)tiles;
   const int grid = (int)std::min<int64_t>(tiles, num_sms());  // persistent: one CTA per SM
-  conv_tc2_kernel<BN, STAGES, HAS_RES, OUT_F32><<<grid, TC_THREADS, S::TOTAL, st>>>(m.a, m.a2, m.b, m.b2, m.y, m.r, tp);
+  conv_tc2_kernel<BN, STAGES, HAS_RES, OUT_F32, POOL><<<grid, TC_THREADS, S::TOTAL, st>>>(m.a, m.a2, m.b, m.b2, m.y, m.r, tp);
   VLTK_LAUNCH_CHECK();
   return 0;
 }
@@ -681,8 +767,10 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const TcParams& tp, int c
 
 }  // namespace
 
+size_t conv_tc_pool_partial_bytes(int64_t M, int cout) { return (size_t)ceil_div64(M, BM) * 2 * cout * sizeof(float); }
+
 int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorMapCache* cache, cudaStream_t st,
-                   const TcSplit* split) {
+                   const TcSplit* split, const TcPool* pool) {
   const bool out_f32 = p.out_dtype == DT_F32;
   const bool is_split = split && split->x_lo && split->w_lo;
   VLTK_CHECK(p.in_dtype == DT_BF16, "conv_tc: bf16 operands only");
@@ -746,6 +834,7 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
     t2.scale = p.scale; t2.shift = p.shift; t2.M = M; t2.Cout = p.Cout; t2.relu = p.relu;
     t2.OH = p.OH; t2.OW = p.OW; t2.stride = p.stride; t2.pad = p.pad; t2.dil = p.dil; t2.KW = p.KW;
     t2.taps = p.KH * p.KW; t2.cblocks = p.Cin / BK; t2.n_tiles = 0; t2.num_tiles = 0;
+    t2.pool_partial = nullptr; t2.pool_rows = 1;
     t2.npass = is_split ? 3 : 1;                       // hi*hi, lo*hi, hi*lo
     t2.pass_a[0] = 0; t2.pass_a[1] = 1; t2.pass_a[2] = 0;
     t2.pass_b[0] = 0; t2.pass_b[1] = 0; t2.pass_b[2] = 1;
@@ -753,6 +842,17 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
       if (bn == 256) return launch2<256, 4, false, true>(m, t2, cout_pad, st);
       if (bn == 128) return launch2<128, 4, false, true>(m, t2, cout_pad, st);
       return launch2<64, 4, false, true>(m, t2, cout_pad, st);
+    }
+    if (pool && pool->out) {
+      VLTK_CHECK(p.residual && bn == 256 && !out_f32 && !is_split, "conv_tc: the pooled epilogue is built for the res5 conv3 shape (residual, Cout %% 256 == 0, K > 256)");
+      VLTK_CHECK(pool->rows >= BM && M % pool->rows == 0 && p.Cout % 4 == 0, "conv_tc: pool_rows=%d must be >= %d and divide M", pool->rows, BM);
+      t2.pool_partial = pool->partial; t2.pool_rows = pool->rows;
+      if (launch2<256, 3, true, false, true>(m, t2, cout_pad, st)) return -1;
+      const int rois = (int)(M / pool->rows);
+      const int64_t tot = (int64_t)rois * (p.Cout / 4);
+      pool_finish_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(pool->partial, pool->out, rois, pool->rows, p.Cout);
+      VLTK_LAUNCH_CHECK();
+      return 0;
     }
     if (p.residual) {
       if (bn == 256) return launch2<256, 3, true, false>(m, t2, cout_pad, st);

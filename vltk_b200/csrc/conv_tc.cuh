@@ -25,9 +25,19 @@ struct TcSplit {
   const void* x_lo = nullptr;   // same geometry as p.x
   const bf16* w_lo = nullptr;   // same geometry as w_nk
 };
+// Optional fused row-group mean (res5 tail, frcnn.py:1401): rows are ROIs of `rows` consecutive pixels; the
+// layer's output tile is NOT stored — out[M/rows][Cout] (f32) receives the mean of each group, computed from
+// the fp32 epilogue values.  `partial` is scratch of conv_tc_pool_partial_bytes(M, Cout).  Requires a residual,
+// Cout % 256 == 0, K > 256, rows >= 128 (a 128-row tile then spans at most two ROIs).
+struct TcPool {
+  float* out = nullptr;
+  float* partial = nullptr;
+  int rows = 0;
+};
+size_t conv_tc_pool_partial_bytes(int64_t M, int cout);
 // out_dtype may be DT_F32 (no residual) or DT_BF16.
 int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorMapCache* cache,
-                   cudaStream_t st, const TcSplit* split = nullptr);
+                   cudaStream_t st, const TcSplit* split = nullptr, const TcPool* pool = nullptr);
 
 // ---- pack.cu: reference-layout weights [cout][cin][taps] (DEVICE f32) -> kernel layouts
 int pack_weight_kn(const float* w, float* w_kn, int cout, int cin, int taps, int ldw, bool round_bf16,

@@ -217,7 +217,7 @@ Shapes make_shapes(const vltk_frcnn_config& c, int N, int H, int W) {
 // Runs one layer.  x: [N,H,W,cin_pad]
 int run_conv(vltk_frcnn* h, const LayerW& L, const void* x, DType xdt, int N, int H, int W, void* y,
              DType ydt, int ldy, const void* residual, int ldr, int relu, cudaStream_t st, int* oh_out = nullptr,
-             int* ow_out = nullptr) {
+             int* ow_out = nullptr, const TcPool* pool = nullptr) {
   ConvProblem p;
   memset(&p, 0, sizeof(p));
   p.x = x; p.ldx = L.cin_pad; p.y = y; p.ldy = ldy; p.residual = residual; p.ldr = ldr;
@@ -245,7 +245,8 @@ int run_conv(vltk_frcnn* h, const LayerW& L, const void* x, DType xdt, int N, in
     rec.e0 = get_event(); rec.e1 = get_event();
     cudaEventRecord(rec.e0, st);
   }
-  int rc = tc ? conv_tc_launch(p, L.w_nk, L.cout_pad, &h->tmaps, st) : conv_simt_launch(p, L.w_kn, L.ldw, st);
+  if (pool && !tc) { set_error("internal: fused mean-pool needs the tensor-core path"); return -2; }
+  int rc = tc ? conv_tc_launch(p, L.w_nk, L.cout_pad, &h->tmaps, st, nullptr, pool) : conv_simt_launch(p, L.w_kn, L.ldw, st);
   if (h->profiling) {
     cudaEventRecord(rec.e1, st);
     h->prof.push_back(rec);
@@ -275,7 +276,7 @@ static const char* kKindName[K_NUM] = {"tcgen05", "simt", "roi_pool", "rpn_selec
 
 // bottleneck (frcnn.py:963-979): x -> conv1 -> conv2 -> conv3 (+shortcut(x) | x) -> relu
 int run_block(vltk_frcnn* h, const Block& B, const void* x, int N, int H, int W, void* out, void* t1,
-              void* t2, void* sbuf, cudaStream_t st, int* oh, int* ow) {
+              void* t2, void* sbuf, cudaStream_t st, int* oh, int* ow, const TcPool* pool = nullptr) {
   const DType d = h->act;
   int h1, w1;
   if (run_conv(h, B.c1, x, d, N, H, W, t1, d, B.c1.ldw, nullptr, 0, 1, st, &h1, &w1)) return -1;
@@ -286,7 +287,7 @@ int run_block(vltk_frcnn* h, const Block& B, const void* x, int N, int H, int W,
     if (run_conv(h, B.sc, x, d, N, H, W, sbuf, d, B.sc.ldw, nullptr, 0, 0, st)) return -1;
     res = sbuf;
   }
-  if (run_conv(h, B.c3, t2, d, N, h1, w1, out, d, B.c3.ldw, res, ldr, 1, st)) return -1;
+  if (run_conv(h, B.c3, t2, d, N, h1, w1, out, d, B.c3.ldw, res, ldr, 1, st, nullptr, nullptr, pool)) return -1;
   *oh = h1; *ow = w1;
   return 0;
 }
@@ -487,7 +488,7 @@ static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void*
 enum {
   B_IN4, B_STEM, B_POOL, B_A, B_B, B_T1, B_T2, B_S, B_RPNH, B_HEAD, B_SIZES, B_SCALES, B_SBOX, B_SSCORE,
   B_SIDX, B_SVALID, B_MASK, B_PROP, B_PSCORE, B_PIDX, B_COUNT, B_POOLED, B_R5A, B_R5B, B_R5T1, B_R5T2,
-  B_R5S, B_FEATS, B_CLS, B_BBOX, B_ARGMAX, B_TG, B_AH, B_ATTR, B_FHI, B_FLO, B_AHHI, B_AHLO, B_STEMA, B_NUM
+  B_R5S, B_FEATS, B_CLS, B_BBOX, B_ARGMAX, B_TG, B_AH, B_ATTR, B_FHI, B_FLO, B_AHHI, B_AHLO, B_STEMA, B_PARTIAL, B_NUM
 };
 
 static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void** p) {
@@ -526,6 +527,7 @@ static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void*
   p[B_FHI] = b.take((size_t)NR * D * 2); p[B_FLO] = b.take((size_t)NR * D * 2);
   p[B_AHHI] = b.take((size_t)NR * (D / 4) * 2); p[B_AHLO] = b.take((size_t)NR * (D / 4) * 2);
   p[B_STEMA] = b.take(h->stem_tc.w_nk ? (size_t)N * s.Hs * s.Ws * 192 * 2 : 0);
+  p[B_PARTIAL] = b.take(h->use_tc ? conv_tc_pool_partial_bytes((int64_t)NR * PP, D) : 0);
   return b.off + 256;
 }
 
@@ -639,13 +641,22 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   x = p[B_POOLED];
   void* r5[2] = {p[B_R5A], p[B_R5B]};
   flip = 0;
-  for (auto& blk : h->res5) {
+  // The last block's output is only ever consumed by the 14x14 mean (frcnn.py:1401): on the tensor pipe its
+  // conv3 epilogue reduces the fp32 tile per ROI instead of storing 2 GB that would be read straight back.
+  const bool fuse_mean = h->use_tc && h->res5.back().c3.w_nk && PP >= 128 && D % 256 == 0 && h->res5.back().c3.cin > 256;   // K > 256: the shape the pooled tile config is built for
+  TcPool pool;
+  pool.out = (float*)p[B_FEATS]; pool.partial = (float*)p[B_PARTIAL]; pool.rows = PP;
+  for (size_t bi = 0; bi < h->res5.size(); ++bi) {
     int oh, ow;
-    if (run_block(h, blk, x, NR, s.P, s.P, r5[flip], p[B_R5T1], p[B_R5T2], p[B_R5S], st, &oh, &ow)) return -1;
+    const bool last = bi + 1 == h->res5.size();
+    if (run_block(h, h->res5[bi], x, NR, s.P, s.P, r5[flip], p[B_R5T1], p[B_R5T2], p[B_R5S], st, &oh, &ow,
+                  (last && fuse_mean) ? &pool : nullptr)) return -1;
     x = r5[flip]; flip ^= 1;
   }
-  { StageTimer t(h, K_MEAN, (double)NR * PP * D * esz(d) + (double)NR * D * 4, st);
-    if (mean_rows(x, (float*)p[B_FEATS], d, NR, PP, D, st)) return -1; }
+  if (!fuse_mean) {
+    StageTimer t(h, K_MEAN, (double)NR * PP * D * esz(d) + (double)NR * D * 4, st);
+    if (mean_rows(x, (float*)p[B_FEATS], d, NR, PP, D, st)) return -1;
+  }
   h->launches++;
   tap(h, "feats", p[B_FEATS], (int64_t)NR * D, DT_F32);
 
@@ -819,6 +830,41 @@ int vltk_conv2d_nhwc(const void* x, const float* weight, const float* scale, con
     cudaStreamSynchronize(st);
     cudaFree(w_kn);
   }
+  return rc;
+}
+
+int vltk_conv2d_meanpool_nhwc(const void* x, const float* weight, const float* scale, const float* shift,
+                              const void* residual, float* pooled, int n, int hh, int ww, int cin, int cout, int kh,
+                              int stride, int pad, int dil, int relu, int pool_rows, void* stream) {
+  VLTK_CHECK(x && weight && residual && pooled, "conv2d_meanpool: null argument");
+  VLTK_CHECK(cin % 64 == 0 && cout % 256 == 0, "conv2d_meanpool: cin %% 64 and cout %% 256 required");
+  cudaStream_t st = (cudaStream_t)stream;
+  ConvProblem p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.ldx = cin; p.residual = residual; p.ldr = cout; p.ldy = cout;
+  p.N = n; p.H = hh; p.W = ww; p.Cin = cin; p.KH = p.KW = kh; p.stride = stride; p.pad = pad; p.dil = dil;
+  p.OH = (hh + 2 * pad - (dil * (kh - 1) + 1)) / stride + 1;
+  p.OW = (ww + 2 * pad - (dil * (kh - 1) + 1)) / stride + 1;
+  p.Cout = cout; p.relu = relu; p.in_dtype = DT_BF16; p.out_dtype = DT_BF16;
+  const int64_t M = (int64_t)n * p.OH * p.OW;
+  const int K = kh * kh * cin;
+  bf16 *w_nk = nullptr, *ydummy = nullptr;
+  float *sc = nullptr, *sh = nullptr, *partial = nullptr;
+  VLTK_CUDA(cudaMalloc(&w_nk, (size_t)cout * K * 2));
+  VLTK_CUDA(cudaMalloc(&ydummy, (size_t)128 * cout * 2));        // tensor map target only: never written
+  VLTK_CUDA(cudaMalloc(&sc, (size_t)cout * 4));
+  VLTK_CUDA(cudaMalloc(&sh, (size_t)cout * 4));
+  VLTK_CUDA(cudaMalloc(&partial, conv_tc_pool_partial_bytes(M, cout)));
+  p.y = ydummy;
+  int rc = pack_weight_nk(weight, w_nk, cout, cin, kh * kh, st);
+  if (!rc) rc = pad_vector(scale, sc, cout, cout, 1.f, st);
+  if (!rc) rc = pad_vector(shift, sh, cout, cout, 0.f, st);
+  p.scale = sc; p.shift = sh;
+  TcPool pool; pool.out = pooled; pool.partial = partial; pool.rows = pool_rows;
+  TensorMapCache cache;
+  if (!rc) rc = conv_tc_launch(p, w_nk, cout, &cache, st, nullptr, &pool);
+  cudaStreamSynchronize(st);
+  cudaFree(w_nk); cudaFree(ydummy); cudaFree(sc); cudaFree(sh); cudaFree(partial);
   return rc;
 }
 

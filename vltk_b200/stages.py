@@ -46,6 +46,29 @@ def conv2d_nhwc(x, weight, scale=None, shift=None, residual=None, stride=1, pad=
     return y
 
 
+def conv2d_meanpool_nhwc(x, weight, scale, shift, residual, pool_rows, stride=1, pad=0, dil=1, relu=True):
+    """The res5 tail on the tensor pipe (frcnn.py:1389, 1401): act(conv(x,w)*scale + shift + residual) whose
+    output is reduced to the mean of every `pool_rows` consecutive pixels instead of being stored.
+    x, residual: bf16 NHWC; returns f32 [N*OH*OW/pool_rows, Cout]."""
+    L = _lib.lib()
+    assert x.dtype == torch.bfloat16 and residual.dtype == torch.bfloat16 and x.is_contiguous() and residual.is_contiguous()
+    n, h, w, cin = x.shape
+    cout, _, k, _ = weight.shape
+    oh = (h + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    ow = (w + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    m = n * oh * ow
+    assert m % pool_rows == 0
+    out = torch.empty((m // pool_rows, cout), dtype=torch.float32, device=x.device)
+    wt = weight.to(x.device, torch.float32).contiguous()
+    sc, sh = scale.to(x.device, torch.float32).contiguous(), shift.to(x.device, torch.float32).contiguous()
+    with torch.cuda.device(x.device):
+        _lib.check(L.vltk_conv2d_meanpool_nhwc(x.data_ptr(), wt.data_ptr(), sc.data_ptr(), sh.data_ptr(),
+                                               residual.data_ptr(), out.data_ptr(), n, h, w, cin, cout, k,
+                                               stride, pad, dil, int(relu), pool_rows, _stream(x)),
+                   "vltk_conv2d_meanpool_nhwc")
+    return out
+
+
 def linear_tc3(x, weight, bias=None, relu=False):
     """F.linear(x, weight, bias) on the tensor pipe with split-bf16 (hi*hi + lo*hi + hi*lo) operands
     and fp32 accumulate/output — how the predictor linears (frcnn.py:1729-1737) run in bf16 mode."""
