@@ -196,6 +196,28 @@ def test_determinism_and_batch_invariance():
     assert torch.equal(sw["roi_features"][0], a["roi_features"][1])
 
 
+def test_forward_stream_equals_forward():
+    """The pipelined public API (H2D / compute / D2H of neighbouring batches overlapped on three streams)
+    must return, in order, exactly what one synchronous forward() per batch returns — including across
+    batches of different canvas shapes (slot buffers are reallocated) and more batches than pipeline depth."""
+    from vltk_b200.preprocess import Preprocess
+    model, cfg = get_model("mixed", "fp32")
+    pre = Preprocess(cfg)
+    host = []
+    for name in ("mixed", "tiny", "mixed", "stripes", "tiny", "mixed", "constant"):
+        _, _, raws = cases.case_inputs(name)
+        _, images, sizes, scales = pre(raws)
+        host.append((images.cpu(), sizes, scales if name != "stripes" else None))   # one batch without scales_yx
+    ref = [model(x, sz, scales_yx=sc, padding="max_detections", return_tensors="np") for x, sz, sc in host]
+    for depth in (1, 2, 3):
+        got = list(model.forward_stream(iter(host), depth=depth))
+        assert len(got) == len(ref)
+        for a, b in zip(got, ref):
+            for k in ("obj_ids", "attr_ids", "boxes", "normalized_boxes", "obj_probs", "attr_probs", "roi_features",
+                      "preds_per_image", "sizes", "keep_idx"):
+                assert np.array_equal(a[k], b[k]), (depth, k)
+
+
 def test_error_behaviour():
     from vltk_b200 import _lib
     from vltk_b200.frcnn import FRCNN

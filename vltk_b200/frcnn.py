@@ -218,6 +218,72 @@ class FRCNN:
     __call__ = forward
     inference = forward
 
+    def forward_stream(self, batches, max_detections=None, pad_value=0.0, depth=2):
+        """Pipelined `forward(..., padding="max_detections", return_tensors="np")` over an iterable of host
+        batches `(images, image_shapes, scales_yx)`: the host->device copy of batch i+1 and the device->host
+        copy of batch i-1 run on their own streams while batch i computes (the forward itself never
+        synchronises).  Yields one dict of numpy arrays per batch, in order.  Every batch's images are copied
+        from (pinned) host memory and every result is read back to the host, exactly like `forward`."""
+        if not self._finalized:
+            raise RuntimeError("load_state_dict() has not been called")
+        ro = self.roi_outputs
+        md = int(max_detections or ro.max_detections)
+        mind = min(int(ro.min_detections), md)
+        dev = self.device
+        keys = ("obj_ids", "obj_probs", "attr_ids", "attr_probs", "boxes", "roi_features", "preds_per_image",
+                "normalized_boxes", "keep_idx")
+        with torch.cuda.device(dev):
+            compute = torch.cuda.current_stream(dev)
+            s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            slots = [dict(x=None, ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event(), ev_out=torch.cuda.Event(),
+                          host=None, dev_out=None, sizes=None, busy=False) for _ in range(depth)]
+
+            def collect(sl):
+                sl["ev_out"].synchronize()
+                out = OrderedDict((k, sl["host"][k].numpy().copy()) for k in keys)   # staging buffers are reused
+                out["preds_per_image"] = out["preds_per_image"].astype(np.int64)
+                out["sizes"] = sl["sizes"].astype(np.int64)
+                sl["busy"] = False
+                return out
+
+            pending = []
+            for i, (images, image_shapes, scales_yx) in enumerate(batches):
+                sl = slots[i % depth]
+                if sl["busy"]:                       # its previous result has not been handed out yet
+                    yield collect(pending.pop(0))
+                x = torch.as_tensor(images)
+                if x.is_cuda:
+                    raise ValueError("forward_stream takes host batches; use forward() for device tensors")
+                x = x.float().contiguous()
+                if not x.is_pinned():
+                    x = x.pin_memory()
+                if sl["x"] is None or sl["x"].shape != x.shape:
+                    sl["x"] = torch.empty(x.shape, dtype=torch.float32, device=dev)
+                sizes = np.asarray(torch.as_tensor(image_shapes).cpu().numpy(), dtype=np.int32)
+                scales = None if scales_yx is None else np.asarray(torch.as_tensor(scales_yx).cpu().numpy(), dtype=np.float32)
+                with torch.cuda.stream(s_in):
+                    s_in.wait_event(sl["ev_done"])   # the forward that last read this input buffer is finished
+                    sl["x"].copy_(x, non_blocking=True)
+                    sl["ev_in"].record(s_in)
+                compute.wait_event(sl["ev_in"])
+                compute.wait_event(sl["ev_out"])     # the D2H that last read this slot's outputs is finished
+                t = self.run(sl["x"], sizes, scales, md, mind, ro.nms_thresh, float(pad_value))
+                keep_alive = t.pop("_keepalive")
+                sl["ev_done"].record(compute)
+                if sl["host"] is None or sl["host"]["roi_features"].shape != t["roi_features"].shape:
+                    sl["host"] = {k: torch.empty(t[k].shape, dtype=t[k].dtype).pin_memory() for k in keys}
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(sl["ev_done"])
+                    for k in keys:
+                        sl["host"][k].copy_(t[k], non_blocking=True)
+                    sl["ev_out"].record(s_out)
+                sl["dev_out"], sl["sizes"], sl["busy"], sl["_x_host"], sl["_ka"] = t, sizes, True, x, keep_alive
+                pending.append(sl)
+                if len(pending) >= depth:            # hand out the oldest result while newer batches run
+                    yield collect(pending.pop(0))
+            while pending:
+                yield collect(pending.pop(0))
+
     # ------------------------------------------------------------------ test taps
     def debug_read(self, name: str, dtype=np.float32) -> np.ndarray:
         """Copies an intermediate of the last forward to the host (tests only)."""
