@@ -218,6 +218,30 @@ def test_forward_stream_equals_forward():
                 assert np.array_equal(a[k], b[k]), (depth, k)
 
 
+def test_two_devices_in_one_process():
+    """The C ABI allows one process to own engines on several GPUs: the >48 KB shared-memory opt-in of the
+    big kernels is per device and must be repeated on each (a per-process flag would make the second device's
+    first launch fail)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from vltk_b200.frcnn import FRCNN
+    from vltk_b200.preprocess import Preprocess
+    cfg = cases.case_config("tiny")
+    _, _, raws = cases.case_inputs("tiny")
+    outs = []
+    for dev in (0, 1):
+        for mode in ("bf16", "fp32"):
+            m = FRCNN.from_pretrained(state_dict=weights(0), config=cfg, mode=mode, device=dev)
+            _, images, sizes, scales = Preprocess(cfg, device=dev)(raws)
+            o = m(images, sizes, scales_yx=scales, padding="max_detections", return_tensors="np")
+            outs.append((dev, mode, o))
+    for mode in ("bf16", "fp32"):
+        a = next(o for d, m_, o in outs if d == 0 and m_ == mode)
+        b = next(o for d, m_, o in outs if d == 1 and m_ == mode)
+        for k in ("obj_ids", "attr_ids", "boxes", "roi_features", "preds_per_image"):
+            assert np.array_equal(a[k], b[k]), (mode, k)    # same kernels, same inputs: bit-identical across GPUs
+
+
 def test_error_behaviour():
     from vltk_b200 import _lib
     from vltk_b200.frcnn import FRCNN

@@ -36,6 +36,21 @@ const char* get_error();
 
 #define VLTK_LAUNCH_CHECK() VLTK_CUDA(cudaGetLastError())
 
+// cudaFuncSetAttribute (the >48 KB dynamic shared memory opt-in) is PER DEVICE: a process that drives several
+// GPUs must repeat it on each one.  Returns true the first time it is called for the current device with a
+// given per-kernel flag array (one `static DeviceOnce` per kernel / template instantiation).
+struct DeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 // ---- element access helpers (fp32 or bf16 activations) -----------------------------------
 __device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 load4(const bf16* p) {

@@ -703,15 +703,17 @@ int make_rowmajor_map(const void* ptr, int64_t rows, int cols, int ld, bool f32,
   return 0;
 }
 
-int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+int num_sms() {            // of the CURRENT device (a process may drive several)
+  static int cache[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (!cache[dev]) {
+    int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    cache[dev] = n > 0 ? n : 148;
   }
-  return n;
+  return cache[dev];
 }
 
 // feats[roi][c] = (sum of the row tiles' partial sums for that ROI, ascending tile order) / rows
@@ -736,10 +738,9 @@ struct Maps { CUtensorMap a, a2, b, b2, y, r; };
 template <int BN, int STAGES, bool HAS_RES, bool OUT_F32, bool POOL = false>
 int launch2(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
   using S = Smem2<BN, STAGES, HAS_RES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce once;
+  if (once.first()) {
     VLTK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STAGES, HAS_RES, OUT_F32, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set = true;
   }
   tp.n_tiles = cout_pad / BN;
   const int64_t tiles = ceil_div64(tp.M, BM) * tp.n_tiles;
@@ -754,10 +755,9 @@ int launch2(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
 template <int BN, int STAGES>
 int launch(const CUtensorMap& a, const CUtensorMap& b, const TcParams& tp, int cout_pad, cudaStream_t st) {
   using S = Smem<BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce once;
+  if (once.first()) {
     VLTK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set = true;
   }
   dim3 grid(cout_pad / BN, (unsigned)ceil_div64(tp.M, BM));
   conv_tc_kernel<BN, STAGES><<<grid, TC_THREADS, S::TOTAL, st>>>(a, b, tp);
@@ -789,6 +789,7 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
   // per tile) and run 7-34 % faster with BN=128, whose finer tiles keep both TMEM accumulators busy.
   int bn = (cout_pad % 256 == 0) ? 256 : (cout_pad % 128 == 0 ? 128 : 64);
   if (K <= 256 && cout_pad % 128 == 0) bn = 128;
+  if (cache->maps.size() > 8192) cache->maps.clear();   // keys hold buffer addresses: bound growth across reallocations
   CUtensorMap ta, tb;
   TensorMapCache::Key ka(p.x, p.N, p.H, p.W, p.Cin, p.ldx, p.KH, p.stride, p.pad, p.dil, 0);
   TensorMapCache::Key kb(w_nk, K, cout_pad, bn, 0, 0, 0, 0, 0, 0, 1);

@@ -299,10 +299,9 @@ int sort_boxes_desc(const float* boxes, const float* scores, int K, float* sboxe
   if (K == 0) return 0;
   int sort_n = 2;
   while (sort_n < K) sort_n <<= 1;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce once;
+  if (once.first()) {
     VLTK_CUDA(cudaFuncSetAttribute(sort_boxes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
-    attr_set = true;
   }
   sort_boxes_kernel<<<1, SEL_THREADS, (size_t)sort_n * 8, st>>>(boxes, scores, K, sort_n, sboxes, sscores, order);
   VLTK_LAUNCH_CHECK();
@@ -323,10 +322,9 @@ int rpn_select(const RpnSelectArgs& a, cudaStream_t st) {
   int sort_n = 2;
   while (sort_n < a.K) sort_n <<= 1;
   size_t smem = (size_t)sort_n * sizeof(unsigned long long);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce once;
+  if (once.first()) {
     VLTK_CUDA(cudaFuncSetAttribute(rpn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
-    attr_set = true;
   }
   if (a.N == 0) return 0;
   rpn_select_kernel<<<a.N, SEL_THREADS, smem, st>>>(a, sort_n);

@@ -238,10 +238,9 @@ int roi_tail(const TailArgs& a, cudaStream_t st) {
   const int RW = ceil_div(a.R, 64);
   size_t smem = (size_t)a.R * 16 + (size_t)sort_n * 8 + (size_t)a.R * RW * 8 + (size_t)RW * 8 +
                 (size_t)a.R * 4 * 5 + (size_t)a.max_det * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce once;
+  if (once.first()) {
     VLTK_CUDA(cudaFuncSetAttribute(roi_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_set = true;
   }
   VLTK_CHECK(smem <= 100 * 1024, "roi_tail: smem %zu too large", smem);
   float t[4] = {0.f, 0.f, 0.f, 0.f};
