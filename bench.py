@@ -327,7 +327,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * BATCH, "mode": args.mode, "streams_in_flight": args.streams,
                        "value_timed_with_profiling_events": "the K timed steps carry ~250 cudaEventRecords/step (per-launch roofline timing); e2e loops do not",
-                       "arithmetic": ("bf16 operands / fp32 accumulate on tcgen05; fp32 stem, RPN head, predictor and tail"
+                       "arithmetic": ("bf16 operands / fp32 accumulate on tcgen05 (stem, res2-res5, RPN 3x3); predictor linears fp32-faithful on tcgen05 (3-pass split-bf16, fp32 logits); RPN 1x1 head and the whole selection tail in fp32"
                                       if args.mode == "bf16" else "fp32 FMA (CUDA cores), index-exact parity mode"),
                        "parallelism": f"images sharded by rank, dp{world}, no data-path collective",
                        "l2": "4 rotating input batches (230 MB) and multi-GB activations exceed the 126 MB L2",
@@ -339,7 +339,7 @@ def main():
                     "sync_forward_value": sync_value, "sync_forward_ms_per_step": ms_sync / args.steps,
                     "sync_api": "FRCNN.forward(host pinned f32, padding='max_detections', return_tensors='np'), one call per step"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM)" if dom == "tcgen05" else "conv_simt_kernel",
+            "roofline": {"bound": "tensor", "kernel": "conv_tc2_kernel (tcgen05/TMEM implicit GEMM, TMA im2col)" if dom == "tcgen05" else "conv_simt_kernel",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                          "traffic": traffic, "traffic_source": traffic_note, "peak_source": pk_src + (", sustained bf16" if "bf16_tflops_sustained" in pk else ""),
                          "launches_per_step": d_n / args.steps, "ms_per_step": d_ms / args.steps,
