@@ -30,16 +30,12 @@ int nchw3_to_nhwc4(const float* x, void* y, DType dt, int N, int H, int W, cudaS
 // K2a (bf16 mode): im2col of the 7x7 s2 p3 stem (frcnn.py:860-868) so that the 3-channel conv becomes
 // a plain [M,192] x [64,192]^T tensor-core GEMM.  Row m = output pixel; k = (kh*7+kw)*3 + c for
 // k < 147, zero for k in [147,192).  One thread per 16-byte chunk (8 consecutive k) of a row.
-__global__ void stem_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ a, int H, int W, int OH, int OW,
-                                   int64_t total) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int chunk = (int)(i % 24);
-  const int64_t m = i / 24;
-  const int ow = (int)(m % OW);
-  const int64_t t = m / OW;
-  const int oh = (int)(t % OH);
-  const int n = (int)(t / OH);
+__global__ void stem_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ a, int H, int W, int OH, int OW) {
+  // grid (ceil(OW*24/256), OH, N): no runtime-divisor or 64-bit index arithmetic per thread
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= OW * 24) return;
+  const int ow = t / 24, chunk = t - ow * 24;
+  const int oh = blockIdx.y, n = blockIdx.z;
   const float* xb = x + (int64_t)n * H * W * 4;
   const int ih0 = oh * 2 - 3, iw0 = ow * 2 - 3;
   float v[8];
@@ -59,13 +55,15 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, bf16* __restrict
   __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
   for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+  const int64_t m = ((int64_t)n * OH + oh) * OW + ow;
   *reinterpret_cast<uint4*>(a + m * 192 + chunk * 8) = o;
 }
 
 int stem_im2col(const float* x_nhwc4, void* a, int N, int H, int W, int OH, int OW, cudaStream_t st) {
-  const int64_t total = (int64_t)N * OH * OW * 24;
-  if (total == 0) return 0;
-  stem_im2col_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(x_nhwc4, (bf16*)a, H, W, OH, OW, total);
+  if ((int64_t)N * OH * OW == 0) return 0;
+  VLTK_CHECK(OH <= 65535 && N <= 65535, "stem_im2col: image too tall / batch too large for the grid");
+  dim3 grid(ceil_div(OW * 24, 256), OH, N);
+  stem_im2col_kernel<<<grid, 256, 0, st>>>(x_nhwc4, (bf16*)a, H, W, OH, OW);
   VLTK_LAUNCH_CHECK();
   return 0;
 }
@@ -75,22 +73,21 @@ int stem_im2col(const float* x_nhwc4, void* a, int N, int H, int W, int OH, int 
 template <typename T>
 __global__ void maxpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W,
                                     int C, int OH, int OW) {
+  // grid (ceil(OW*C/4 / 256), OH, N)
   const int c4 = C / 4;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t tot = (int64_t)N * OH * OW * c4;
-  if (i >= tot) return;
-  int c = (int)(i % c4) * 4;
-  int64_t t = i / c4;
-  int ow = (int)(t % OW); t /= OW;
-  int oh = (int)(t % OH);
-  int n = (int)(t / OH);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= OW * c4) return;
+  const int ow = t / c4, c = (t - ow * c4) * 4;
+  const int oh = blockIdx.y, n = blockIdx.z;
   float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
   const int h0 = oh * 2, w0 = ow * 2;
+#pragma unroll
   for (int dh = 0; dh < 3; ++dh) {
-    int h = h0 + dh;
+    const int h = h0 + dh;
     if (h >= H) break;
+#pragma unroll
     for (int dw = 0; dw < 3; ++dw) {
-      int w = w0 + dw;
+      const int w = w0 + dw;
       if (w >= W) break;
       float4 v = load4(x + (((int64_t)n * H + h) * W + w) * C + c);
       m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
@@ -102,9 +99,9 @@ __global__ void maxpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ y, 
 int maxpool3x3s2_ceil(const void* x, void* y, DType dt, int N, int H, int W, int C, int OH, int OW,
                       cudaStream_t st) {
   VLTK_CHECK(C % 4 == 0, "maxpool: C=%d must be a multiple of 4", C);
-  int64_t tot = (int64_t)N * OH * OW * (C / 4);
-  if (tot == 0) return 0;
-  unsigned grid = (unsigned)ceil_div64(tot, 256);
+  if ((int64_t)N * OH * OW == 0) return 0;
+  VLTK_CHECK(OH <= 65535 && N <= 65535, "maxpool: image too tall / batch too large for the grid");
+  dim3 grid(ceil_div(OW * (C / 4), 256), OH, N);
   if (dt == DT_F32) maxpool3x3s2_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, N, H, W, C, OH, OW);
   else maxpool3x3s2_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)y, N, H, W, C, OH, OW);
   VLTK_LAUNCH_CHECK();

@@ -32,23 +32,26 @@ template <> struct Vec<bf16> {
   }
 };
 
-// One CTA per (roi, output bin), one thread per 16-byte channel vector: 470 k small independent
-// CTAs per batch of 2400 ROIs keep plenty of loads in flight, the bin geometry is CTA-uniform
-// (no per-thread 64-bit index arithmetic), and every access is a coalesced channel run.
+// One CTA per (roi, output row ph).  threadIdx.x walks the 16-byte channel vectors and threadIdx.y splits the
+// P bins of the row, so each thread pools ~P/2 bins whose loads are mutually independent (several L2 requests
+// in flight per thread instead of one exposed latency per tiny CTA), the ROI geometry is computed once per
+// thread, and every access is a coalesced channel run.
 template <typename T>
 __global__ void __launch_bounds__(256)
 roi_pool_kernel(const T* __restrict__ feat, int H, int W, int C, const float* __restrict__ rois,
                 const int* __restrict__ count, const int* __restrict__ bidx, int R, int P, float scale,
                 T* __restrict__ out) {
   using V = Vec<T>;
-  const int c = threadIdx.x * V::N;
-  if (c >= C) return;
-  const int ph = blockIdx.x / P, pw = blockIdx.x - ph * P;
-  const int roi = blockIdx.y;
+  const int cv = C / V::N;
+  const int ph = blockIdx.x, roi = blockIdx.y;
   // engine path: ROI slot r of image n, masked by count[n]; stage path: explicit batch index
   const int n = bidx ? bidx[roi] : roi / R, r = roi - (roi / R) * R;
-  T* o = out + (((int64_t)roi * P + ph) * P + pw) * C + c;
-  if (!bidx && r >= count[n]) { V::fill(0.f).store(o); return; }
+  T* orow = out + ((int64_t)roi * P + ph) * P * C;
+  if (!bidx && r >= count[n]) {
+    for (int pw = threadIdx.y; pw < P; pw += blockDim.y)
+      for (int c = threadIdx.x; c < cv; c += blockDim.x) V::fill(0.f).store(orow + (int64_t)pw * C + c * V::N);
+    return;
+  }
   const float4 b = reinterpret_cast<const float4*>(rois)[roi];
   // round half away from zero of the float product (C `round`)
   const int sw = (int)roundf(b.x * scale), sh = (int)roundf(b.y * scale);
@@ -56,18 +59,22 @@ roi_pool_kernel(const T* __restrict__ feat, int H, int W, int C, const float* __
   const int rw = max(ew - sw + 1, 1), rh = max(eh - sh + 1, 1);
   const float bin_h = (float)rh / (float)P, bin_w = (float)rw / (float)P;
   int hs = (int)floorf((float)ph * bin_h) + sh, he = (int)ceilf((float)(ph + 1) * bin_h) + sh;
-  int ws = (int)floorf((float)pw * bin_w) + sw, we = (int)ceilf((float)(pw + 1) * bin_w) + sw;
   hs = min(max(hs, 0), H); he = min(max(he, 0), H);
-  ws = min(max(ws, 0), W); we = min(max(we, 0), W);
-  if (he <= hs || we <= ws) { V::fill(0.f).store(o); return; }   // empty bin -> 0
-  const T* f = feat + (int64_t)n * H * W * C + c;
-  V m = V::fill(-INFINITY);
-  for (int h = hs; h < he; ++h) {
-    const T* row = f + (int64_t)h * W * C;
+  const T* f = feat + (int64_t)n * H * W * C;
+  for (int c = threadIdx.x; c < cv; c += blockDim.x) {
+    const T* fc = f + c * V::N;
 #pragma unroll 4
-    for (int w = ws; w < we; ++w) m.max_with(V::load(row + (int64_t)w * C));
+    for (int pw = threadIdx.y; pw < P; pw += blockDim.y) {
+      int ws = (int)floorf((float)pw * bin_w) + sw, we = (int)ceilf((float)(pw + 1) * bin_w) + sw;
+      ws = min(max(ws, 0), W); we = min(max(we, 0), W);
+      V m = (he <= hs || we <= ws) ? V::fill(0.f) : V::fill(-INFINITY);   // empty bin -> 0
+      for (int h = hs; h < he; ++h) {
+        const T* row = fc + (int64_t)h * W * C;
+        for (int w = ws; w < we; ++w) m.max_with(V::load(row + (int64_t)w * C));
+      }
+      m.store(orow + (int64_t)pw * C + c * V::N);
+    }
   }
-  m.store(o);
 }
 
 }  // namespace
@@ -77,11 +84,11 @@ int roi_pool(const void* feat, DType dt, int N, int H, int W, int C, const float
   VLTK_CHECK(C % 8 == 0, "roi_pool: C=%d must be a multiple of 8", C);
   if (N * R == 0) return 0;
   if (dt == DT_F32) {
-    VLTK_CHECK(C / 4 <= 256, "roi_pool: C=%d too large for one CTA per bin", C);
-    roi_pool_kernel<float><<<dim3(P * P, N * R), round_up(C / 4, 32), 0, st>>>((const float*)feat, H, W, C, rois, count, nullptr, R, P, scale, (float*)out);
+    const int tx = min(128, round_up(C / 4, 32));
+    roi_pool_kernel<float><<<dim3(P, N * R), dim3(tx, 256 / tx), 0, st>>>((const float*)feat, H, W, C, rois, count, nullptr, R, P, scale, (float*)out);
   } else {
-    VLTK_CHECK(C / 8 <= 256, "roi_pool: C=%d too large for one CTA per bin", C);
-    roi_pool_kernel<bf16><<<dim3(P * P, N * R), round_up(C / 8, 32), 0, st>>>((const bf16*)feat, H, W, C, rois, count, nullptr, R, P, scale, (bf16*)out);
+    const int tx = min(128, round_up(C / 8, 32));
+    roi_pool_kernel<bf16><<<dim3(P, N * R), dim3(tx, 256 / tx), 0, st>>>((const bf16*)feat, H, W, C, rois, count, nullptr, R, P, scale, (bf16*)out);
   }
   VLTK_LAUNCH_CHECK();
   return 0;
@@ -92,8 +99,8 @@ int roi_pool_indexed(const void* feat, DType dt, int H, int W, int C, const floa
   VLTK_CHECK(C % 4 == 0, "roi_pool: C=%d must be a multiple of 4", C);
   VLTK_CHECK(dt == DT_F32, "roi_pool_indexed: f32 only");
   if (R == 0) return 0;
-  VLTK_CHECK(C / 4 <= 256, "roi_pool: C=%d too large for one CTA per bin", C);
-  roi_pool_kernel<float><<<dim3(P * P, R), round_up(C / 4, 32), 0, st>>>((const float*)feat, H, W, C, boxes, nullptr, bidx, R, P, scale, (float*)out);
+  const int tx = min(128, round_up(C / 4, 32));
+  roi_pool_kernel<float><<<dim3(P, R), dim3(tx, 256 / tx), 0, st>>>((const float*)feat, H, W, C, boxes, nullptr, bidx, R, P, scale, (float*)out);
   VLTK_LAUNCH_CHECK();
   return 0;
 }
