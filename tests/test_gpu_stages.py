@@ -172,6 +172,25 @@ def test_nms_matches_oracle_exactly(dev, n, thr, seed):
     assert np.array_equal(keep, ref)
 
 
+def test_nms_prefix_schedule_falls_back_exactly(dev):
+    """For K > 1024 the kernels first run on the 1024 best candidates (greedy NMS decisions only look
+    backwards, so a prefix is exact) and recompute everything, guarded by a device flag, only when that
+    prefix holds fewer than max_keep survivors.  Here the top 1024 scores are near-duplicates of 40 boxes, so
+    the prefix yields ~40 survivors and the fallback MUST produce the rest."""
+    from vltk_b200 import stages
+    g = torch.Generator().manual_seed(11)
+    base = _rand_boxes(40, 12, span=900.0)
+    dup = base[torch.randint(0, 40, (1024,), generator=g)] + torch.rand(1024, 4, generator=g) * 0.5
+    rest = _rand_boxes(4976, 13, span=1200.0)
+    boxes = torch.cat([dup, rest])
+    scores = torch.cat([torch.rand(1024, generator=g) + 2.0, torch.rand(4976, generator=g)])   # duplicates rank first
+    ref = O.nms_np(boxes.numpy(), scores.numpy(), 0.7)
+    assert (np.sort(ref[:60]) < 1024).sum() <= 45 and len(ref) > 300    # the prefix alone is far short of 300
+    for mk in (300, 50, 30):   # 300: fallback needed; 30: satisfied inside the prefix
+        keep = stages.nms(boxes.to(dev), scores.to(dev), 0.7, max_keep=mk).cpu().numpy()
+        assert np.array_equal(keep, ref[:mk]), mk
+
+
 def test_nms_edge_cases(dev):
     from vltk_b200 import stages
     # duplicates with tied scores: the lower index survives (stable order); zero-area boxes give

@@ -488,7 +488,7 @@ static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void*
 enum {
   B_IN4, B_STEM, B_POOL, B_A, B_B, B_T1, B_T2, B_S, B_RPNH, B_HEAD, B_SIZES, B_SCALES, B_SBOX, B_SSCORE,
   B_SIDX, B_SVALID, B_MASK, B_PROP, B_PSCORE, B_PIDX, B_COUNT, B_POOLED, B_R5A, B_R5B, B_R5T1, B_R5T2,
-  B_R5S, B_FEATS, B_CLS, B_BBOX, B_ARGMAX, B_TG, B_AH, B_ATTR, B_FHI, B_FLO, B_AHHI, B_AHLO, B_STEMA, B_PARTIAL, B_NUM
+  B_R5S, B_FEATS, B_CLS, B_BBOX, B_ARGMAX, B_TG, B_AH, B_ATTR, B_FHI, B_FLO, B_AHHI, B_AHLO, B_STEMA, B_PARTIAL, B_NMSDONE, B_NUM
 };
 
 static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void** p) {
@@ -528,6 +528,7 @@ static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void*
   p[B_AHHI] = b.take((size_t)NR * (D / 4) * 2); p[B_AHLO] = b.take((size_t)NR * (D / 4) * 2);
   p[B_STEMA] = b.take(h->stem_tc.w_nk ? (size_t)N * s.Hs * s.Ws * 192 * 2 : 0);
   p[B_PARTIAL] = b.take(h->use_tc ? conv_tc_pool_partial_bytes((int64_t)NR * PP, D) : 0);
+  p[B_NMSDONE] = b.take((size_t)N * 4);
   return b.off + 256;
 }
 
@@ -622,10 +623,10 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   na.boxes = ra.boxes; na.scores = ra.scores; na.valid = ra.valid; na.N = n; na.K = s.K;
   na.thresh = c.rpn_nms_thresh; na.max_keep = s.R; na.mask = (unsigned long long*)p[B_MASK];
   na.out_boxes = (float*)p[B_PROP]; na.out_scores = (float*)p[B_PSCORE]; na.out_idx = (int*)p[B_PIDX];
-  na.out_count = (int*)p[B_COUNT];
+  na.out_count = (int*)p[B_COUNT]; na.done = (int*)p[B_NMSDONE];
   { StageTimer t(h, K_NMS, (double)n * s.K * 20.0 + (double)n * s.R * 20.0, st);
     if (nms_sorted(na, st)) return -1; }
-  h->launches += 3;
+  h->launches += (s.K > 1024) ? 5 : 3;   // select + (prefix mask/scan + guarded full mask/scan | mask/scan)
   tap(h, "topk_anchor_idx", p[B_SIDX], (int64_t)n * s.K, DT_F32);  // int32 payload, read raw
   tap(h, "proposals", p[B_PROP], (int64_t)n * s.R * 4, DT_F32);
   tap(h, "proposal_logits", p[B_PSCORE], (int64_t)n * s.R, DT_F32);
@@ -920,6 +921,8 @@ int vltk_rpn_proposals(const float* logits, const float* deltas, const float* ce
   VLTK_CUDA(cudaMalloc(&valid, (size_t)n * K));
   VLTK_CUDA(cudaMalloc(&mask, nms_mask_bytes(n, K)));
   VLTK_CUDA(cudaMalloc(&pidx, (size_t)n * post_topk * 4));
+  int* done = nullptr;
+  VLTK_CUDA(cudaMalloc(&done, (size_t)n * 4));
   if (!proposal_logits) VLTK_CUDA(cudaMalloc(&psc, (size_t)n * post_topk * 4));
   VLTK_CUDA(cudaMemcpyAsync(cell, cell_host, (size_t)a * 16, cudaMemcpyHostToDevice, st));
   VLTK_CUDA(cudaMemcpyAsync(sizes, sizes_hw, (size_t)n * 8, cudaMemcpyHostToDevice, st));
@@ -937,9 +940,10 @@ int vltk_rpn_proposals(const float* logits, const float* deltas, const float* ce
   memset(&na, 0, sizeof(na));
   na.boxes = sbox; na.scores = ssc; na.valid = valid; na.N = n; na.K = K; na.thresh = nms_thresh; na.max_keep = post_topk;
   na.mask = mask; na.out_boxes = proposals; na.out_scores = proposal_logits ? proposal_logits : psc; na.out_idx = pidx;
-  na.out_count = counts;
+  na.out_count = counts; na.done = done;
   if (!rc) rc = nms_sorted(na, st);
   cudaStreamSynchronize(st);
+  cudaFree(done);
   cudaFree(head); cudaFree(cell); cudaFree(sizes); cudaFree(sbox); cudaFree(ssc); cudaFree(sidx);
   cudaFree(valid); cudaFree(mask); cudaFree(pidx); if (psc) cudaFree(psc);
   return rc;
@@ -959,14 +963,17 @@ int vltk_nms(const float* boxes, const float* scores, int k, float thresh, int m
   VLTK_CUDA(cudaMalloc(&obox, (size_t)max_keep * 16));
   VLTK_CUDA(cudaMalloc(&oidx, (size_t)max_keep * 4));
   VLTK_CUDA(cudaMalloc(&mask, nms_mask_bytes(1, std::max(k, 1))));
+  int* done = nullptr;
+  VLTK_CUDA(cudaMalloc(&done, 4));
   int rc = sort_boxes_desc(boxes, scores, k, sbox, ssc, order, st);
   NmsArgs na;
   memset(&na, 0, sizeof(na));
   na.boxes = sbox; na.scores = ssc; na.valid = nullptr; na.N = 1; na.K = k; na.thresh = thresh; na.max_keep = max_keep;
-  na.mask = mask; na.out_boxes = obox; na.out_scores = nullptr; na.out_idx = oidx; na.out_count = count;
+  na.mask = mask; na.out_boxes = obox; na.out_scores = nullptr; na.out_idx = oidx; na.out_count = count; na.done = done;
   if (!rc) rc = nms_sorted(na, st);
   if (!rc) rc = remap_indices(oidx, order, max_keep, keep, st);
   cudaStreamSynchronize(st);
+  cudaFree(done);
   cudaFree(sbox); cudaFree(ssc); cudaFree(order); cudaFree(obox); cudaFree(oidx); cudaFree(mask);
   return rc;
 }

@@ -47,6 +47,7 @@ struct NmsArgs {
   float thresh;
   int max_keep;
   unsigned long long* mask;  // workspace [N, K, ceil(K/64)]
+  int* done;                 // workspace [N] or nullptr: enables the exact prefix-first schedule for K > 1024
   // outputs
   float* out_boxes;       // [N, max_keep, 4]  (zero-filled past count)
   float* out_scores;      // [N, max_keep]

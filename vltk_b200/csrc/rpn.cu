@@ -158,60 +158,68 @@ __device__ __forceinline__ bool iou_gt(const float4& a, float area_a, const floa
   return ovr > thr;  // NaN (0/0) never suppresses
 }
 
-// grid (KB, KB, N), 64 threads: row block y vs column block x (upper triangle only)
+// grid (KBe, KBe, N), 64 threads: row block y vs column block x (upper triangle only) over the first Ke
+// candidates; the mask row stride stays KB words.  Images whose `done` flag is set are skipped.
 __global__ void __launch_bounds__(64)
-nms_mask_kernel(const float* __restrict__ boxes, int K, int KB, float thr,
-                unsigned long long* __restrict__ mask) {
+nms_mask_kernel(const float* __restrict__ boxes, int K, int Ke, int KB, float thr,
+                unsigned long long* __restrict__ mask, const int* __restrict__ done) {
   const int cb = blockIdx.x, rb = blockIdx.y, n = blockIdx.z;
   if (cb < rb) return;
+  if (done && done[n]) return;
   __shared__ float4 cbox[64];
   __shared__ float carea[64];
   const int tid = threadIdx.x;
   const float4* b4 = reinterpret_cast<const float4*>(boxes) + (int64_t)n * K;
   const int j0 = cb * 64;
-  if (j0 + tid < K) {
+  if (j0 + tid < Ke) {
     float4 b = b4[j0 + tid];
     cbox[tid] = b;
     carea[tid] = (b.z - b.x) * (b.w - b.y);
   }
   __syncthreads();
   const int i = rb * 64 + tid;
-  if (i >= K) return;
+  if (i >= Ke) return;
   const float4 me = b4[i];
   const float area = (me.z - me.x) * (me.w - me.y);
   unsigned long long bits = 0ull;
-  const int lim = min(64, K - j0);
+  const int lim = min(64, Ke - j0);
   for (int b = 0; b < lim; ++b) {
     if (j0 + b > i && iou_gt(me, area, cbox[b], carea[b], thr)) bits |= 1ull << b;
   }
   mask[((int64_t)n * K + i) * KB + cb] = bits;
 }
 
-// one CTA per image; thread t owns the 64-bit "removed" word of chunk t
+// One CTA per image; thread t owns the 64-bit "removed" word of chunk t.  Scans the first Ke candidates.
+//   phase 1 (Ke < K, done_out != nullptr): greedy NMS decisions for candidate j depend only on candidates
+//     before j, so the prefix result is exact; if it already holds max_keep survivors the image is DONE
+//     (done_out[n] = 1 and outputs are written), otherwise done_out[n] = 0 and nothing is written;
+//   phase 2 / single phase (Ke == K): skipped for images flagged in done_in, else the full scan.
 __global__ void __launch_bounds__(128)
-nms_scan_kernel(NmsArgs a, int KB) {
+nms_scan_kernel(NmsArgs a, int KB, int Ke, const int* __restrict__ done_in, int* __restrict__ done_out) {
   __shared__ unsigned long long diag[64];
   __shared__ unsigned long long s_kept_bits;
   __shared__ int s_count;
   extern __shared__ int kept_list[];  // max_keep ints
   const int tid = threadIdx.x, n = blockIdx.x, K = a.K;
+  if (done_in && done_in[n]) return;
+  const int KBe = (Ke + 63) / 64;
   const unsigned long long* __restrict__ mask = a.mask + (int64_t)n * K * KB;
 
   unsigned long long removed = 0ull;
-  if (tid < KB) {
+  if (tid < KBe) {
     for (int b = 0; b < 64; ++b) {
       int j = tid * 64 + b;
-      bool ok = j < K && (a.valid == nullptr || a.valid[(int64_t)n * K + j]);
+      bool ok = j < Ke && (a.valid == nullptr || a.valid[(int64_t)n * K + j]);
       if (!ok) removed |= 1ull << b;
     }
   }
   if (tid == 0) s_count = 0;
   __syncthreads();
 
-  for (int c = 0; c < KB; ++c) {
+  for (int c = 0; c < KBe; ++c) {
     if (tid < 64) {
       int i = c * 64 + tid;
-      diag[tid] = (i < K) ? mask[(int64_t)i * KB + c] : 0ull;
+      diag[tid] = (i < Ke) ? mask[(int64_t)i * KB + c] : 0ull;
     }
     __syncthreads();
     if (tid == c) {  // owner of this chunk resolves it serially
@@ -230,18 +238,32 @@ nms_scan_kernel(NmsArgs a, int KB) {
     __syncthreads();
     if (s_count >= a.max_keep) break;
     unsigned long long kb = s_kept_bits;
-    if (tid > c && tid < KB) {
+    if (tid > c && tid < KBe) {
+      // OR the kept rows' masks into this thread's word, 8 INDEPENDENT loads at a time (one load per
+      // iteration of a data-dependent loop serialised ~64 L2 latencies per chunk and was the whole cost)
       while (kb) {
-        int b = __ffsll((long long)kb) - 1;
-        kb &= kb - 1;
-        removed |= mask[(int64_t)(c * 64 + b) * KB + tid];
+        unsigned long long v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = 0ull;
+          if (kb) {
+            const int b = __ffsll((long long)kb) - 1;
+            kb &= kb - 1;
+            v[j] = mask[(int64_t)(c * 64 + b) * KB + tid];
+          }
+        }
+        removed |= ((v[0] | v[1]) | (v[2] | v[3])) | ((v[4] | v[5]) | (v[6] | v[7]));
       }
     }
-    // diag / s_kept_bits are rewritten only after the next iteration's barriers
     __syncthreads();
   }
   __syncthreads();
   const int cnt = s_count;
+  if (done_out) {
+    const bool fin = cnt >= a.max_keep || Ke >= K;
+    if (tid == 0) done_out[n] = fin ? 1 : 0;
+    if (!fin) return;                 // uniform: the full phase will produce this image
+  }
   if (tid == 0) a.out_count[n] = cnt;
   for (int t = tid; t < a.max_keep; t += blockDim.x) {
     const int64_t o = (int64_t)n * a.max_keep + t;
@@ -339,12 +361,27 @@ int nms_sorted(const NmsArgs& a, cudaStream_t st) {
   VLTK_CHECK(KB <= 128, "nms: K=%d too large (max 8192)", a.K);
   VLTK_CHECK(a.max_keep <= 8192, "nms: max_keep too large");
   if (a.N == 0) return 0;
+  const size_t sm = a.max_keep * sizeof(int);
+  constexpr int PREFIX = 1024;   // the first max_keep survivors almost always sit in the first ~1k candidates
+  if (a.done && a.K > PREFIX) {
+    const int KBp = PREFIX / 64;
+    nms_mask_kernel<<<dim3(KBp, KBp, a.N), 64, 0, st>>>(a.boxes, a.K, PREFIX, KB, a.thresh, a.mask, nullptr);
+    VLTK_LAUNCH_CHECK();
+    nms_scan_kernel<<<a.N, 128, sm, st>>>(a, KB, PREFIX, nullptr, a.done);
+    VLTK_LAUNCH_CHECK();
+    // exact fallback for images whose prefix did not yield max_keep survivors (no host sync: blocks of
+    // finished images exit on the device flag)
+    nms_mask_kernel<<<dim3(KB, KB, a.N), 64, 0, st>>>(a.boxes, a.K, a.K, KB, a.thresh, a.mask, a.done);
+    VLTK_LAUNCH_CHECK();
+    nms_scan_kernel<<<a.N, 128, sm, st>>>(a, KB, a.K, a.done, nullptr);
+    VLTK_LAUNCH_CHECK();
+    return 0;
+  }
   if (a.K > 0) {
-    dim3 grid(KB, KB, a.N);
-    nms_mask_kernel<<<grid, 64, 0, st>>>(a.boxes, a.K, KB, a.thresh, a.mask);
+    nms_mask_kernel<<<dim3(KB, KB, a.N), 64, 0, st>>>(a.boxes, a.K, a.K, KB, a.thresh, a.mask, nullptr);
     VLTK_LAUNCH_CHECK();
   }
-  nms_scan_kernel<<<a.N, 128, a.max_keep * sizeof(int), st>>>(a, KB);
+  nms_scan_kernel<<<a.N, 128, sm, st>>>(a, KB, a.K, nullptr, nullptr);
   VLTK_LAUNCH_CHECK();
   return 0;
 }
