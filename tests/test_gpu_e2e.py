@@ -224,6 +224,35 @@ def test_full_batch8_equals_smaller_batches(mode):
         np.testing.assert_allclose(full["boxes"][:2].reshape(-1, 4), g["boxes"], rtol=0, atol=1e-2)
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_maximum_canvas_1333x1333(mode):
+    """Maximum sizes: a landscape 800x1333 and a portrait 1333x800 image in one batch pad to the largest canvas
+    the 800/1333 resize rule can produce (1333x1333, res4 84x84 = 105 840 anchors per image).  Checked through
+    properties: every image equals itself run alone on the same canvas (bit-exact), clipping respects each
+    image's own (h, w), detections are full, and the result is reproducible after interleaved smaller calls."""
+    from vltk_b200 import synthetic
+    model, cfg = get_model("cfg1", mode)
+    mean = torch.tensor(cfg.pixel_mean).view(3, 1, 1)
+    x = torch.zeros(2, 3, 1333, 1333)
+    shapes = [(800, 1333), (1333, 800)]
+    for i, (h, w) in enumerate(shapes):
+        x[i, :, :h, :w] = synthetic.make_raw_image(h, w, 60 + i).permute(2, 0, 1).float() - mean
+    sizes = torch.tensor(shapes)
+    scales = torch.tensor([[0.5, 0.5], [1.25, 1.25]])
+    both = model(x, sizes, scales_yx=scales, padding="max_detections", return_tensors="np")
+    assert both["preds_per_image"].tolist() == [36, 36]
+    for i, (h, w) in enumerate(shapes):
+        one = model(x[i:i + 1].contiguous(), sizes[i:i + 1], scales_yx=scales[i:i + 1], padding="max_detections", return_tensors="np")
+        for k in ("obj_ids", "attr_ids", "boxes", "roi_features", "obj_probs", "keep_idx"):
+            assert np.array_equal(one[k][0], both[k][i]), (mode, i, k)
+        b = both["boxes"][i] / np.array([scales[i, 1], scales[i, 0], scales[i, 1], scales[i, 0]], np.float32)
+        assert (b[:, 0::2] >= 0).all() and (b[:, 0::2] <= w + 1e-3).all()     # clipped to THIS image's width ...
+        assert (b[:, 1::2] >= 0).all() and (b[:, 1::2] <= h + 1e-3).all()     # ... and height, not the canvas
+        assert (both["normalized_boxes"][i] <= 1.0 + 1e-5).all()
+    again = model(x, sizes, scales_yx=scales, padding="max_detections", return_tensors="np")
+    assert np.array_equal(again["roi_features"], both["roi_features"])      # reproducible after the smaller calls above
+
+
 def test_forward_stream_equals_forward():
     """The pipelined public API (H2D / compute / D2H of neighbouring batches overlapped on three streams)
     must return, in order, exactly what one synchronous forward() per batch returns — including across
