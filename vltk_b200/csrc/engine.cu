@@ -254,6 +254,26 @@ int run_conv(vltk_frcnn* h, const LayerW& L, const void* x, DType xdt, int N, in
   return rc;
 }
 
+// Scratch of the stage entry points (tests / microbenchmarks): released on EVERY exit path, after the stream
+// has drained — an early error return must not leak device memory or free buffers a queued kernel still uses.
+struct Scratch {
+  cudaStream_t st;
+  std::vector<void*> ptrs;
+  explicit Scratch(cudaStream_t s) : st(s) {}
+  Scratch(const Scratch&) = delete;
+  Scratch& operator=(const Scratch&) = delete;
+  ~Scratch() {
+    cudaStreamSynchronize(st);
+    for (void* q : ptrs) cudaFree(q);
+  }
+  template <typename T>
+  cudaError_t get(T** out, size_t bytes) {
+    cudaError_t e = cudaMalloc((void**)out, bytes ? bytes : 16);
+    if (e == cudaSuccess) ptrs.push_back((void*)*out);
+    return e;
+  }
+};
+
 // Brackets a non-GEMM launch with events when profiling (kind >= 2; `bytes` = algorithmic bytes moved)
 struct StageTimer {
   vltk_frcnn* h; cudaStream_t st; bool on;
@@ -801,6 +821,7 @@ int vltk_conv2d_nhwc(const void* x, const float* weight, const float* scale, con
   VLTK_CHECK(kh == kw, "conv2d: square kernels only");
   VLTK_CHECK(cin % 4 == 0 && cout % 4 == 0, "conv2d: cin/cout must be multiples of 4 for the stage entry");
   cudaStream_t st = (cudaStream_t)stream;
+  Scratch scratch(st);
   const DType d = mode == VLTK_MODE_BF16 ? DT_BF16 : DT_F32;
   ConvProblem p;
   memset(&p, 0, sizeof(p));
@@ -816,10 +837,10 @@ int vltk_conv2d_nhwc(const void* x, const float* weight, const float* scale, con
     const int cout_pad = round_up(cout, 64);
     bf16* w_nk = nullptr;
     float *sc = nullptr, *sh = nullptr;
-    VLTK_CUDA(cudaMalloc(&w_nk, (size_t)cout_pad * K * 2));
+    VLTK_CUDA(scratch.get(&w_nk, (size_t)cout_pad * K * 2));
     VLTK_CUDA(cudaMemsetAsync(w_nk, 0, (size_t)cout_pad * K * 2, st));
-    VLTK_CUDA(cudaMalloc(&sc, (size_t)cout_pad * 4));
-    VLTK_CUDA(cudaMalloc(&sh, (size_t)cout_pad * 4));
+    VLTK_CUDA(scratch.get(&sc, (size_t)cout_pad * 4));
+    VLTK_CUDA(scratch.get(&sh, (size_t)cout_pad * 4));
     rc = pack_weight_nk(weight, w_nk, cout, cin, kh * kw, st);
     if (!rc) rc = pad_vector(scale, sc, cout, cout_pad, 1.f, st);
     if (!rc) rc = pad_vector(shift, sh, cout, cout_pad, 0.f, st);
@@ -827,15 +848,13 @@ int vltk_conv2d_nhwc(const void* x, const float* weight, const float* scale, con
     TensorMapCache cache;
     if (!rc) rc = conv_tc_launch(p, w_nk, cout_pad, &cache, st);
     cudaStreamSynchronize(st);
-    cudaFree(w_nk); cudaFree(sc); cudaFree(sh);
   } else {
     float* w_kn = nullptr;
-    VLTK_CUDA(cudaMalloc(&w_kn, (size_t)K_pad * cout * 4));
+    VLTK_CUDA(scratch.get(&w_kn, (size_t)K_pad * cout * 4));
     VLTK_CUDA(cudaMemsetAsync(w_kn, 0, (size_t)K_pad * cout * 4, st));
     rc = pack_weight_kn(weight, w_kn, cout, cin, kh * kw, cout, d == DT_BF16, st);
     if (!rc) rc = conv_simt_launch(p, w_kn, cout, st);
     cudaStreamSynchronize(st);
-    cudaFree(w_kn);
   }
   return rc;
 }
@@ -846,6 +865,7 @@ int vltk_conv2d_meanpool_nhwc(const void* x, const float* weight, const float* s
   VLTK_CHECK(x && weight && residual && pooled, "conv2d_meanpool: null argument");
   VLTK_CHECK(cin % 64 == 0 && cout % 256 == 0, "conv2d_meanpool: cin %% 64 and cout %% 256 required");
   cudaStream_t st = (cudaStream_t)stream;
+  Scratch scratch(st);
   ConvProblem p;
   memset(&p, 0, sizeof(p));
   p.x = x; p.ldx = cin; p.residual = residual; p.ldr = cout; p.ldy = cout;
@@ -857,11 +877,11 @@ int vltk_conv2d_meanpool_nhwc(const void* x, const float* weight, const float* s
   const int K = kh * kh * cin;
   bf16 *w_nk = nullptr, *ydummy = nullptr;
   float *sc = nullptr, *sh = nullptr, *partial = nullptr;
-  VLTK_CUDA(cudaMalloc(&w_nk, (size_t)cout * K * 2));
-  VLTK_CUDA(cudaMalloc(&ydummy, (size_t)128 * cout * 2));        // tensor map target only: never written
-  VLTK_CUDA(cudaMalloc(&sc, (size_t)cout * 4));
-  VLTK_CUDA(cudaMalloc(&sh, (size_t)cout * 4));
-  VLTK_CUDA(cudaMalloc(&partial, conv_tc_pool_partial_bytes(M, cout)));
+  VLTK_CUDA(scratch.get(&w_nk, (size_t)cout * K * 2));
+  VLTK_CUDA(scratch.get(&ydummy, (size_t)128 * cout * 2));        // tensor map target only: never written
+  VLTK_CUDA(scratch.get(&sc, (size_t)cout * 4));
+  VLTK_CUDA(scratch.get(&sh, (size_t)cout * 4));
+  VLTK_CUDA(scratch.get(&partial, conv_tc_pool_partial_bytes(M, cout)));
   p.y = ydummy;
   int rc = pack_weight_nk(weight, w_nk, cout, cin, kh * kh, st);
   if (!rc) rc = pad_vector(scale, sc, cout, cout, 1.f, st);
@@ -871,7 +891,6 @@ int vltk_conv2d_meanpool_nhwc(const void* x, const float* weight, const float* s
   TensorMapCache cache;
   if (!rc) rc = conv_tc_launch(p, w_nk, cout, &cache, st, nullptr, &pool);
   cudaStreamSynchronize(st);
-  cudaFree(w_nk); cudaFree(ydummy); cudaFree(sc); cudaFree(sh); cudaFree(partial);
   return rc;
 }
 
@@ -880,11 +899,12 @@ int vltk_linear_tc3(const float* x, const float* weight, const float* bias, floa
   VLTK_CHECK(x && weight && y, "linear_tc3: null argument");
   VLTK_CHECK(k % 64 == 0 && n % 64 == 0, "linear_tc3: k and n must be multiples of 64");
   cudaStream_t st = (cudaStream_t)stream;
+  Scratch scratch(st);
   bf16 *xhi = nullptr, *xlo = nullptr, *whi = nullptr, *wlo = nullptr;
   float* sh = nullptr;
-  VLTK_CUDA(cudaMalloc(&xhi, (size_t)m * k * 2)); VLTK_CUDA(cudaMalloc(&xlo, (size_t)m * k * 2));
-  VLTK_CUDA(cudaMalloc(&whi, (size_t)n * k * 2)); VLTK_CUDA(cudaMalloc(&wlo, (size_t)n * k * 2));
-  VLTK_CUDA(cudaMalloc(&sh, (size_t)n * 4));
+  VLTK_CUDA(scratch.get(&xhi, (size_t)m * k * 2)); VLTK_CUDA(scratch.get(&xlo, (size_t)m * k * 2));
+  VLTK_CUDA(scratch.get(&whi, (size_t)n * k * 2)); VLTK_CUDA(scratch.get(&wlo, (size_t)n * k * 2));
+  VLTK_CUDA(scratch.get(&sh, (size_t)n * 4));
   int rc = split_f32(x, nullptr, 0, xhi, xlo, (int64_t)m * k, st);
   if (!rc) rc = split_f32(weight, nullptr, 0, whi, wlo, (int64_t)n * k, st);   // [n][k] is already the B layout
   if (!rc) rc = pad_vector(bias, sh, n, n, 0.f, st);
@@ -896,7 +916,6 @@ int vltk_linear_tc3(const float* x, const float* weight, const float* bias, floa
   TensorMapCache cache;
   if (!rc) rc = conv_tc_launch(q, whi, n, &cache, st, &sp);
   cudaStreamSynchronize(st);
-  cudaFree(xhi); cudaFree(xlo); cudaFree(whi); cudaFree(wlo); cudaFree(sh);
   return rc;
 }
 
@@ -907,23 +926,24 @@ int vltk_rpn_proposals(const float* logits, const float* deltas, const float* ce
   VLTK_CHECK(logits && deltas && cell_host && sizes_hw && proposals && counts, "rpn_proposals: null argument");
   VLTK_CHECK(pre_topk >= 1 && pre_topk <= 8192 && post_topk >= 1 && post_topk <= 8192, "rpn_proposals: topk out of range");
   cudaStream_t st = (cudaStream_t)stream;
+  Scratch scratch(st);
   const int HW = h4 * w4, ldh = round_up(5 * a, 4), K = std::min(pre_topk, HW * a);
   float *head = nullptr, *cell = nullptr, *sbox = nullptr, *ssc = nullptr, *psc = nullptr;
   int *sizes = nullptr, *sidx = nullptr, *pidx = nullptr;
   uint8_t* valid = nullptr;
   unsigned long long* mask = nullptr;
-  VLTK_CUDA(cudaMalloc(&head, (size_t)n * HW * ldh * 4));
-  VLTK_CUDA(cudaMalloc(&cell, (size_t)a * 16));
-  VLTK_CUDA(cudaMalloc(&sizes, (size_t)n * 8));
-  VLTK_CUDA(cudaMalloc(&sbox, (size_t)n * K * 16));
-  VLTK_CUDA(cudaMalloc(&ssc, (size_t)n * K * 4));
-  VLTK_CUDA(cudaMalloc(&sidx, (size_t)n * K * 4));
-  VLTK_CUDA(cudaMalloc(&valid, (size_t)n * K));
-  VLTK_CUDA(cudaMalloc(&mask, nms_mask_bytes(n, K)));
-  VLTK_CUDA(cudaMalloc(&pidx, (size_t)n * post_topk * 4));
+  VLTK_CUDA(scratch.get(&head, (size_t)n * HW * ldh * 4));
+  VLTK_CUDA(scratch.get(&cell, (size_t)a * 16));
+  VLTK_CUDA(scratch.get(&sizes, (size_t)n * 8));
+  VLTK_CUDA(scratch.get(&sbox, (size_t)n * K * 16));
+  VLTK_CUDA(scratch.get(&ssc, (size_t)n * K * 4));
+  VLTK_CUDA(scratch.get(&sidx, (size_t)n * K * 4));
+  VLTK_CUDA(scratch.get(&valid, (size_t)n * K));
+  VLTK_CUDA(scratch.get(&mask, nms_mask_bytes(n, K)));
+  VLTK_CUDA(scratch.get(&pidx, (size_t)n * post_topk * 4));
   int* done = nullptr;
-  VLTK_CUDA(cudaMalloc(&done, (size_t)n * 4));
-  if (!proposal_logits) VLTK_CUDA(cudaMalloc(&psc, (size_t)n * post_topk * 4));
+  VLTK_CUDA(scratch.get(&done, (size_t)n * 4));
+  if (!proposal_logits) VLTK_CUDA(scratch.get(&psc, (size_t)n * post_topk * 4));
   VLTK_CUDA(cudaMemcpyAsync(cell, cell_host, (size_t)a * 16, cudaMemcpyHostToDevice, st));
   VLTK_CUDA(cudaMemcpyAsync(sizes, sizes_hw, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   int64_t t1 = (int64_t)n * 4 * a * HW, t2 = (int64_t)n * a * HW;
@@ -943,9 +963,6 @@ int vltk_rpn_proposals(const float* logits, const float* deltas, const float* ce
   na.out_count = counts; na.done = done;
   if (!rc) rc = nms_sorted(na, st);
   cudaStreamSynchronize(st);
-  cudaFree(done);
-  cudaFree(head); cudaFree(cell); cudaFree(sizes); cudaFree(sbox); cudaFree(ssc); cudaFree(sidx);
-  cudaFree(valid); cudaFree(mask); cudaFree(pidx); if (psc) cudaFree(psc);
   return rc;
 }
 
@@ -954,17 +971,18 @@ int vltk_nms(const float* boxes, const float* scores, int k, float thresh, int m
   VLTK_CHECK(boxes && scores && keep && count, "nms: null argument");
   VLTK_CHECK(k >= 0 && k <= 8192 && max_keep >= 1 && max_keep <= 8192, "nms: k must be <= 8192");
   cudaStream_t st = (cudaStream_t)stream;
+  Scratch scratch(st);
   float *sbox = nullptr, *ssc = nullptr, *obox = nullptr;
   int *order = nullptr, *oidx = nullptr;
   unsigned long long* mask = nullptr;
-  VLTK_CUDA(cudaMalloc(&sbox, (size_t)std::max(k, 1) * 16));
-  VLTK_CUDA(cudaMalloc(&ssc, (size_t)std::max(k, 1) * 4));
-  VLTK_CUDA(cudaMalloc(&order, (size_t)std::max(k, 1) * 4));
-  VLTK_CUDA(cudaMalloc(&obox, (size_t)max_keep * 16));
-  VLTK_CUDA(cudaMalloc(&oidx, (size_t)max_keep * 4));
-  VLTK_CUDA(cudaMalloc(&mask, nms_mask_bytes(1, std::max(k, 1))));
+  VLTK_CUDA(scratch.get(&sbox, (size_t)std::max(k, 1) * 16));
+  VLTK_CUDA(scratch.get(&ssc, (size_t)std::max(k, 1) * 4));
+  VLTK_CUDA(scratch.get(&order, (size_t)std::max(k, 1) * 4));
+  VLTK_CUDA(scratch.get(&obox, (size_t)max_keep * 16));
+  VLTK_CUDA(scratch.get(&oidx, (size_t)max_keep * 4));
+  VLTK_CUDA(scratch.get(&mask, nms_mask_bytes(1, std::max(k, 1))));
   int* done = nullptr;
-  VLTK_CUDA(cudaMalloc(&done, 4));
+  VLTK_CUDA(scratch.get(&done, 4));
   int rc = sort_boxes_desc(boxes, scores, k, sbox, ssc, order, st);
   NmsArgs na;
   memset(&na, 0, sizeof(na));
@@ -973,8 +991,6 @@ int vltk_nms(const float* boxes, const float* scores, int k, float thresh, int m
   if (!rc) rc = nms_sorted(na, st);
   if (!rc) rc = remap_indices(oidx, order, max_keep, keep, st);
   cudaStreamSynchronize(st);
-  cudaFree(done);
-  cudaFree(sbox); cudaFree(ssc); cudaFree(order); cudaFree(obox); cudaFree(oidx); cudaFree(mask);
   return rc;
 }
 
@@ -983,14 +999,15 @@ int vltk_roi_pool_nchw(const float* feat, int n, int c, int hh, int ww, const fl
   VLTK_CHECK(feat && rois5 && out, "roi_pool: null argument");
   VLTK_CHECK(c % 4 == 0, "roi_pool: C must be a multiple of 4");
   cudaStream_t st = (cudaStream_t)stream;
+  Scratch scratch(st);
   // the stage entry accepts arbitrary batch indices: pool each ROI as its own "image slot"
   float *nhwc = nullptr, *boxes = nullptr, *tmp = nullptr;
   int *bidx = nullptr, *ones = nullptr;
-  VLTK_CUDA(cudaMalloc(&nhwc, (size_t)n * hh * ww * c * 4));
-  VLTK_CUDA(cudaMalloc(&boxes, (size_t)std::max(r, 1) * 16));
-  VLTK_CUDA(cudaMalloc(&bidx, (size_t)std::max(r, 1) * 4));
-  VLTK_CUDA(cudaMalloc(&ones, (size_t)std::max(n, 1) * 4));
-  VLTK_CUDA(cudaMalloc(&tmp, (size_t)std::max(r, 1) * pp * pp * c * 4));
+  VLTK_CUDA(scratch.get(&nhwc, (size_t)n * hh * ww * c * 4));
+  VLTK_CUDA(scratch.get(&boxes, (size_t)std::max(r, 1) * 16));
+  VLTK_CUDA(scratch.get(&bidx, (size_t)std::max(r, 1) * 4));
+  VLTK_CUDA(scratch.get(&ones, (size_t)std::max(n, 1) * 4));
+  VLTK_CUDA(scratch.get(&tmp, (size_t)std::max(r, 1) * pp * pp * c * 4));
   int64_t tot = (int64_t)n * c * hh * ww;
   nchw_to_nhwc_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(feat, nhwc, c, hh * ww, c, 0, tot);
   int rc = 0;
@@ -1001,7 +1018,6 @@ int vltk_roi_pool_nchw(const float* feat, int n, int c, int hh, int ww, const fl
     nhwc_to_nchw_kernel<<<(unsigned)ceil_div64(to, 256), 256, 0, st>>>(tmp, out, c, pp * pp, to);
   }
   cudaStreamSynchronize(st);
-  cudaFree(nhwc); cudaFree(boxes); cudaFree(bidx); cudaFree(ones); cudaFree(tmp);
   VLTK_LAUNCH_CHECK();
   return rc;
 }
@@ -1013,10 +1029,11 @@ int vltk_roi_outputs(const float* obj_logits, const float* attr_logits, const fl
   VLTK_CHECK(obj_logits && attr_logits && box_deltas && feats && proposals && counts && sizes_hw && knobs && out,
              "roi_outputs: null argument");
   cudaStream_t st = (cudaStream_t)stream;
+  Scratch scratch(st);
   int* sizes = nullptr;
   float* scales = nullptr;
-  VLTK_CUDA(cudaMalloc(&sizes, (size_t)n * 8));
-  VLTK_CUDA(cudaMalloc(&scales, (size_t)n * 8));
+  VLTK_CUDA(scratch.get(&sizes, (size_t)n * 8));
+  VLTK_CUDA(scratch.get(&scales, (size_t)n * 8));
   VLTK_CUDA(cudaMemcpyAsync(sizes, sizes_hw, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   if (scales_yx) VLTK_CUDA(cudaMemcpyAsync(scales, scales_yx, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   TailArgs ta;
@@ -1033,7 +1050,6 @@ int vltk_roi_outputs(const float* obj_logits, const float* attr_logits, const fl
   ta.roi_features = out->roi_features; ta.preds_per_image = out->preds_per_image; ta.keep_idx = out->keep_idx;
   int rc = roi_tail(ta, st);
   cudaStreamSynchronize(st);
-  cudaFree(sizes); cudaFree(scales);
   return rc;
 }
 
