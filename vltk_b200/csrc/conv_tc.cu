@@ -15,6 +15,7 @@
 // (frcnn.py:794-822, 963-979, 1345-1355, 1569).
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "conv_tc.cuh"
 
@@ -413,6 +414,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // Programmatic dependent launch: everything above (smem carve-up, mbarrier init, TMEM allocation, descriptor
+  // prefetch) touched no activation, so it may overlap the previous kernel's tail.  Let OUR successor become
+  // resident as early as SM resources allow, then wait for the predecessor grid to complete and flush before the
+  // first global access of any role.  Each kernel waits for its predecessor's FULL completion, so completion is
+  // transitive along the stream and the engine's ping-pong buffers stay hazard-free.  (No-ops when the kernel
+  // was launched without the attribute.)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
   if (warp == 0 && lane == 0) {
     // ================= TMA producer =================
     int stage = 0; uint32_t phase = 0;
@@ -747,7 +757,15 @@ int launch2(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
   VLTK_CHECK(tiles < (1ll << 31), "conv_tc: too many tiles");
   tp.num_tiles = (int)tiles;
   const int grid = (int)std::min<int64_t>(tiles, num_sms());  // persistent: one CTA per SM
-  conv_tc2_kernel<BN, STAGES, HAS_RES, OUT_F32, POOL><<<grid, TC_THREADS, S::TOTAL, st>>>(m.a, m.a2, m.b, m.b2, m.y, m.r, tp);
+  static const bool use_pdl = [] { const char* e = getenv("VLTK_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+  VLTK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<BN, STAGES, HAS_RES, OUT_F32, POOL>, m.a, m.a2, m.b, m.b2, m.y, m.r, tp));
   VLTK_LAUNCH_CHECK();
   return 0;
 }
