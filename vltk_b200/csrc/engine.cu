@@ -508,7 +508,7 @@ static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void*
 enum {
   B_IN4, B_STEM, B_POOL, B_A, B_B, B_T1, B_T2, B_S, B_RPNH, B_HEAD, B_SIZES, B_SCALES, B_SBOX, B_SSCORE,
   B_SIDX, B_SVALID, B_MASK, B_PROP, B_PSCORE, B_PIDX, B_COUNT, B_POOLED, B_R5A, B_R5B, B_R5T1, B_R5T2,
-  B_R5S, B_FEATS, B_CLS, B_BBOX, B_ARGMAX, B_TG, B_AH, B_ATTR, B_FHI, B_FLO, B_AHHI, B_AHLO, B_STEMA, B_PARTIAL, B_NMSDONE, B_NUM
+  B_R5S, B_FEATS, B_CLS, B_BBOX, B_ARGMAX, B_TG, B_AH, B_ATTR, B_FHI, B_FLO, B_AHHI, B_AHLO, B_STEMA, B_PARTIAL, B_NMSDONE, B_ROISTAT, B_NUM
 };
 
 static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void** p) {
@@ -549,6 +549,7 @@ static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void*
   p[B_STEMA] = b.take(h->stem_tc.w_nk ? (size_t)N * s.Hs * s.Ws * 192 * 2 : 0);
   p[B_PARTIAL] = b.take(h->use_tc ? conv_tc_pool_partial_bytes((int64_t)NR * PP, D) : 0);
   p[B_NMSDONE] = b.take((size_t)N * 4);
+  p[B_ROISTAT] = b.take((size_t)NR * 32);
   return b.off + 256;
 }
 
@@ -751,9 +752,10 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   ta.boxes = out->boxes; ta.norm_boxes = out->normalized_boxes; ta.obj_ids = (long long*)out->obj_ids;
   ta.obj_probs = out->obj_probs; ta.attr_ids = (long long*)out->attr_ids; ta.attr_probs = out->attr_probs;
   ta.roi_features = out->roi_features; ta.preds_per_image = out->preds_per_image; ta.keep_idx = out->keep_idx;
+  ta.stats = (float*)p[B_ROISTAT];
   { StageTimer t(h, K_TAIL, (double)NR * (ldc + lda + 4 + 4) * 4.0 + (double)n * knobs->max_detections * (D + 12) * 4.0, st);
     if (roi_tail(ta, st)) return -1; }
-  h->launches++;
+  h->launches += 2;   // roi_stats + roi_tail
   return 0;
 }
 
@@ -1048,6 +1050,7 @@ int vltk_roi_outputs(const float* obj_logits, const float* attr_logits, const fl
   ta.boxes = out->boxes; ta.norm_boxes = out->normalized_boxes; ta.obj_ids = (long long*)out->obj_ids;
   ta.obj_probs = out->obj_probs; ta.attr_ids = (long long*)out->attr_ids; ta.attr_probs = out->attr_probs;
   ta.roi_features = out->roi_features; ta.preds_per_image = out->preds_per_image; ta.keep_idx = out->keep_idx;
+  VLTK_CUDA(scratch.get(&ta.stats, (size_t)n * r * 32));
   int rc = roi_tail(ta, st);
   cudaStreamSynchronize(st);
   return rc;

@@ -95,6 +95,7 @@ struct TailArgs {
   float* boxes; float* norm_boxes; long long* obj_ids; float* obj_probs;
   long long* attr_ids; float* attr_probs; float* roi_features; int* preds_per_image;
   int* keep_idx;               // [N, max_det] index into the image's proposal list (-1 pad)
+  float* stats;                // scratch [N*R, 8] f32: per-ROI box / prob / attr prob / ids (roi_stats_kernel)
 };
 int roi_tail(const TailArgs& a, cudaStream_t st);
 

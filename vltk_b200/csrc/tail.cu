@@ -36,8 +36,63 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Phase 1, for every ROI slot of the batch in parallel (one warp per ROI, ~N*R warps over the whole GPU instead of
+// 16 warps per image): class / attribute posteriors and the winning class's decoded + clipped box.
+//   stats[row] = {x1, y1, x2, y2, prob, attr_prob, bitcast(cls), bitcast(attr)}   (32 B per ROI)
+__global__ void __launch_bounds__(256)
+roi_stats_kernel(TailArgs a, float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (int64_t)a.N * a.R) return;
+  const int n = (int)(row / a.R), r = (int)(row - (int64_t)n * a.R);
+  if (r >= min(a.count[n], a.R)) return;                 // empty slot: never read by the tail
+  const float img_h = (float)a.sizes_hw[2 * n], img_w = (float)a.sizes_hw[2 * n + 1];
+  const int NC = a.num_classes, NA = a.num_attrs;
+  const float* __restrict__ l = a.cls_logits + row * a.ldc;
+  float best = -INFINITY; int bi = 0x7fffffff; float mx = -INFINITY;
+  for (int i = lane; i <= NC; i += 32) {
+    float v = l[i];
+    mx = fmaxf(mx, v);
+    if (i < NC && v > best) { best = v; bi = i; }
+  }
+  mx = warp_max(mx);
+  warp_argmax(best, bi);
+  float s = 0.f;
+  for (int i = lane; i <= NC; i += 32) s += expf(l[i] - mx);
+  s = warp_sum(s);
+  const float prob = expf(best - mx) / s;
+
+  const float* __restrict__ al = a.attr_logits + row * a.lda;
+  float ab = -INFINITY; int ai = 0x7fffffff;
+  for (int i = lane; i < NA; i += 32) {
+    float v = al[i];
+    if (v > ab) { ab = v; ai = i; }
+  }
+  warp_argmax(ab, ai);
+  float as = 0.f;
+  for (int i = lane; i < NA; i += 32) as += expf(al[i] - ab);
+  as = warp_sum(as);
+
+  if (lane == 0) {
+    const float4 d = *reinterpret_cast<const float4*>(a.bbox_deltas + row * a.ldb + 4 * bi);
+    const float4 p = reinterpret_cast<const float4*>(a.proposals)[row];
+    const float w = p.z - p.x, h = p.w - p.y;
+    const float cx = p.x + 0.5f * w, cy = p.y + 0.5f * h;
+    const float dx = d.x / a.wx, dy = d.y / a.wy;
+    const float dw = fminf(d.z / a.ww, SCALE_CLAMP), dh = fminf(d.w / a.wh, SCALE_CLAMP);
+    const float pcx = dx * w + cx, pcy = dy * h + cy;
+    const float pw = expf(dw) * w, ph = expf(dh) * h;
+    float x1 = pcx - 0.5f * pw, y1 = pcy - 0.5f * ph, x2 = pcx + 0.5f * pw, y2 = pcy + 0.5f * ph;
+    x1 = fminf(fmaxf(x1, 0.f), img_w); y1 = fminf(fmaxf(y1, 0.f), img_h);
+    x2 = fminf(fmaxf(x2, 0.f), img_w); y2 = fminf(fmaxf(y2, 0.f), img_h);
+    float4* o = reinterpret_cast<float4*>(stats + row * 8);
+    o[0] = make_float4(x1, y1, x2, y2);
+    o[1] = make_float4(prob, 1.0f / as /* exp(max-max)/sum */, __int_as_float(bi), __int_as_float(ai));
+  }
+}
+
 __global__ void __launch_bounds__(TAIL_THREADS)
-roi_tail_kernel(TailArgs a, float t0, float t1, float t2, float t3, int SORT_N, int RW) {
+roi_tail_kernel(TailArgs a, const float* __restrict__ stats, float t0, float t1, float t2, float t3, int SORT_N, int RW) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // carve dynamic smem
   float4* s_box = reinterpret_cast<float4*>(smem_raw);                       // [R]
@@ -52,58 +107,20 @@ roi_tail_kernel(TailArgs a, float t0, float t1, float t2, float t3, int SORT_N, 
   int* s_kept = s_order + a.R;                                                // [max_det]
   __shared__ int s_nkept, s_done;
 
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tid = threadIdx.x;
   const int n = blockIdx.x, R = a.R;
   const int cnt = min(a.count[n], R);
   const float img_h = (float)a.sizes_hw[2 * n], img_w = (float)a.sizes_hw[2 * n + 1];
-  const int NC = a.num_classes, NA = a.num_attrs;
 
-  // ---- 1. per-ROI class / attribute posteriors + box decode (one warp per ROI)
-  for (int r = wid; r < cnt; r += TAIL_THREADS / 32) {
-    const int64_t row = (int64_t)n * R + r;
-    const float* __restrict__ l = a.cls_logits + row * a.ldc;
-    float best = -INFINITY; int bi = 0x7fffffff; float mx = -INFINITY;
-    for (int i = lane; i <= NC; i += 32) {
-      float v = l[i];
-      mx = fmaxf(mx, v);
-      if (i < NC && v > best) { best = v; bi = i; }
-    }
-    mx = warp_max(mx);
-    warp_argmax(best, bi);
-    float s = 0.f;
-    for (int i = lane; i <= NC; i += 32) s += expf(l[i] - mx);
-    s = warp_sum(s);
-    const float prob = expf(best - mx) / s;
-
-    const float* __restrict__ al = a.attr_logits + row * a.lda;
-    float ab = -INFINITY; int ai = 0x7fffffff;
-    for (int i = lane; i < NA; i += 32) {
-      float v = al[i];
-      if (v > ab) { ab = v; ai = i; }
-    }
-    warp_argmax(ab, ai);
-    float as = 0.f;
-    for (int i = lane; i < NA; i += 32) as += expf(al[i] - ab);
-    as = warp_sum(as);
-
-    if (lane == 0) {
-      const float4 d = *reinterpret_cast<const float4*>(a.bbox_deltas + row * a.ldb + 4 * bi);
-      const float4 p = reinterpret_cast<const float4*>(a.proposals)[row];
-      const float w = p.z - p.x, h = p.w - p.y;
-      const float cx = p.x + 0.5f * w, cy = p.y + 0.5f * h;
-      const float dx = d.x / a.wx, dy = d.y / a.wy;
-      const float dw = fminf(d.z / a.ww, SCALE_CLAMP), dh = fminf(d.w / a.wh, SCALE_CLAMP);
-      const float pcx = dx * w + cx, pcy = dy * h + cy;
-      const float pw = expf(dw) * w, ph = expf(dh) * h;
-      float x1 = pcx - 0.5f * pw, y1 = pcy - 0.5f * ph, x2 = pcx + 0.5f * pw, y2 = pcy + 0.5f * ph;
-      x1 = fminf(fmaxf(x1, 0.f), img_w); y1 = fminf(fmaxf(y1, 0.f), img_h);
-      x2 = fminf(fmaxf(x2, 0.f), img_w); y2 = fminf(fmaxf(y2, 0.f), img_h);
-      s_box[r] = make_float4(x1, y1, x2, y2);
-      s_score[r] = prob;
-      s_cls[r] = bi;
-      s_attr[r] = ai;
-      s_attr_p[r] = 1.0f / as;  // exp(max-max)/sum
-    }
+  // ---- 1. per-ROI posteriors + decoded boxes were computed by roi_stats_kernel
+  for (int r = tid; r < cnt; r += TAIL_THREADS) {
+    const float4* st4 = reinterpret_cast<const float4*>(stats + ((int64_t)n * R + r) * 8);
+    const float4 b = st4[0], q = st4[1];
+    s_box[r] = b;
+    s_score[r] = q.x;
+    s_attr_p[r] = q.y;
+    s_cls[r] = __float_as_int(q.z);
+    s_attr[r] = __float_as_int(q.w);
   }
   // ---- 2. stable descending sort of the scores (ties: lower ROI index first)
   for (int i = tid; i < SORT_N; i += TAIL_THREADS) s_keys[i] = 0ull;
@@ -245,7 +262,11 @@ int roi_tail(const TailArgs& a, cudaStream_t st) {
   VLTK_CHECK(smem <= 100 * 1024, "roi_tail: smem %zu too large", smem);
   float t[4] = {0.f, 0.f, 0.f, 0.f};
   for (int i = 0; i < a.n_thresh; ++i) t[i] = a.nms_thresh[i];
-  roi_tail_kernel<<<a.N, TAIL_THREADS, smem, st>>>(a, t[0], t[1], t[2], t[3], sort_n, RW);
+  VLTK_CHECK(a.stats != nullptr, "roi_tail: stats scratch (N*R*8 floats) missing");
+  const int64_t rows = (int64_t)a.N * a.R;
+  roi_stats_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, st>>>(a, a.stats);
+  VLTK_LAUNCH_CHECK();
+  roi_tail_kernel<<<a.N, TAIL_THREADS, smem, st>>>(a, a.stats, t[0], t[1], t[2], t[3], sort_n, RW);
   VLTK_LAUNCH_CHECK();
   return 0;
 }
