@@ -129,8 +129,6 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-// named barrier over the 4 epilogue warps only (id 1; id 0 is __syncthreads)
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 // Sum 64 per-lane values (one per column) over the 32 lanes (rows) of a warp in 62 shuffles instead of
 // 64 x 5: at each step lanes exchange HALF of their live values with the partner lane, so the live set
 // halves (64 -> 32 -> ... -> 2).  On return lane L holds the totals of columns 2L (v[0]) and 2L+1 (v[1]).
@@ -349,30 +347,39 @@ struct TcParams2 {
   int pool_rows;
 };
 
-template <int BN, int STAGES, bool HAS_RES>
+template <int BN, int STAGES, bool HAS_RES, int EG = 1>
 struct Smem2 {
+  static constexpr int GSC = (BN / EG > 64) ? BN / EG : 64;   // scale (and shift) floats staged per epilogue group
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
   static constexpr int OFF_OUT = STAGES * STAGE_BYTES;
   static constexpr int OFF_RES = OFF_OUT + 2 * SLAB_BYTES;
   static constexpr int OFF_SCALE = OFF_RES + (HAS_RES ? RS * SLAB_BYTES : 0);
-  static constexpr int OFF_BARS = OFF_SCALE + 2 * BN * 4;
+  static constexpr int OFF_BARS = OFF_SCALE + 2 * EG * GSC * 4;
   static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * RS;
   static constexpr int TOTAL = OFF_BARS + NUM_BARS * 8 + 16;
   static_assert(TOTAL <= 232448, "exceeds the 227 KB shared memory of one sm_100 CTA");
 };
 
-template <int BN, int STAGES, bool HAS_RES, bool OUT_F32, bool POOL = false>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int BN, int STAGES, bool HAS_RES, bool OUT_F32, bool POOL = false, int EG = 1>
+__global__ void __launch_bounds__(128 + 128 * EG, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2,
                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, TcParams2 p) {
-  using S = Smem2<BN, STAGES, HAS_RES>;
+  using S = Smem2<BN, STAGES, HAS_RES, EG>;
   static_assert(!(HAS_RES && OUT_F32), "fp32 output has no residual path");
   static_assert(!POOL || !OUT_F32, "the pooled epilogue reduces the bf16-path tile");
+  static_assert(EG == 1 || EG == 2, "one or two epilogue warpgroups");
+  static_assert(!POOL || EG == 1, "the pooled epilogue runs on one warpgroup");
   constexpr int SLABC = OUT_F32 ? 32 : SLAB;   // columns per 128 B staging row (fp32: 32, bf16: 64)
   constexpr int NSLAB = BN / SLABC;
+  // EG epilogue warpgroups (warps 4-7, 8-11) share the slabs round-robin over the CTA's global slab sequence
+  // c = it * NSLAB + s: group g owns the slabs with c % EG == g, has its own staging buffers (2 / EG), its own
+  // named barrier and its own scale/shift cache, so the two groups never synchronise with each other and two
+  // warps per SM sub-partition hide each other's tcgen05.ld / shared-memory / barrier latencies.
+  constexpr int NBUF = 2 / EG;                 // 128 x 128 B staging buffers per group
+  constexpr int TE_COUNT = 4 * (NSLAB < EG ? NSLAB : EG);   // warps that drain one accumulator
   // no static smem in this kernel: the dynamic window starts at the CTA's (1024 B aligned) base
   extern __shared__ __align__(1024) unsigned char smem_dyn2[];
   const uint32_t base = smem_u32(smem_dyn2);
@@ -382,8 +389,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   unsigned char* gbase = smem_dyn2;
   const uint32_t sA = base, sB = base + S::OFF_B, sOut = base + S::OFF_OUT, sRes = base + S::OFF_RES;
-  float* s_scale = reinterpret_cast<float*>(gbase + S::OFF_SCALE);
-  float* s_shift = s_scale + BN;
+  float* s_scale_all = reinterpret_cast<float*>(gbase + S::OFF_SCALE);
   const uint32_t bars = base + S::OFF_BARS;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
@@ -404,7 +410,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TE_COUNT); }
     for (int s = 0; s < RS; ++s) { mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), 4); }
     fence_barrier_init();
   }
@@ -488,28 +494,43 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp >= 4) {
     // ================= epilogue =================
-    const int e = warp - 4;                   // TMEM lane quarter == warp id % 4
+    const int g = (warp - 4) >> 2;            // epilogue warpgroup
+    const int e = warp & 3;                   // TMEM lane quarter == warp id % 4
     const int row = e * 32 + lane;            // row of the tile owned by this thread
-    const int et = threadIdx.x - 128;         // 0..127
+    const int et = threadIdx.x - 128 - g * 128;   // 0..127 within the group
     const bool issuer = et == 0;
     const uint32_t swz = (uint32_t)(row & 7);
-    int slot = 0; uint32_t rphase = 0;
+    const uint32_t sOutG = sOut + (uint32_t)(g * NBUF) * SLAB_BYTES;
+    float* s_scale = s_scale_all + g * 2 * S::GSC;
+    float* s_shift = s_scale + S::GSC;
+    auto group_barrier = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
     int obuf = 0, it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int n0 = (t % p.n_tiles) * BN;
       const int m0 = (t / p.n_tiles) * BM;
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1) & 1u;
-      // per-tile BN scale/shift -> smem (previous tile's readers are past its last epi_barrier)
-      for (int i = et; i < BN; i += 128) {
-        s_scale[i] = p.scale ? p.scale[n0 + i] : 1.f;
-        s_shift[i] = p.shift ? p.shift[n0 + i] : 0.f;
+      const int c0 = it * NSLAB;              // global index of this tile's first slab
+      const int s_first = (g - c0 % EG + EG) % EG;
+      if (s_first >= NSLAB) continue;         // (NSLAB < EG) this tile belongs to the other group
+      // my slabs' BN scale/shift -> my smem cache (this group's previous readers are past their last barrier)
+      for (int i = et; i < S::GSC; i += 128) {
+        const int j = i / SLABC, s = s_first + j * EG;
+        if (s < NSLAB) {
+          const int col = n0 + s * SLABC + (i - j * SLABC);
+          s_scale[i] = p.scale ? p.scale[col] : 1.f;
+          s_shift[i] = p.shift ? p.shift[col] : 0.f;
+        }
       }
       mbar_wait(tfull_bar(acc), use);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int s = 0; s < NSLAB; ++s) {
+      for (int s = s_first, j = 0; s < NSLAB; s += EG, ++j) {
+        const int c = c0 + s;
+        const int slot = c % RS;
+        const uint32_t rphase = (uint32_t)(c / RS) & 1u;
+        (void)slot; (void)rphase;
         uint32_t v[SLABC];
         if constexpr (OUT_F32) {
           tmem_ld32(tacc + (uint32_t)(s * SLABC), v);
@@ -520,25 +541,25 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tmem_ld32(tacc + (uint32_t)(s * SLABC + 32), hi);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { v[j] = lo[j]; v[32 + j] = hi[j]; }
+          for (int jj = 0; jj < 32; ++jj) { v[jj] = lo[jj]; v[32 + jj] = hi[jj]; }
         }
-        if (s == NSLAB - 1) {                 // accumulator fully read: hand it back to the MMA warp
+        if (s + EG >= NSLAB) {                // my last slab of this accumulator: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
         if (HAS_RES) mbar_wait(rfull_bar(slot), rphase);
-        if (!POOL && issuer) bulk_wait_read<1>();   // the store that last read sOut[obuf] has drained it
-        epi_barrier();                        // sOut[obuf] reusable (POOL: last slab's column readers done); scale/shift visible
-        const uint32_t orow = sOut + obuf * SLAB_BYTES + (uint32_t)row * 128u;
+        if (!POOL && issuer) bulk_wait_read<NBUF - 1>();   // the store that last read sOutG[obuf] has drained it
+        group_barrier();                      // sOutG[obuf] reusable (POOL: last slab's column readers done); scale/shift visible
+        const uint32_t orow = sOutG + obuf * SLAB_BYTES + (uint32_t)row * 128u;
         const uint32_t rrow = sRes + slot * SLAB_BYTES + (uint32_t)row * 128u;
         float pv[POOL ? 64 : 1];              // POOL: this row's 64 fp32 epilogue values of the slab
         (void)pv;
         if constexpr (OUT_F32) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {       // 4 fp32 channels = one 16 B chunk
-            const float4 sc = *reinterpret_cast<const float4*>(s_scale + s * SLABC + q * 4);
-            const float4 sh = *reinterpret_cast<const float4*>(s_shift + s * SLABC + q * 4);
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + j * SLABC + q * 4);
+            const float4 sh = *reinterpret_cast<const float4*>(s_shift + j * SLABC + q * 4);
             float f0 = fmaf(__uint_as_float(v[q * 4 + 0]), sc.x, sh.x), f1 = fmaf(__uint_as_float(v[q * 4 + 1]), sc.y, sh.y);
             float f2 = fmaf(__uint_as_float(v[q * 4 + 2]), sc.z, sh.z), f3 = fmaf(__uint_as_float(v[q * 4 + 3]), sc.w, sh.w);
             if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
@@ -549,10 +570,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int q = 0; q < 8; ++q) {       // 8 bf16 channels = one 16 B chunk, stored at chunk q ^ (row % 8)
             const uint32_t coff = ((uint32_t)q ^ swz) << 4;
-            const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + s * SLABC + q * 8);
-            const float4 sc1 = *reinterpret_cast<const float4*>(s_scale + s * SLABC + q * 8 + 4);
-            const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + s * SLABC + q * 8);
-            const float4 sh1 = *reinterpret_cast<const float4*>(s_shift + s * SLABC + q * 8 + 4);
+            const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + j * SLABC + q * 8);
+            const float4 sc1 = *reinterpret_cast<const float4*>(s_scale + j * SLABC + q * 8 + 4);
+            const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + j * SLABC + q * 8);
+            const float4 sh1 = *reinterpret_cast<const float4*>(s_shift + j * SLABC + q * 8 + 4);
             float f[8];
             f[0] = fmaf(__uint_as_float(v[q * 8 + 0]), sc0.x, sh0.x); f[1] = fmaf(__uint_as_float(v[q * 8 + 1]), sc0.y, sh0.y);
             f[2] = fmaf(__uint_as_float(v[q * 8 + 2]), sc0.z, sh0.z); f[3] = fmaf(__uint_as_float(v[q * 8 + 3]), sc0.w, sh0.w);
@@ -586,7 +607,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (HAS_RES) {                        // this warp is done with the residual slab
           __syncwarp();
           if (lane == 0) mbar_arrive(rempty_bar(slot));
-          if (++slot == RS) { slot = 0; rphase ^= 1u; }
         }
         if constexpr (POOL) {
           // per-ROI column sums of this slab without staging the tile: rows of this warp that belong to the
@@ -616,7 +636,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           *reinterpret_cast<float2*>(comb + (0 * 4 + e) * 64 + 2 * lane) = ta;   // lane L owns columns 2L, 2L+1
           *reinterpret_cast<float2*>(comb + (1 * 4 + e) * 64 + 2 * lane) = tb;
-          epi_barrier();
+          group_barrier();
           {                                                                // 128 threads = 2 segments x 64 columns
             const int col = et & 63, seg = et >> 6;
             const float* c4 = comb + seg * 256 + col;
@@ -626,12 +646,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         } else {
           fence_proxy_async_smem();           // generic-proxy smem writes -> visible to the TMA unit
-          epi_barrier();
+          group_barrier();
           if (issuer) {
-            tma_store_2d(&tmY, sOut + obuf * SLAB_BYTES, n0 + s * SLABC, m0);
+            tma_store_2d(&tmY, sOutG + obuf * SLAB_BYTES, n0 + s * SLABC, m0);
             bulk_commit();
           }
-          obuf ^= 1;
+          if (NBUF > 1) obuf ^= 1;
         }
       }
     }
@@ -745,12 +765,12 @@ __global__ void pool_finish_kernel(const float* __restrict__ partial, float* __r
 
 struct Maps { CUtensorMap a, a2, b, b2, y, r; };
 
-template <int BN, int STAGES, bool HAS_RES, bool OUT_F32, bool POOL = false>
-int launch2(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
-  using S = Smem2<BN, STAGES, HAS_RES>;
+template <int BN, int STAGES, bool HAS_RES, bool OUT_F32, bool POOL = false, int EG = 1>
+int launch2e(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
+  using S = Smem2<BN, STAGES, HAS_RES, EG>;
   static DeviceOnce once;
   if (once.first()) {
-    VLTK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STAGES, HAS_RES, OUT_F32, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    VLTK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STAGES, HAS_RES, OUT_F32, POOL, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   }
   tp.n_tiles = cout_pad / BN;
   const int64_t tiles = ceil_div64(tp.M, BM) * tp.n_tiles;
@@ -760,14 +780,25 @@ int launch2(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
   static const bool use_pdl = [] { const char* e = getenv("VLTK_PDL"); return !(e && e[0] == '0'); }();
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128 + 128 * EG); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
-  VLTK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<BN, STAGES, HAS_RES, OUT_F32, POOL>, m.a, m.a2, m.b, m.b2, m.y, m.r, tp));
+  VLTK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc2_kernel<BN, STAGES, HAS_RES, OUT_F32, POOL, EG>, m.a, m.a2, m.b, m.b2, m.y, m.r, tp));
   VLTK_LAUNCH_CHECK();
   return 0;
+}
+
+// Two epilogue warpgroups unless VLTK_EPI_GROUPS=1 (A/B switch; the pooled epilogue always runs on one).
+template <int BN, int STAGES, bool HAS_RES, bool OUT_F32, bool POOL = false>
+int launch2(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
+  static const bool one = [] { const char* e = getenv("VLTK_EPI_GROUPS"); return e && e[0] == '1'; }();
+  if constexpr (POOL) return launch2e<BN, STAGES, HAS_RES, OUT_F32, POOL, 1>(m, tp, cout_pad, st);
+  else {
+    if (one) return launch2e<BN, STAGES, HAS_RES, OUT_F32, false, 1>(m, tp, cout_pad, st);
+    return launch2e<BN, STAGES, HAS_RES, OUT_F32, false, 2>(m, tp, cout_pad, st);
+  }
 }
 
 template <int BN, int STAGES>
