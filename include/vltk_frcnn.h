@@ -133,6 +133,15 @@ int vltk_conv2d_meanpool_nhwc(const void* x, const float* weight, const float* s
                               const void* residual, float* pooled, int n, int h, int w, int cin, int cout,
                               int k, int stride, int pad, int dil, int relu, int pool_rows, void* stream);
 
+/* A projection bottleneck's tail in bf16 mode (frcnn.py:918-925, 971-979): conv3 and the 1x1 shortcut as ONE
+ * K-concatenated tcgen05 GEMM, y = act(x . w^T + x2[::stride2, ::stride2] . w2^T + shift), frozen-BN scales
+ * already folded into w / w2 by the caller.  x [N,h,w,cin], x2 [N,h2,w2,cin2] bf16 NHWC (DEVICE) with
+ * (h2-1)/stride2+1 == h (same for w); weight [cout,cin], weight2 [cout,cin2] DEVICE f32 (rounded to bf16);
+ * shift [cout] or NULL; y [N,h,w,cout] bf16.  cin, cin2, cout % 64 == 0. */
+int vltk_conv2d_dual_nhwc(const void* x, const float* weight, const void* x2, const float* weight2,
+                          const float* shift, void* y, int n, int h, int w, int cin, int h2, int w2,
+                          int cin2, int stride2, int cout, int relu, void* stream);
+
 /* nn.Linear on the tensor pipe with fp32-faithful arithmetic (frcnn.py:1729-1737 in bf16 mode):
  * y[m,n] = act(x[m,k] . weight[n,k]^T + bias), all DEVICE f32; operands are split into bf16
  * hi+lo planes and accumulated as hi*hi + lo*hi + hi*lo in one fp32 TMEM tile.  k,n % 64 == 0. */

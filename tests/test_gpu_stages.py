@@ -83,6 +83,31 @@ def test_conv_tcgen05_matches_simt_and_reference(dev, case):
     assert ((y_tc - ref).abs() <= ulp * (ref.abs() + 1e-2)).all()
 
 
+def test_residual_ring_two_epilogue_groups_is_deterministic_under_hbm_load(dev):
+    """res5 conv3 shape at HBM scale (M = 600*196 rows, K=512 -> 2048, +residual, ~1.4 GB of traffic): the two
+    epilogue warpgroups share ONE residual TMA ring, whose boxes land out of order under load.  Without the ring
+    guard in conv_tc.cu a parity wait could pass on the other group's stale phase (wrong data, then a hung
+    pipeline).  Ten back-to-back runs must be bit-identical and match an fp64 evaluation on sampled rows."""
+    from vltk_b200 import stages
+    g = torch.Generator().manual_seed(77)
+    rois, cin, cout = 600, 512, 2048
+    x = torch.randn(rois, 14, 14, cin, generator=g).to(dev).bfloat16()
+    wt = (torch.randn(cout, cin, 1, 1, generator=g) * (2.0 / cin) ** 0.5).bfloat16().float().to(dev)
+    sc = (torch.rand(cout, generator=g) * 0.2 + 0.9).to(dev)
+    sh = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    res = torch.randn(rois, 14, 14, cout, generator=g).to(dev).bfloat16()
+    y0 = stages.conv2d_nhwc(x, wt, sc, sh, res, 1, 0, 1, True, mode="bf16", tensor_cores=True)
+    for _ in range(9):
+        y = stages.conv2d_nhwc(x, wt, sc, sh, res, 1, 0, 1, True, mode="bf16", tensor_cores=True)
+        assert torch.equal(y, y0)
+    rows = torch.randint(0, rois * 196, (512,), generator=g)
+    xs = x.reshape(-1, cin)[rows.to(dev)].double()
+    ref = torch.relu(xs @ wt.reshape(cout, cin).double().T * sc.double() + sh.double()
+                     + res.reshape(-1, cout)[rows.to(dev)].double()).cpu()
+    got = y0.reshape(-1, cout)[rows.to(dev)].double().cpu()
+    assert ((got - ref).abs() <= 2.0 ** -7 * (ref.abs() + 1e-2)).all()
+
+
 @pytest.mark.parametrize("rois,cin,cout", [(1, 512, 256), (5, 512, 2048), (37, 1024, 512)])
 def test_fused_meanpool_epilogue_matches_conv_then_mean(dev, rois, cin, cout):
     """res5 tail: the last conv3's epilogue reduces each ROI's 14x14 = 196 rows to their mean (from the fp32
@@ -101,6 +126,30 @@ def test_fused_meanpool_epilogue_matches_conv_then_mean(dev, rois, cin, cout):
     np.testing.assert_allclose(pooled.numpy(), ref.numpy(), rtol=2e-5, atol=2e-5)
     again = stages.conv2d_meanpool_nhwc(x, wt, sc, sh, res, 196).cpu()
     assert torch.equal(pooled, again)          # fixed reduction order: bit-reproducible, no atomics
+
+
+@pytest.mark.parametrize("n,h,w,mid,cin,cout,stride", [(2, 14, 14, 512, 1024, 2048, 1), (1, 19, 32, 128, 256, 512, 2),
+                                                     (3, 10, 13, 64, 64, 256, 1), (1, 9, 9, 256, 512, 1024, 2)])
+def test_projection_block_tail_as_one_concatenated_gemm(dev, n, h, w, mid, cin, cout, stride):
+    """Projection bottlenecks in bf16 mode (frcnn.py:918-925, 971-979): relu(BN3(conv3(t2)) + BNs(shortcut(x)))
+    runs as ONE tcgen05 GEMM over K = mid + cin with both BN scales folded into the bf16 weights.  Checked
+    against an fp64 evaluation of the same folded bf16 operands (1 bf16 ulp) — including the strided 1x1
+    sampling of x on the stage-entry blocks (stride 2 lives in the shortcut, frcnn.py:932)."""
+    from vltk_b200 import stages
+    g = torch.Generator().manual_seed(h * 31 + cin)
+    h2, w2 = (h - 1) * stride + 1 + (stride - 1), (w - 1) * stride + 1     # h2 odd/even mix: (h2-1)//stride+1 == h
+    assert (h2 - 1) // stride + 1 == h and (w2 - 1) // stride + 1 == w
+    t2 = torch.randn(n, h, w, mid, generator=g).abs().to(dev).bfloat16()
+    x = torch.randn(n, h2, w2, cin, generator=g).abs().to(dev).bfloat16()
+    w3 = (torch.randn(cout, mid, generator=g) * (1.0 / mid) ** 0.5).bfloat16().float()
+    ws = (torch.randn(cout, cin, generator=g) * (1.0 / cin) ** 0.5).bfloat16().float()
+    sh = torch.randn(cout, generator=g) * 0.1
+    y = stages.conv2d_dual_nhwc(t2, w3.to(dev), x, ws.to(dev), sh.to(dev), stride2=stride, relu=True).float().cpu()
+    xs = x.cpu().double()[:, ::stride, ::stride]
+    ref = torch.relu(t2.cpu().double() @ w3.double().T + xs @ ws.double().T + sh.double())
+    ulp = 2.0 ** -7
+    assert y.shape == ref.shape
+    assert ((y.double() - ref).abs() <= ulp * (ref.abs() + 1e-2)).all(), float((y.double() - ref).abs().max())
 
 
 @pytest.mark.parametrize("m,k,n", [(300, 2048, 1664), (37, 512, 448), (2400, 2048, 6400)])

@@ -339,7 +339,8 @@ struct TcParams2 {
   // split-precision GEMM: the K loop runs `npass` times; pass i reads A from map pass_a[i] (0: tmA,
   // 1: tmA2) and W from map pass_b[i] (0: tmB, 1: tmB2), all accumulating into the same TMEM tile.
   // npass = 1 is the plain bf16 product; {hi*hi, lo*hi, hi*lo} gives an fp32-faithful product.
-  int npass, pass_a[3], pass_b[3];
+  // Each pass has its own K extent and sampling stride (K-concatenated dual GEMM, TcConcat).
+  int npass, pass_a[3], pass_b[3], pass_cblocks[3], pass_stride[3];
   // POOL epilogue (res5 tail, frcnn.py:1401): rows are grouped in ROIs of `pool_rows` consecutive pixels;
   // instead of storing the tile, each row tile writes fp32 column sums of its (at most two) ROI segments to
   // pool_partial[(m_tile*2 + seg) * Cout + c]; pool_finish() adds the 2-3 partials per ROI in a fixed order.
@@ -358,7 +359,7 @@ struct Smem2 {
   static constexpr int OFF_SCALE = OFF_RES + (HAS_RES ? RS * SLAB_BYTES : 0);
   static constexpr int OFF_BARS = OFF_SCALE + 2 * EG * GSC * 4;
   static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * RS;
-  static constexpr int TOTAL = OFF_BARS + NUM_BARS * 8 + 16;
+  static constexpr int TOTAL = OFF_BARS + NUM_BARS * 8 + 16;   // + tmem slot (4 B) + seen[2] (8 B)
   static_assert(TOTAL <= 232448, "exceeds the 227 KB shared memory of one sm_100 CTA");
 };
 
@@ -399,9 +400,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   auto rempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + 4 + RS + s); };
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + S::OFF_BARS + S::NUM_BARS * 8);
   const uint32_t tmem_slot = bars + S::NUM_BARS * 8;
+  // seen[g] = last residual slab whose arrival epilogue group g has OBSERVED (see the epilogue's ring guard)
+  volatile int* seen = reinterpret_cast<volatile int*>(gbase + S::OFF_BARS + S::NUM_BARS * 8 + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = p.npass * p.taps * p.cblocks;
+  int num_kb = 0;
+  for (int ps = 0; ps < p.npass; ++ps) num_kb += p.taps * p.pass_cblocks[ps];
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY);
@@ -412,6 +416,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TE_COUNT); }
     for (int s = 0; s < RS; ++s) { mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), 4); }
+    seen[0] = -1; seen[1] = -1;
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
@@ -438,18 +443,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int ow0 = (int)(m0 % p.OW);
       const int64_t q = m0 / p.OW;
       const int oh0 = (int)(q % p.OH), img0 = (int)(q / p.OH);
-      const int bw = ow0 * p.stride - p.pad, bh = oh0 * p.stride - p.pad;
       for (int ps = 0; ps < p.npass; ++ps) {
         const CUtensorMap* ma = p.pass_a[ps] ? &tmA2 : &tmA;
         const CUtensorMap* mb = p.pass_b[ps] ? &tmB2 : &tmB;
+        const int cblocks = p.pass_cblocks[ps];
+        const int bw = ow0 * p.pass_stride[ps] - p.pad, bh = oh0 * p.pass_stride[ps] - p.pad;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int kh = tap / p.KW, kw = tap - kh * p.KW;
-          for (int cb = 0; cb < p.cblocks; ++cb) {
+          for (int cb = 0; cb < cblocks; ++cb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             mbar_expect_tx(full_bar(stage), S::STAGE_BYTES);
             tma_load_im2col_4d(sA + stage * A_STAGE_BYTES, ma, full_bar(stage), cb * BK, bw, bh, img0,
                                (uint16_t)(kw * p.dil), (uint16_t)(kh * p.dil));
-            tma_load_2d(sB + stage * S::B_STAGE_BYTES, mb, full_bar(stage), (tap * p.cblocks + cb) * BK, n0);
+            tma_load_2d(sB + stage * S::B_STAGE_BYTES, mb, full_bar(stage), (tap * cblocks + cb) * BK, n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -548,7 +554,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
-        if (HAS_RES) mbar_wait(rfull_bar(slot), rphase);
+        if (HAS_RES) {
+          if constexpr (EG == 2) {
+            // Parity waits are only sound when the slot's PREVIOUS phase is known complete.  With one consumer that
+            // is implied (it consumed that phase itself); with two groups sharing one ring the previous occupant of
+            // this slot (slab c - RS, RS odd) belongs to the OTHER group, and its bytes may still be in flight when
+            // we get here (TMA boxes land out of order under HBM load) — a parity wait would then return at once
+            // on the stale phase.  So first wait until the other group has seen slab c - RS land.  This never adds a
+            // stall: slab c is only issued after the other group RELEASED slab c - RS.
+            static_assert(RS % 2 == 1, "slab c - RS must belong to the other epilogue group");
+            if (c >= RS) {
+              for (uint32_t spin = 0; seen[g ^ 1] < c - RS; ++spin)
+                if (spin > (1u << 26)) { printf("conv_tc2: residual ring guard timeout\n"); __trap(); }
+            }
+          }
+          mbar_wait(rfull_bar(slot), rphase);
+          if (EG == 2 && issuer) seen[g] = c;
+        }
         if (!POOL && issuer) bulk_wait_read<NBUF - 1>();   // the store that last read sOutG[obuf] has drained it
         group_barrier();                      // sOutG[obuf] reusable (POOL: last slab's column readers done); scale/shift visible
         const uint32_t orow = sOutG + obuf * SLAB_BYTES + (uint32_t)row * 128u;
@@ -819,9 +841,14 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const TcParams& tp, int c
 size_t conv_tc_pool_partial_bytes(int64_t M, int cout) { return (size_t)ceil_div64(M, BM) * 2 * cout * sizeof(float); }
 
 int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorMapCache* cache, cudaStream_t st,
-                   const TcSplit* split, const TcPool* pool) {
+                   const TcSplit* split, const TcPool* pool, const TcConcat* concat) {
   const bool out_f32 = p.out_dtype == DT_F32;
   const bool is_split = split && split->x_lo && split->w_lo;
+  const bool is_concat = concat && concat->x2 && concat->w2;
+  VLTK_CHECK(!(is_concat && (is_split || (pool && pool->out))), "conv_tc: concat excludes split / pooled epilogue");
+  VLTK_CHECK(!is_concat || (p.KH == 1 && p.KW == 1 && p.pad == 0 && concat->Cin2 % BK == 0 && concat->ldx2 % 8 == 0 &&
+                            (concat->H2 - 1) / concat->stride2 + 1 == p.OH && (concat->W2 - 1) / concat->stride2 + 1 == p.OW),
+             "conv_tc: concat needs a 1x1 primary conv and a second operand on the same output grid");
   VLTK_CHECK(p.in_dtype == DT_BF16, "conv_tc: bf16 operands only");
   VLTK_CHECK(!(out_f32 && p.residual), "conv_tc: fp32 output has no residual path");
   VLTK_CHECK(p.Cin % BK == 0, "conv_tc: Cin=%d must be a multiple of %d", p.Cin, BK);
@@ -837,7 +864,7 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
   // they do NOT run at half the cost of N=256); layers with K <= 256 are epilogue-bound (1-4 k-blocks
   // per tile) and run 7-34 % faster with BN=128, whose finer tiles keep both TMEM accumulators busy.
   int bn = (cout_pad % 256 == 0) ? 256 : (cout_pad % 128 == 0 ? 128 : 64);
-  if (K <= 256 && cout_pad % 128 == 0) bn = 128;
+  if (K + (is_concat ? concat->Cin2 : 0) <= 256 && cout_pad % 128 == 0) bn = 128;
   if (cache->maps.size() > 8192) cache->maps.clear();   // keys hold buffer addresses: bound growth across reallocations
   CUtensorMap ta, tb;
   TensorMapCache::Key ka(p.x, p.N, p.H, p.W, p.Cin, p.ldx, p.KH, p.stride, p.pad, p.dil, 0);
@@ -854,6 +881,7 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
   } else tb = ib->second;
 
   static const bool use_v1 = [] { const char* e = getenv("VLTK_TC_V1"); return e && e[0] == '1'; }();
+  VLTK_CHECK(!(use_v1 && is_concat), "conv_tc: the v1 kernel has no concat path");
   if (!use_v1 || out_f32 || is_split) {
     VLTK_CHECK(p.Cout % 64 == 0 && cout_pad == p.Cout, "conv_tc: Cout=%d must be a multiple of 64", p.Cout);
     Maps m;
@@ -880,6 +908,15 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
       if (cached(TensorMapCache::Key(split->w_lo, K, cout_pad, bn, 0, 0, 0, 0, 0, 0, 1), &m.b2,
                  [&](CUtensorMap* d) { return make_b_map(split->w_lo, K, cout_pad, bn, d); })) return -1;
     }
+    if (is_concat) {
+      ConvProblem p2 = p;
+      p2.x = concat->x2; p2.ldx = concat->ldx2; p2.H = concat->H2; p2.W = concat->W2; p2.Cin = concat->Cin2;
+      p2.stride = concat->stride2;
+      if (cached(TensorMapCache::Key(p2.x, p2.N, p2.H, p2.W, p2.Cin, p2.ldx, p2.KH, p2.stride, p2.pad, p2.dil, 0), &m.a2,
+                 [&](CUtensorMap* d) { return make_a_map(p2, d); })) return -1;
+      if (cached(TensorMapCache::Key(concat->w2, concat->Cin2, cout_pad, bn, 0, 0, 0, 0, 0, 0, 1), &m.b2,
+                 [&](CUtensorMap* d) { return make_b_map(concat->w2, concat->Cin2, cout_pad, bn, d); })) return -1;
+    }
     TcParams2 t2;
     t2.scale = p.scale; t2.shift = p.shift; t2.M = M; t2.Cout = p.Cout; t2.relu = p.relu;
     t2.OH = p.OH; t2.OW = p.OW; t2.stride = p.stride; t2.pad = p.pad; t2.dil = p.dil; t2.KW = p.KW;
@@ -888,6 +925,11 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
     t2.npass = is_split ? 3 : 1;                       // hi*hi, lo*hi, hi*lo
     t2.pass_a[0] = 0; t2.pass_a[1] = 1; t2.pass_a[2] = 0;
     t2.pass_b[0] = 0; t2.pass_b[1] = 0; t2.pass_b[2] = 1;
+    for (int i = 0; i < 3; ++i) { t2.pass_cblocks[i] = t2.cblocks; t2.pass_stride[i] = p.stride; }
+    if (is_concat) {                                   // pass 1 = the second operand pair
+      t2.npass = 2; t2.pass_a[1] = 1; t2.pass_b[1] = 1;
+      t2.pass_cblocks[1] = concat->Cin2 / BK; t2.pass_stride[1] = concat->stride2;
+    }
     if (out_f32) {
       if (bn == 256) return launch2<256, 4, false, true>(m, t2, cout_pad, st);
       if (bn == 128) return launch2<128, 4, false, true>(m, t2, cout_pad, st);

@@ -35,9 +35,22 @@ struct TcPool {
   int rows = 0;
 };
 size_t conv_tc_pool_partial_bytes(int64_t M, int cout);
+// Optional second operand pair accumulated into the SAME output tile (K-concatenation of two 1x1 convs):
+//   y = act((x (*) w + x2 (*) w2) * scale + shift (+ residual))
+// x2 is a bf16 NHWC tensor [N, H2, W2, Cin2] sampled with stride2 (a strided 1x1, pad 0) onto the same
+// [N, OH, OW] output grid; w2 is bf16 [cout_pad][Cin2].  This is how a bottleneck's projection shortcut
+// (frcnn.py:918-925, 971-976) is folded into its conv3: with both frozen-BN scales pre-multiplied into the
+// weights, conv3(t2) + shortcut(x) is ONE GEMM over K = mid + cin and the shortcut tensor is never written
+// to or re-read from HBM.  Requires a 1x1 primary conv.
+struct TcConcat {
+  const void* x2 = nullptr;
+  int ldx2 = 0, H2 = 0, W2 = 0, Cin2 = 0, stride2 = 1;
+  const bf16* w2 = nullptr;
+};
 // out_dtype may be DT_F32 (no residual) or DT_BF16.
 int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorMapCache* cache,
-                   cudaStream_t st, const TcSplit* split = nullptr, const TcPool* pool = nullptr);
+                   cudaStream_t st, const TcSplit* split = nullptr, const TcPool* pool = nullptr,
+                   const TcConcat* concat = nullptr);
 
 // ---- pack.cu: reference-layout weights [cout][cin][taps] (DEVICE f32) -> kernel layouts
 int pack_weight_kn(const float* w, float* w_kn, int cout, int cin, int taps, int ldw, bool round_bf16,

@@ -39,7 +39,14 @@ struct LayerW {           // one conv / linear layer, packed for the kernels
   float* shift = nullptr; // [ldw]
 };
 
-struct Block { LayerW c1, c2, c3, sc; bool has_sc = false; };
+struct Block {
+  LayerW c1, c2, c3, sc;
+  bool has_sc = false;
+  // projection blocks on the tensor pipe: conv3 and shortcut as ONE K-concatenated GEMM (conv_tc.cuh TcConcat).
+  // Both frozen-BN scales are folded into the bf16 weights, the shifts are summed.
+  LayerW c3f;               // w_nk = bf16(scale3 * W3), scale = nullptr, shift = shift3 + shift_sc
+  bf16* scf_w = nullptr;    // bf16(scale_sc * W_sc)  [cout][cin]
+};
 
 struct Tap { const void* p = nullptr; int64_t n = 0; DType dt = DT_F32; };
 
@@ -173,6 +180,19 @@ int pack_split_linear(vltk_frcnn* h, LayerW& L, const std::vector<float>& w, int
   return 0;
 }
 
+// frozen BN (eps 1e-5, frcnn.py:163-173) as y = x*sc + sh
+int bn_fold(vltk_frcnn* h, const std::string& n, int cout, std::vector<float>& sc, std::vector<float>& sh) {
+  const auto* g = find(h, n + ".weight", cout); const auto* b = find(h, n + ".bias", cout);
+  const auto* m = find(h, n + ".running_mean", cout); const auto* v = find(h, n + ".running_var", cout);
+  if (!g || !b || !m || !v) return -2;
+  for (int o = 0; o < cout; ++o) {
+    const float invstd = 1.0f / sqrtf((*v)[o] + 1e-5f);
+    sc[o] = (*g)[o] * invstd;
+    sh[o] = (*b)[o] - (*m)[o] * sc[o];
+  }
+  return 0;
+}
+
 int pack_block(vltk_frcnn* h, Block& B, const std::string& p, int cin, int mid, int cout, int stride,
                int dil, bool rb, bool tc) {
   B.has_sc = cin != cout;
@@ -181,6 +201,25 @@ int pack_block(vltk_frcnn* h, Block& B, const std::string& p, int cin, int mid, 
   if (pack_layer(h, B.c2, p + ".conv2", mid, mid, 3, 1, dil, dil, 1, true, false, rb, tc)) return -1;
   // conv3: BN only; the ReLU comes after the residual add and is applied by the same epilogue
   if (pack_layer(h, B.c3, p + ".conv3", mid, cout, 1, 1, 0, 1, 1, true, false, rb, tc)) return -1;
+  if (tc && B.has_sc && B.c3.w_nk && B.sc.w_nk && cout % 64 == 0) {
+    const auto* w3 = find(h, p + ".conv3.weight", (int64_t)cout * mid);
+    const auto* ws = find(h, p + ".shortcut.weight", (int64_t)cout * cin);
+    if (!w3 || !ws) return -2;
+    std::vector<float> s3(cout), b3(cout), ss(cout), bs(cout);
+    if (bn_fold(h, p + ".conv3.norm", cout, s3, b3) || bn_fold(h, p + ".shortcut.norm", cout, ss, bs)) return -2;
+    std::vector<bf16> f3((size_t)cout * mid), fs((size_t)cout * cin);
+    for (int o = 0; o < cout; ++o) {
+      for (int c = 0; c < mid; ++c) f3[(size_t)o * mid + c] = __float2bfloat16_rn(s3[o] * (*w3)[(size_t)o * mid + c]);
+      for (int c = 0; c < cin; ++c) fs[(size_t)o * cin + c] = __float2bfloat16_rn(ss[o] * (*ws)[(size_t)o * cin + c]);
+      b3[o] += bs[o];
+    }
+    B.c3f = B.c3;
+    B.c3f.scale = nullptr;
+    if (dev_alloc(h, (void**)&B.c3f.w_nk, f3.size() * 2) || dev_alloc(h, (void**)&B.scf_w, fs.size() * 2)) return -1;
+    VLTK_CUDA(cudaMemcpy(B.c3f.w_nk, f3.data(), f3.size() * 2, cudaMemcpyHostToDevice));
+    VLTK_CUDA(cudaMemcpy(B.scf_w, fs.data(), fs.size() * 2, cudaMemcpyHostToDevice));
+    if (upload(h, b3, &B.c3f.shift)) return -1;
+  }
   return 0;
 }
 
@@ -217,7 +256,7 @@ Shapes make_shapes(const vltk_frcnn_config& c, int N, int H, int W) {
 // Runs one layer.  x: [N,H,W,cin_pad]
 int run_conv(vltk_frcnn* h, const LayerW& L, const void* x, DType xdt, int N, int H, int W, void* y,
              DType ydt, int ldy, const void* residual, int ldr, int relu, cudaStream_t st, int* oh_out = nullptr,
-             int* ow_out = nullptr, const TcPool* pool = nullptr) {
+             int* ow_out = nullptr, const TcPool* pool = nullptr, const TcConcat* cc = nullptr) {
   ConvProblem p;
   memset(&p, 0, sizeof(p));
   p.x = x; p.ldx = L.cin_pad; p.y = y; p.ldy = ldy; p.residual = residual; p.ldr = ldr;
@@ -241,12 +280,13 @@ int run_conv(vltk_frcnn* h, const LayerW& L, const void* x, DType xdt, int N, in
     };
     rec.kind = tc ? 0 : 1;
     rec.M = (int64_t)N * p.OH * p.OW; rec.K = L.k * L.k * L.cin; rec.Cout = L.cout;
+    if (cc) rec.K += cc->Cin2;                           // K-concatenated second GEMM (projection shortcut)
     rec.flops = 2.0 * (double)rec.M * rec.K * rec.Cout;  // algorithmic: unpadded cin/cout
     rec.e0 = get_event(); rec.e1 = get_event();
     cudaEventRecord(rec.e0, st);
   }
-  if (pool && !tc) { set_error("internal: fused mean-pool needs the tensor-core path"); return -2; }
-  int rc = tc ? conv_tc_launch(p, L.w_nk, L.cout_pad, &h->tmaps, st, nullptr, pool) : conv_simt_launch(p, L.w_kn, L.ldw, st);
+  if ((pool || cc) && !tc) { set_error("internal: fused mean-pool / concat need the tensor-core path"); return -2; }
+  int rc = tc ? conv_tc_launch(p, L.w_nk, L.cout_pad, &h->tmaps, st, nullptr, pool, cc) : conv_simt_launch(p, L.w_kn, L.ldw, st);
   if (h->profiling) {
     cudaEventRecord(rec.e1, st);
     h->prof.push_back(rec);
@@ -301,6 +341,19 @@ int run_block(vltk_frcnn* h, const Block& B, const void* x, int N, int H, int W,
   int h1, w1;
   if (run_conv(h, B.c1, x, d, N, H, W, t1, d, B.c1.ldw, nullptr, 0, 1, st, &h1, &w1)) return -1;
   if (run_conv(h, B.c2, t1, d, N, h1, w1, t2, d, B.c2.ldw, nullptr, 0, 1, st)) return -1;
+  // projection block on the tensor pipe: out = relu(t2 * W3' + x (*) Wsc' + shift) in ONE launch; the shortcut
+  // tensor never exists (saves its HBM write + re-read and a launch).  VLTK_FUSE_SC=0 restores the two-launch form.
+  static const bool fuse_sc = [] {
+    const char* e = getenv("VLTK_FUSE_SC"); const char* v1 = getenv("VLTK_TC_V1");
+    return !(e && e[0] == '0') && !(v1 && v1[0] == '1');
+  }();
+  if (fuse_sc && B.has_sc && B.scf_w && h->use_tc && d == DT_BF16 && !pool) {
+    TcConcat cc;
+    cc.x2 = x; cc.ldx2 = B.sc.cin_pad; cc.H2 = H; cc.W2 = W; cc.Cin2 = B.sc.cin; cc.stride2 = B.sc.stride; cc.w2 = B.scf_w;
+    if (run_conv(h, B.c3f, t2, d, N, h1, w1, out, d, B.c3.ldw, nullptr, 0, 1, st, nullptr, nullptr, nullptr, &cc)) return -1;
+    *oh = h1; *ow = w1;
+    return 0;
+  }
   const void* res = x;
   int ldr = B.c3.ldw;
   if (B.has_sc) {
@@ -892,6 +945,34 @@ int vltk_conv2d_meanpool_nhwc(const void* x, const float* weight, const float* s
   TcPool pool; pool.out = pooled; pool.partial = partial; pool.rows = pool_rows;
   TensorMapCache cache;
   if (!rc) rc = conv_tc_launch(p, w_nk, cout, &cache, st, nullptr, &pool);
+  cudaStreamSynchronize(st);
+  return rc;
+}
+
+int vltk_conv2d_dual_nhwc(const void* x, const float* weight, const void* x2, const float* weight2, const float* shift,
+                          void* y, int n, int hh, int ww, int cin, int h2, int w2, int cin2, int stride2, int cout,
+                          int relu, void* stream) {
+  VLTK_CHECK(x && weight && x2 && weight2 && y, "conv2d_dual: null argument");
+  VLTK_CHECK(cin % 64 == 0 && cin2 % 64 == 0 && cout % 64 == 0, "conv2d_dual: cin, cin2, cout must be multiples of 64");
+  cudaStream_t st = (cudaStream_t)stream;
+  Scratch scratch(st);
+  ConvProblem p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.ldx = cin; p.y = y; p.ldy = cout; p.N = n; p.H = p.OH = hh; p.W = p.OW = ww; p.Cin = cin;
+  p.KH = p.KW = 1; p.stride = 1; p.dil = 1; p.Cout = cout; p.relu = relu; p.in_dtype = DT_BF16; p.out_dtype = DT_BF16;
+  bf16 *w1 = nullptr, *wb = nullptr;
+  float* sh = nullptr;
+  VLTK_CUDA(scratch.get(&w1, (size_t)cout * cin * 2));
+  VLTK_CUDA(scratch.get(&wb, (size_t)cout * cin2 * 2));
+  VLTK_CUDA(scratch.get(&sh, (size_t)cout * 4));
+  int rc = pack_weight_nk(weight, w1, cout, cin, 1, st);
+  if (!rc) rc = pack_weight_nk(weight2, wb, cout, cin2, 1, st);
+  if (!rc) rc = pad_vector(shift, sh, cout, cout, 0.f, st);
+  p.shift = sh;
+  TcConcat cc;
+  cc.x2 = x2; cc.ldx2 = cin2; cc.H2 = h2; cc.W2 = w2; cc.Cin2 = cin2; cc.stride2 = stride2; cc.w2 = wb;
+  TensorMapCache cache;
+  if (!rc) rc = conv_tc_launch(p, w1, cout, &cache, st, nullptr, nullptr, &cc);
   cudaStreamSynchronize(st);
   return rc;
 }

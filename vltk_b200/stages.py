@@ -69,6 +69,28 @@ def conv2d_meanpool_nhwc(x, weight, scale, shift, residual, pool_rows, stride=1,
     return out
 
 
+def conv2d_dual_nhwc(x, weight, x2, weight2, shift=None, stride2=1, relu=True):
+    """A projection bottleneck's tail on the tensor pipe (frcnn.py:918-925, 971-979): conv3(x) + shortcut(x2)
+    as ONE K-concatenated GEMM, y = act(x.w^T + x2[:, ::stride2, ::stride2].w2^T + shift); BN scales are
+    expected to be folded into the weights already.  x [N,h,w,cin], x2 [N,h2,w2,cin2] bf16 NHWC;
+    weight [cout,cin], weight2 [cout,cin2] f32."""
+    L = _lib.lib()
+    assert x.dtype == torch.bfloat16 and x2.dtype == torch.bfloat16 and x.is_contiguous() and x2.is_contiguous()
+    n, h, w, cin = x.shape
+    _, h2, w2, cin2 = x2.shape
+    cout = weight.shape[0]
+    assert (h2 - 1) // stride2 + 1 == h and (w2 - 1) // stride2 + 1 == w
+    y = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=x.device)
+    wa = weight.to(x.device, torch.float32).reshape(cout, cin).contiguous()
+    wb = weight2.to(x.device, torch.float32).reshape(cout, cin2).contiguous()
+    sh = None if shift is None else shift.to(x.device, torch.float32).contiguous()
+    with torch.cuda.device(x.device):
+        _lib.check(L.vltk_conv2d_dual_nhwc(x.data_ptr(), wa.data_ptr(), x2.data_ptr(), wb.data_ptr(), _ptr(sh),
+                                           y.data_ptr(), n, h, w, cin, h2, w2, cin2, stride2, cout, int(relu),
+                                           _stream(x)), "vltk_conv2d_dual_nhwc")
+    return y
+
+
 def linear_tc3(x, weight, bias=None, relu=False):
     """F.linear(x, weight, bias) on the tensor pipe with split-bf16 (hi*hi + lo*hi + hi*lo) operands
     and fp32 accumulate/output — how the predictor linears (frcnn.py:1729-1737) run in bf16 mode."""
