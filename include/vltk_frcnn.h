@@ -189,8 +189,10 @@ int64_t vltk_frcnn_launch_count(vltk_frcnn_t* h);
 /* Per-launch CUDA-event timing of the dense kernels (bench.py's roofline leg).  While enabled,
  * every conv/GEMM launch is bracketed by two events on the launch stream.  profile_read
  * synchronises, then fills agg[6] = {tcgen05 ms, tcgen05 FLOPs, tcgen05 launches, SIMT ms,
- * SIMT FLOPs, SIMT launches} summed since the last read, optionally writes one CSV line per
- * launch ("kind,M,K,Cout,ms") into csv (NUL-terminated, truncated at cap), and clears the log. */
+ * SIMT FLOPs, SIMT launches} since the last read — a kind's ms is the UNION of its launches' event intervals
+ * (the two backbone half-batch streams overlap; overlapped time is counted once) — optionally writes one CSV
+ * line per launch ("kind,M,K,Cout,ms", each launch's own duration) into csv (NUL-terminated, truncated at
+ * cap), and clears the log. */
 int vltk_frcnn_profile_enable(vltk_frcnn_t* h, int enable);
 int vltk_frcnn_profile_read(vltk_frcnn_t* h, double* agg, char* csv, size_t cap);
 

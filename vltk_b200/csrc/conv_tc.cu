@@ -864,7 +864,8 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
   // they do NOT run at half the cost of N=256); layers with K <= 256 are epilogue-bound (1-4 k-blocks
   // per tile) and run 7-34 % faster with BN=128, whose finer tiles keep both TMEM accumulators busy.
   int bn = (cout_pad % 256 == 0) ? 256 : (cout_pad % 128 == 0 ? 128 : 64);
-  if (K + (is_concat ? concat->Cin2 : 0) <= 256 && cout_pad % 128 == 0) bn = 128;
+  static const int smallk = [] { const char* e = getenv("VLTK_SMALLK"); return e ? atoi(e) : 256; }();   // tuning knob
+  if (K + (is_concat ? concat->Cin2 : 0) <= smallk && cout_pad % 128 == 0) bn = 128;
   if (cache->maps.size() > 8192) cache->maps.clear();   // keys hold buffer addresses: bound growth across reallocations
   CUtensorMap ta, tb;
   TensorMapCache::Key ka(p.x, p.N, p.H, p.W, p.Cin, p.ldx, p.KH, p.stride, p.pad, p.dil, 0);

@@ -78,6 +78,9 @@ struct vltk_frcnn {
   struct ProfRec { int kind; double flops; int64_t M; int K, Cout; cudaEvent_t e0, e1; };
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> event_pool;
+  // res2-res4 of a batch run as two image halves on two streams (see forward): fork/join plumbing
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace vltk_eng {
@@ -441,6 +444,9 @@ void vltk_frcnn_destroy(vltk_frcnn_t* h) {
   for (void* p : h->owned) cudaFree(p);
   for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
 }
 
@@ -561,7 +567,7 @@ static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void*
 enum {
   B_IN4, B_STEM, B_POOL, B_A, B_B, B_T1, B_T2, B_S, B_RPNH, B_HEAD, B_SIZES, B_SCALES, B_SBOX, B_SSCORE,
   B_SIDX, B_SVALID, B_MASK, B_PROP, B_PSCORE, B_PIDX, B_COUNT, B_POOLED, B_R5A, B_R5B, B_R5T1, B_R5T2,
-  B_R5S, B_FEATS, B_CLS, B_BBOX, B_ARGMAX, B_TG, B_AH, B_ATTR, B_FHI, B_FLO, B_AHHI, B_AHLO, B_STEMA, B_PARTIAL, B_NMSDONE, B_ROISTAT, B_NUM
+  B_R5S, B_FEATS, B_CLS, B_BBOX, B_ARGMAX, B_TG, B_AH, B_ATTR, B_FHI, B_FLO, B_AHHI, B_AHLO, B_STEMA, B_PARTIAL, B_NMSDONE, B_ROISTAT, B_RES4, B_NUM
 };
 
 static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void** p) {
@@ -603,6 +609,7 @@ static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void*
   p[B_PARTIAL] = b.take(h->use_tc ? conv_tc_pool_partial_bytes((int64_t)NR * PP, D) : 0);
   p[B_NMSDONE] = b.take((size_t)N * 4);
   p[B_ROISTAT] = b.take((size_t)NR * 32);
+  p[B_RES4] = b.take((size_t)N * s.h4 * s.w4 * c2 * 4 * e);
   return b.off + 256;
 }
 
@@ -667,12 +674,58 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   int ch = s.Hp, cw = s.Wp;
   void* pp[2] = {p[B_A], p[B_B]};
   int flip = 0;
-  for (auto& stage : h->stages)
-    for (auto& blk : stage) {
-      int oh, ow;
-      if (run_block(h, blk, x, n, ch, cw, pp[flip], p[B_T1], p[B_T2], p[B_S], st, &oh, &ow)) return -1;
-      x = pp[flip]; flip ^= 1; ch = oh; cw = ow;
-    }
+  // res2-res4 are ~90 SMALL launches (res4: 19 152 pixel rows = 150 row tiles on 148 SMs, 20-40 us each, half of it
+  // launch ramp and a second wave of 2 tiles).  Images are independent up to the RPN, so on the tensor pipe the
+  // batch is split into two image halves that run the same layers on two streams: each half's kernels need ~75
+  // CTAs, the two streams' kernels pack the 148 SMs together and overlap each other's ramps and tails.  Every
+  // output row is computed from its own input rows only, so the result is bit-identical to the unsplit order.
+  // VLTK_SPLIT_BACKBONE=0 restores the single-stream order.
+  static const bool want_split = [] { const char* e = getenv("VLTK_SPLIT_BACKBONE"); return !(e && e[0] == '0'); }();
+  const bool split = want_split && h->use_tc && n >= 2;
+  if (split && !h->side) {
+    VLTK_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    VLTK_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    VLTK_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  }
+  const int nA = split ? (n + 1) / 2 : n, nB = n - nA;
+  if (split) {
+    VLTK_CUDA(cudaEventRecord(h->ev_fork, st));
+    VLTK_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+  }
+  {
+    // Half B lives at a FIXED offset (= half A's capacity) in every shared scratch buffer, so the two halves' regions
+    // stay disjoint even when one stream is a stage ahead of the other (tensor shapes — and with them the natural
+    // batch offsets — change from stage to stage).  Only the first block's input (maxpool output) and the last
+    // block's output (the res4 map, its own buffer) are addressed as one contiguous [N,H,W,C] tensor.
+    const size_t e = esz(d);
+    const size_t c2 = c.res2_out_channels;
+    const size_t f_big = std::max({(size_t)s.h2 * s.w2 * c2, (size_t)s.h3 * s.w3 * c2 * 2, (size_t)s.h4 * s.w4 * c2 * 4});
+    const size_t f_mid = std::max({(size_t)s.h2 * s.w2 * (c2 / 4), (size_t)s.h3 * s.w3 * (c2 / 2), (size_t)s.h4 * s.w4 * c2});
+    const size_t offB_big = (size_t)nA * f_big * e, offB_mid = (size_t)nA * f_mid * e;
+    size_t nblk = 0, bi = 0;
+    for (auto& stage : h->stages) nblk += stage.size();
+    int cin_x = c.stem_out_channels;      // channels of the current block input
+    for (auto& stage : h->stages)
+      for (auto& blk : stage) {
+        const bool first = bi == 0, last = bi + 1 == nblk;
+        const int h1 = (ch - 1) / blk.c1.stride + 1, w1 = (cw - 1) / blk.c1.stride + 1;
+        char* outA = last ? (char*)p[B_RES4] : (char*)pp[flip];
+        int oh = 0, ow = 0;
+        if (run_block(h, blk, x, nA, ch, cw, outA, p[B_T1], p[B_T2], p[B_S], st, &oh, &ow)) return -1;
+        if (nB > 0) {
+          const char* xB = (const char*)x + (first ? (size_t)nA * ch * cw * cin_x * e : offB_big);
+          char* outB = last ? (char*)p[B_RES4] + (size_t)nA * h1 * w1 * blk.c3.ldw * e : (char*)pp[flip] + offB_big;
+          int oh2, ow2;
+          if (run_block(h, blk, xB, nB, ch, cw, outB, (char*)p[B_T1] + offB_mid, (char*)p[B_T2] + offB_mid,
+                        (char*)p[B_S] + offB_big, h->side, &oh2, &ow2)) return -1;
+        }
+        x = outA; flip ^= 1; ch = oh; cw = ow; cin_x = blk.c3.ldw; ++bi;
+      }
+  }
+  if (split) {
+    VLTK_CUDA(cudaEventRecord(h->ev_join, h->side));
+    VLTK_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+  }
   VLTK_CHECK(ch == s.h4 && cw == s.w4, "internal: res4 shape mismatch");
   const void* res4 = x;
   const int C4 = c.res2_out_channels * 4, A = c.num_anchors;
@@ -856,14 +909,27 @@ int vltk_frcnn_profile_read(vltk_frcnn_t* h, double* agg, char* csv, size_t cap)
   for (int i = 0; i < 6; ++i) agg[i] = 0.0;
   size_t off = 0;
   if (csv && cap) csv[0] = 0;
+  // Launches of the two backbone half-batch streams overlap in time: a kind's busy time is the UNION of its
+  // launches' [start, end] intervals (each measured against the first recorded event), not their sum.
+  std::vector<std::pair<float, float>> iv[2];
   for (auto& r : h->prof) {
-    float ms = 0.f;
+    float ms = 0.f, t0 = 0.f;
     cudaEventElapsedTime(&ms, r.e0, r.e1);
-    if (r.kind < 2) { agg[3 * r.kind + 0] += ms; agg[3 * r.kind + 1] += r.flops; agg[3 * r.kind + 2] += 1.0; }
+    cudaEventElapsedTime(&t0, h->prof.front().e0, r.e0);
+    if (r.kind < 2) { iv[r.kind].push_back({t0, t0 + ms}); agg[3 * r.kind + 1] += r.flops; agg[3 * r.kind + 2] += 1.0; }
     if (csv && off + 96 < cap)
       off += snprintf(csv + off, cap - off, "%s,%lld,%d,%d,%.5f\n", kKindName[r.kind < K_NUM ? r.kind : 0], (long long)r.M, r.K, r.Cout, ms);
-    h->event_pool.push_back(r.e0); h->event_pool.push_back(r.e1);
   }
+  for (int k = 0; k < 2; ++k) {
+    std::sort(iv[k].begin(), iv[k].end());
+    float lo = 0.f, hi = -1.f;
+    for (auto& x : iv[k]) {
+      if (hi < lo || x.first > hi) { if (hi >= lo) agg[3 * k] += hi - lo; lo = x.first; hi = x.second; }
+      else hi = std::max(hi, x.second);
+    }
+    if (hi >= lo) agg[3 * k] += hi - lo;
+  }
+  for (auto& r : h->prof) { h->event_pool.push_back(r.e0); h->event_pool.push_back(r.e1); }
   h->prof.clear();
   return 0;
 }
