@@ -61,6 +61,12 @@ typedef struct {
   int min_detections;
   int max_detections;
   float pad_value;          /* forward(..., pad_value=) */
+  /* forward(..., ignorey=) — frcnn.py:328-366: HOST [N, n_ignorey, 2] f32 y-ranges (raw-image coordinates) or
+   * NULL.  Honoured only when scales_yx is given too (the reference's own condition); ranges are divided by
+   * scales_yx[n][1], RPN proposals spanning a range are dropped and the others clipped to its nearer end.
+   * n_ignorey <= 16. */
+  const float* ignorey;
+  int n_ignorey;
 } vltk_frcnn_knobs;
 
 /* Dense, caller-allocated DEVICE outputs of one forward call: the model-dict of

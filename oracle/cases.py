@@ -46,14 +46,29 @@ CASES = {
     "cfg2x2": (dict(min_size_test=600, max_size_test=1000), 0, [(600, 1000, 4010), (600, 1000, 4011)]),
     # BASELINE.json configs[2] flavour: mixed aspect ratios with padding, max_detections=100
     "cfg3x2": (dict(min_detections=10, max_detections=100), 0, [(600, 800, 20), (1000, 750, 21)]),
+    # the `ignorey` branch of find_top_rpn_proposals (frcnn.py:328-366): two caller-given y-ranges (raw-image
+    # coordinates) on one resized image (scale 0.78); proposals spanning a range are dropped, others clipped.
+    # One image only: the reference's branch overwrites the shared level_ids and cannot run a larger batch.
+    "ignorey": (dict(min_size_test=192, max_size_test=288, rpn_pre_nms_topk=600, rpn_post_nms_topk=48,
+                     min_detections=8, max_detections=20), 0, [(150, 200, 2)]),
 }
 
-CPU_CASES = ("tiny", "mixed", "constant", "stripes", "few")          # cheap enough for the no-GPU suite
-GPU_CASES = ("tiny", "mixed", "constant", "stripes", "few", "full36", "cfg1", "cfg2x2", "cfg3x2")
+# case -> ignorey [N, J, 2] passed to forward (None for every other case)
+IGNOREY = {"ignorey": [[[40.0, 70.0], [100.0, 118.0]]]}
+
+CPU_CASES = ("tiny", "mixed", "constant", "stripes", "few", "ignorey")   # cheap enough for the no-GPU suite
+GPU_CASES = ("tiny", "mixed", "constant", "stripes", "few", "ignorey", "full36", "cfg1", "cfg2x2", "cfg3x2")
 
 
 def case_config(name: str) -> FRCNNConfig:
     return FRCNNConfig().replace(**CASES[name][0])
+
+
+def case_ignorey(name: str):
+    """-> ignorey tensor [N,J,2] f32 of the case, or None."""
+    import torch
+    v = IGNOREY.get(name)
+    return None if v is None else torch.tensor(v, dtype=torch.float32)
 
 
 def case_inputs(name: str):

@@ -226,12 +226,41 @@ def roi_pool_np(feat: torch.Tensor, rois: torch.Tensor, out: int, scale: float) 
 
 
 # ----------------------------------------------------------------------- RPN select
-def rpn_select(cfg, logits_nchw, deltas_nchw, cell, image_shapes, return_debug=False):
+def apply_ignorey(boxes: torch.Tensor, ranges: torch.Tensor, scale_x: torch.Tensor):
+    """The `ignorey` branch of find_top_rpn_proposals (frcnn.py:328-366) for ONE image, on the decoded,
+    not yet clipped top-k boxes.  ranges [J,2] are caller-given (y0, y1) pairs; the reference divides them
+    by scales_yx[n, 1] (the X scale — reproduced as written).  Per range, in order:
+      * drop every box that spans the whole range (y1 <= r0 and y2 >= r1)          (:333-336)
+      * of the rest, boxes NOT lying entirely past it (not (y1 > r1 and y2 > r0)) are clipped: the box edge
+        nearer to its range end moves there — y2 = int(r0) when |r1-y2| < |r0-y1|, y1 = int(r1) when
+        |r0-y1| < |r1-y2| (`box_ignore_below` is a contradiction and never fires)  (:342-366)
+    Returns (boxes after clipping [K,4], alive mask [K]); dropped rows keep their last coordinates.
+    The reference compacts the arrays instead of masking and, because it also overwrites the shared
+    `level_ids` (:340), only survives batches of one image; semantics per image are identical."""
+    boxes = boxes.clone()
+    alive = torch.ones(len(boxes), dtype=torch.bool)
+    for r in ranges:
+        r = (r * 1) / scale_x                       # `ignoreyij * 1/(scales_yx[n, 1])` (:331)
+        r0, r1 = r[0], r[1]
+        y1, y2 = boxes[:, 1], boxes[:, 3]
+        alive &= ~((r1 <= y2) & (r0 >= y1))
+        past = (y1 > r1) & (y2 > r0)
+        to_clip = alive & ~past
+        clip_top = to_clip & ((r1 - y2).abs() < (r0 - y1).abs())
+        clip_bottom = to_clip & ((r0 - y1).abs() < (r1 - y2).abs())
+        boxes[clip_bottom, 1] = float(int(r1))
+        boxes[clip_top, 3] = float(int(r0))
+    return boxes, alive
+
+
+def rpn_select(cfg, logits_nchw, deltas_nchw, cell, image_shapes, return_debug=False, ignorey=None,
+               scales_yx=None):
     """predict_proposals + predict_objectness_logits + find_top_rpn_proposals +
     RPN.inference re-sort (frcnn.py:748-781, 264-390, 1615-1638), single level.
 
     Returns per image (boxes [n<=post,4], logits [n]); with return_debug also the
-    top-k anchor indices, their decoded+clipped boxes and the kept positions."""
+    top-k anchor indices, their decoded+clipped boxes and the kept positions.
+    ignorey [N,J,2] is honoured only together with scales_yx (frcnn.py:328)."""
     n, a, h, w = logits_nchw.shape
     logits = logits_nchw.permute(0, 2, 3, 1).reshape(n, -1)
     deltas = deltas_nchw.view(n, a, 4, h, w).permute(0, 3, 4, 1, 2).reshape(n, -1, 4)
@@ -244,8 +273,12 @@ def rpn_select(cfg, logits_nchw, deltas_nchw, cell, image_shapes, return_debug=F
         idx = idx[:k]
         sc = srt[:k]
         boxes = apply_deltas(deltas[i][idx], anchors[idx], cfg.rpn_bbox_weights)
+        alive = torch.ones(len(boxes), dtype=torch.bool)
+        if ignorey is not None and scales_yx is not None:
+            boxes, alive = apply_ignorey(boxes, torch.as_tensor(ignorey, dtype=torch.float32)[i],
+                                         torch.as_tensor(scales_yx, dtype=torch.float32)[i, 1])
         clip_boxes_(boxes, image_shapes[i])
-        ok = ((boxes[:, 2] - boxes[:, 0]) > cfg.rpn_min_size) & \
+        ok = alive & ((boxes[:, 2] - boxes[:, 0]) > cfg.rpn_min_size) & \
              ((boxes[:, 3] - boxes[:, 1]) > cfg.rpn_min_size)
         pos = torch.nonzero(ok).squeeze(1)
         keep = nms_np(boxes[pos].numpy(), sc[pos].numpy(), cfg.rpn_nms_thresh,
@@ -308,7 +341,7 @@ def roi_outputs(cfg, obj_logits, attr_logits, box_deltas, proposals: Sequence[to
 # ------------------------------------------------------------------------- forward
 @torch.no_grad()
 def forward(sd: Dict[str, torch.Tensor], cfg, images: torch.Tensor, image_shapes,
-            scales_yx=None, stages: Optional[dict] = None, res5_chunk: int = 64):
+            scales_yx=None, stages: Optional[dict] = None, res5_chunk: int = 64, ignorey=None):
     """FRCNN.inference (frcnn.py:1942-2004).  images [N,3,H,W] f32 normalised+padded;
     image_shapes [N,2] resized (h,w); returns the reference's ragged dict plus `keep`
     (indices into each image's proposal list).  `stages`, if given, is filled with the
@@ -317,7 +350,8 @@ def forward(sd: Dict[str, torch.Tensor], cfg, images: torch.Tensor, image_shapes
     res4 = backbone(sd, images)
     logits, deltas = rpn_head(sd, res4)
     cell = sd["proposal_generator.anchor_generator.cell_anchors.0"]
-    props, dbg = rpn_select(cfg, logits, deltas, cell, image_shapes, return_debug=True)
+    props, dbg = rpn_select(cfg, logits, deltas, cell, image_shapes, return_debug=True, ignorey=ignorey,
+                            scales_yx=scales_yx)
     boxes = [p[0] for p in props]
     rois = torch.cat([torch.cat((torch.full((len(b), 1), float(i)), b), 1)
                       for i, b in enumerate(boxes)], 0)

@@ -69,10 +69,11 @@ def run_reference(name: str):
         feats = model.backbone(images)
         res4 = feats["res4"]
         logits, deltas = model.proposal_generator.rpn_head([res4])
-        boxes, plogits = model.proposal_generator(images, sizes, feats, None, None, scales)
+        ign = cases.case_ignorey(name)
+        boxes, plogits = model.proposal_generator(images, sizes, feats, None, ign, scales)
         obj_logits, attr_logits, box_deltas, pooled = model.roi_heads(feats, boxes, None)
         # end-to-end through the public call as well (must equal the staged run)
-        out = model(images, sizes, scales_yx=scales)
+        out = model(images, sizes, scales_yx=scales, ignorey=ign)
     dt = time.time() - t0
     g = {
         "images_ck": checksum(images), "sizes": sizes.numpy(), "scales_yx": scales.numpy(),
@@ -108,7 +109,7 @@ def run_reference(name: str):
         g["box_deltas_f16"] = box_deltas.numpy().astype(np.float16)
     # decision margins of this case (computed with the oracle port on the same inputs)
     ost = {}
-    oout = O.forward(sd, cfg, images, sizes, scales, stages=ost)
+    oout = O.forward(sd, cfg, images, sizes, scales, stages=ost, ignorey=ign)
     mg = margins.margins(cfg, ost, oout)
     assert margins.certified(mg), f"{name}: seeds are not margin-certified: {mg}"
     g["rpn_topk_anchor_idx"] = torch.stack([d["topk_idx"] for d in ost["rpn_debug"]]).numpy().astype(np.int32)

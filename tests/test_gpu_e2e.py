@@ -40,7 +40,7 @@ def run_case(case, mode, **kw):
     model, cfg = get_model(case, mode)
     _, _, raws = cases.case_inputs(case)
     ids, images, sizes, scales = Preprocess(cfg)(raws)
-    out = model(images, sizes, scales_yx=scales, **kw)
+    out = model(images, sizes, scales_yx=scales, ignorey=cases.case_ignorey(case), **kw)
     return model, cfg, images, sizes, scales, out
 
 
@@ -92,7 +92,7 @@ def test_fp32_matches_reference_golden(case):
     np.testing.assert_allclose(cat(out["roi_features"])[:, ::s], g["roi_features"], rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("case", ["tiny", "mixed"])
+@pytest.mark.parametrize("case", ["tiny", "mixed", "ignorey"])
 def test_fp32_matches_oracle_full_tensors(case):
     cfg, oimg, osz, osc, oout, st = oracle_run(case)
     model, cfg, images, sizes, scales, out = run_case(case, "fp32")
@@ -104,13 +104,42 @@ def test_fp32_matches_oracle_full_tensors(case):
                                    rtol=1e-4, atol=1e-4)
     # padded contract (v1.0.0): dense tensors + sizes + normalized_boxes
     from oracle import frcnn_oracle as O
-    dense = model(images, sizes, scales_yx=scales, padding="max_detections", return_tensors="np")
+    dense = model(images, sizes, scales_yx=scales, padding="max_detections", return_tensors="np",
+                  ignorey=cases.case_ignorey(case))
     ref = O.pad_outputs(oout, osz, osc, cfg.max_detections)
     assert dense["roi_features"].shape == (images.shape[0], cfg.max_detections, 2048)
     assert np.array_equal(dense["obj_ids"], ref["obj_ids"].numpy())
     assert np.array_equal(dense["sizes"], ref["sizes"].numpy())
     np.testing.assert_allclose(dense["normalized_boxes"], ref["normalized_boxes"].numpy(), rtol=0, atol=1e-4)
     np.testing.assert_allclose(dense["boxes"], ref["boxes"].numpy(), rtol=0, atol=1e-2)
+
+
+def test_ignorey_on_a_batch_applies_the_per_image_rule():
+    """forward(..., ignorey=[N,J,2]) on a 2-image batch with different ranges per image.  The reference's branch
+    cannot run this (it overwrites the shared level_ids after the first image, frcnn.py:340); the engine applies
+    the same per-image rule to every image, checked against the oracle restatement (itself pinned to the real
+    reference on the one-image `ignorey` golden)."""
+    from oracle import frcnn_oracle as O
+    from vltk_b200.preprocess import Preprocess
+    model, cfg = get_model("mixed", "fp32")
+    _, _, raws = cases.case_inputs("mixed")
+    ids, images, sizes, scales = Preprocess(cfg)(raws)
+    ign = torch.tensor([[[30.0, 55.0], [90.0, 120.0]], [[100.0, 140.0], [10.0, 20.0]]])
+    oi, osz, osc = O.preprocess(cfg, raws)
+    ref = O.forward(weights(0), cfg, oi, osz, osc, ignorey=ign)
+    base = O.forward(weights(0), cfg, oi, osz, osc)
+    assert any(not torch.equal(a, b) for a, b in zip(ref["boxes"], base["boxes"]))   # the ranges do change the result
+    out = model(images, sizes, scales_yx=scales, ignorey=ign)
+    assert out["preds_per_image"].tolist() == ref["preds_per_image"].tolist()
+    for i in range(2):
+        assert torch.equal(out["keep_idx"][i].cpu(), ref["keep"][i])
+        assert torch.equal(out["obj_ids"][i].cpu(), ref["obj_ids"][i])
+        np.testing.assert_allclose(out["boxes"][i].cpu().numpy(), ref["boxes"][i].numpy(), rtol=0, atol=1e-2)
+    # without scales_yx the reference skips the branch entirely (frcnn.py:328)
+    plain = model(images, sizes, ignorey=ign)
+    noign = model(images, sizes)
+    for i in range(2):
+        assert torch.equal(plain["boxes"][i], noign["boxes"][i])
 
 
 def _iou(a, b):

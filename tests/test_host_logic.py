@@ -132,3 +132,20 @@ def test_arrow_contract_roundtrip_and_reference_fixture(tmp_path):
         row = ref.slice(0, 1).to_pylist()[0]
         assert np.asarray(row["features"]).shape == (36, 2048) and np.asarray(row["box"]).shape == (36, 4)
         assert len(row["attr_ids"]) == 36 and len(row["object_ids"]) == 36
+
+
+def test_oracle_ignorey_rules():
+    """apply_ignorey (frcnn.py:328-366): span -> dropped; nearer end clipped with int() truncation; boxes lying
+    entirely past the range untouched; ranges are divided by the X scale as the reference writes it."""
+    from oracle import frcnn_oracle as O
+    boxes = torch.tensor([[0., 10., 5., 90.],     # spans [40.5, 60.5] -> dropped
+                          [0., 45., 5., 58.],     # inside: |60.5-58| < |40.5-45| -> y2 = int(40.5) = 40
+                          [0., 41., 5., 50.],     # |40.5-41| < |60.5-50| -> y1 = int(60.5) = 60
+                          [0., 70., 5., 95.],     # y1 > r1 and y2 > r0 -> untouched
+                          [0., 5., 5., 30.]])     # before the range, still 'to clip': |60.5-30| < |40.5-5| -> y2 = 40 (sic)
+    out, alive = O.apply_ignorey(boxes, torch.tensor([[81.0, 121.0]]), torch.tensor(2.0))
+    assert alive.tolist() == [False, True, True, True, True]
+    assert out[1].tolist() == [0., 45., 5., 40.]
+    assert out[2].tolist() == [0., 60., 5., 50.]
+    assert out[3].tolist() == [0., 70., 5., 95.]
+    assert out[4].tolist() == [0., 5., 5., 40.]

@@ -37,7 +37,7 @@ def oracle_run(name):
     sd = weights(wseed)
     images, sizes, scales = O.preprocess(cfg, raws)
     st = {}
-    out = O.forward(sd, cfg, images, sizes, scales, stages=st)
+    out = O.forward(sd, cfg, images, sizes, scales, stages=st, ignorey=cases.case_ignorey(name))
     return cfg, images, sizes, scales, out, st
 
 

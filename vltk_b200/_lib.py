@@ -31,7 +31,8 @@ class Config(C.Structure):
 
 class Knobs(C.Structure):
     _fields_ = [("nms_thresh", C.c_float * 4), ("n_nms_thresh", C.c_int),
-                ("min_detections", C.c_int), ("max_detections", C.c_int), ("pad_value", C.c_float)]
+                ("min_detections", C.c_int), ("max_detections", C.c_int), ("pad_value", C.c_float),
+                ("ignorey", C.c_void_p), ("n_ignorey", C.c_int)]
 
 
 class Out(C.Structure):
@@ -128,7 +129,8 @@ def make_config(cfg, mode: str) -> Config:
     return c
 
 
-def make_knobs(nms_thresh, min_det: int, max_det: int, pad_value: float = 0.0) -> Knobs:
+def make_knobs(nms_thresh, min_det: int, max_det: int, pad_value: float = 0.0, ignorey=None) -> Knobs:
+    """ignorey: C-contiguous float32 numpy [N, J, 2] (kept alive by the caller for the duration of the call)."""
     nms_thresh = list(nms_thresh) if isinstance(nms_thresh, (list, tuple)) else [nms_thresh]
     if not 1 <= len(nms_thresh) <= 4:
         raise ValueError("between 1 and 4 NMS thresholds are supported")
@@ -138,4 +140,7 @@ def make_knobs(nms_thresh, min_det: int, max_det: int, pad_value: float = 0.0) -
     k.min_detections = int(min_det)
     k.max_detections = int(max_det)
     k.pad_value = float(pad_value)
+    if ignorey is not None and ignorey.shape[1] > 0:
+        k.ignorey = ignorey.ctypes.data
+        k.n_ignorey = int(ignorey.shape[1])
     return k

@@ -567,7 +567,7 @@ static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void*
 enum {
   B_IN4, B_STEM, B_POOL, B_A, B_B, B_T1, B_T2, B_S, B_RPNH, B_HEAD, B_SIZES, B_SCALES, B_SBOX, B_SSCORE,
   B_SIDX, B_SVALID, B_MASK, B_PROP, B_PSCORE, B_PIDX, B_COUNT, B_POOLED, B_R5A, B_R5B, B_R5T1, B_R5T2,
-  B_R5S, B_FEATS, B_CLS, B_BBOX, B_ARGMAX, B_TG, B_AH, B_ATTR, B_FHI, B_FLO, B_AHHI, B_AHLO, B_STEMA, B_PARTIAL, B_NMSDONE, B_ROISTAT, B_RES4, B_NUM
+  B_R5S, B_FEATS, B_CLS, B_BBOX, B_ARGMAX, B_TG, B_AH, B_ATTR, B_FHI, B_FLO, B_AHHI, B_AHLO, B_STEMA, B_PARTIAL, B_NMSDONE, B_ROISTAT, B_RES4, B_IGNOREY, B_NUM
 };
 
 static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void** p) {
@@ -610,6 +610,7 @@ static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void*
   p[B_NMSDONE] = b.take((size_t)N * 4);
   p[B_ROISTAT] = b.take((size_t)NR * 32);
   p[B_RES4] = b.take((size_t)N * s.h4 * s.w4 * c2 * 4 * e);
+  p[B_IGNOREY] = b.take((size_t)N * 16 * 2 * 4);
   return b.off + 256;
 }
 
@@ -642,6 +643,11 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
 
   VLTK_CUDA(cudaMemcpyAsync(p[B_SIZES], sizes_hw, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   if (scales_yx) VLTK_CUDA(cudaMemcpyAsync(p[B_SCALES], scales_yx, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  const bool use_ignorey = knobs->ignorey && knobs->n_ignorey > 0 && scales_yx;   // frcnn.py:328
+  if (use_ignorey) {
+    VLTK_CHECK(knobs->n_ignorey <= 16, "forward: at most 16 ignorey ranges per image (got %d)", knobs->n_ignorey);
+    VLTK_CUDA(cudaMemcpyAsync(p[B_IGNOREY], knobs->ignorey, (size_t)n * knobs->n_ignorey * 8, cudaMemcpyHostToDevice, st));
+  }
 
   // ---- backbone (frcnn.py:1076-1090)
   { StageTimer t(h, K_LAYOUT, (double)n * height * width * (12 + 16), st);
@@ -743,6 +749,7 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   ra.wx = c.rpn_bbox_weights[0]; ra.wy = c.rpn_bbox_weights[1]; ra.ww = c.rpn_bbox_weights[2]; ra.wh = c.rpn_bbox_weights[3];
   ra.boxes = (float*)p[B_SBOX]; ra.scores = (float*)p[B_SSCORE]; ra.anchor_idx = (int*)p[B_SIDX];
   ra.valid = (uint8_t*)p[B_SVALID]; ra.K = s.K;
+  if (use_ignorey) { ra.ignorey = (const float*)p[B_IGNOREY]; ra.scales_yx = (const float*)p[B_SCALES]; ra.J = knobs->n_ignorey; }
   { StageTimer t(h, K_SELECT, (double)n * s.h4 * s.w4 * A * 20.0 + (double)n * s.K * 20.0, st);
     if (rpn_select(ra, st)) return -1; }
   NmsArgs na;

@@ -36,6 +36,11 @@ struct RpnSelectArgs {
   int* anchor_idx;        // [N, K] flattened anchor index (y*W+x)*A+a (for tests)
   uint8_t* valid;         // [N, K] non-empty flag
   int K;                  // = min(pre_topk, H4*W4*A)
+  // `ignorey` branch (frcnn.py:328-366), active when both pointers are set: J caller-given y-ranges per image,
+  // divided by scales_yx[n][1]; proposals spanning a range are dropped, the others clipped to its nearer end.
+  const float* ignorey;   // [N, J, 2] device or nullptr
+  const float* scales_yx; // [N, 2] device or nullptr
+  int J;
 };
 int rpn_select(const RpnSelectArgs& a, cudaStream_t st);
 

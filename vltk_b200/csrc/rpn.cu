@@ -137,13 +137,28 @@ rpn_select_kernel(RpnSelectArgs a, int SORT_N) {
     const float pw = expf(dw) * w, ph = expf(dh) * h;
     float x1 = pcx - 0.5f * pw, y1 = pcy - 0.5f * ph;
     float x2 = pcx + 0.5f * pw, y2 = pcy + 0.5f * ph;
+    bool alive = true;
+    if (a.ignorey && a.scales_yx) {       // frcnn.py:328-366, on the decoded, not yet clipped box
+      const float sxs = a.scales_yx[2 * n + 1];            // the reference divides by the X scale (:331)
+      for (int j = 0; j < a.J && alive; ++j) {
+        const float r0 = a.ignorey[((int64_t)n * a.J + j) * 2 + 0] / sxs;
+        const float r1 = a.ignorey[((int64_t)n * a.J + j) * 2 + 1] / sxs;
+        if (r1 <= y2 && r0 >= y1) { alive = false; break; }   // spans the whole range: dropped (:333-336)
+        const bool past = y1 > r1 && y2 > r0;                 // (:342-343; `box_ignore_below` can never be true)
+        if (!past) {
+          const float d_top = fabsf(r1 - y2), d_bot = fabsf(r0 - y1);
+          if (d_top < d_bot) y2 = (float)(int)r0;             // clip_top    (:351-357, 366)
+          else if (d_bot < d_top) y1 = (float)(int)r1;        // clip_bottom (:358-365)
+        }
+      }
+    }
     x1 = fminf(fmaxf(x1, 0.f), img_w); y1 = fminf(fmaxf(y1, 0.f), img_h);
     x2 = fminf(fmaxf(x2, 0.f), img_w); y2 = fminf(fmaxf(y2, 0.f), img_h);
     const int64_t o = (int64_t)n * K + r;
     *reinterpret_cast<float4*>(a.boxes + o * 4) = make_float4(x1, y1, x2, y2);
     a.scores[o] = logit;
     a.anchor_idx[o] = (int)idx;
-    a.valid[o] = ((x2 - x1) > a.min_size && (y2 - y1) > a.min_size) ? 1 : 0;
+    a.valid[o] = (alive && (x2 - x1) > a.min_size && (y2 - y1) > a.min_size) ? 1 : 0;
   }
 }
 

@@ -130,7 +130,8 @@ class FRCNN:
         return t, o
 
     def run(self, images: torch.Tensor, sizes_hw: np.ndarray, scales_yx: Optional[np.ndarray],
-            max_detections: int, min_detections: int, nms_thresh, pad_value: float = 0.0, slot: int = 0):
+            max_detections: int, min_detections: int, nms_thresh, pad_value: float = 0.0, slot: int = 0,
+            ignorey: Optional[np.ndarray] = None):
         """Enqueues one forward on the current stream; returns the dense device tensors.  The call
         never synchronises, so forwards on different streams overlap if they use different `slot`s
         (each slot owns a workspace)."""
@@ -147,12 +148,16 @@ class FRCNN:
         ws = self._ws(n, h, w, slot)
         d = self.config.res2_out_channels * 8
         tensors, out = self._alloc_out(n, max_detections, d)
-        knobs = _lib.make_knobs(nms_thresh, min_detections, max_detections, pad_value)
+        if ignorey is not None:      # [N, J, 2] y-ranges (frcnn.py:328-366); only honoured together with scales_yx
+            ignorey = np.ascontiguousarray(ignorey, dtype=np.float32)
+            if ignorey.ndim != 3 or ignorey.shape[0] != n or ignorey.shape[2] != 2:
+                raise ValueError(f"ignorey must be [N={n}, J, 2], got {ignorey.shape}")   # reference: assert ndim == 3
+        knobs = _lib.make_knobs(nms_thresh, min_detections, max_detections, pad_value, ignorey)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self._lib.vltk_frcnn_forward(
             self._h, images.data_ptr(), sizes_hw.ctypes.data, sc_ptr, n, h, w, C.byref(knobs),
             C.byref(out), ws.data_ptr(), ws.numel(), stream), "vltk_frcnn_forward")
-        tensors["_keepalive"] = (images, sizes_hw, scales_yx)
+        tensors["_keepalive"] = (images, sizes_hw, scales_yx, ignorey)
         return tensors
 
     def forward(self, images, image_shapes, gt_boxes=None, proposals=None, scales_yx=None,
@@ -162,11 +167,16 @@ class FRCNN:
 
         padding=None returns the live reference's ragged lists of per-image tensors;
         padding="max_detections" returns the v1.0.0 dense layout [N,max_det,...] plus `sizes`
-        and `normalized_boxes`."""
+        and `normalized_boxes`.
+
+        ignorey [N,J,2] (frcnn.py:328-366, only honoured together with scales_yx, like the reference): per image J
+        y-ranges in raw-image coordinates; RPN proposals spanning a range are dropped and the others clipped to its
+        nearer end before clipping/NMS.  The reference's branch only survives a batch of one image (it overwrites
+        the shared level_ids); here every image of the batch gets the same per-image rule."""
         if self.training:
             raise NotImplementedError()
-        if gt_boxes is not None or proposals is not None or ignorey is not None:
-            raise NotImplementedError("gt_boxes / proposals / ignorey are not part of the extraction path")
+        if gt_boxes is not None or proposals is not None:
+            raise NotImplementedError("gt_boxes / proposals are not part of the extraction path")
         padding = kwargs.get("padding", None)
         return_tensors = kwargs.get("return_tensors", None)
         pad_value = kwargs.get("pad_value", 0)
@@ -187,7 +197,8 @@ class FRCNN:
             sizes = np.asarray(torch.as_tensor(image_shapes).cpu().numpy(), dtype=np.int32)
             scales = None if scales_yx is None else \
                 np.asarray(torch.as_tensor(scales_yx).cpu().numpy(), dtype=np.float32)
-            t = self.run(x, sizes, scales, max_det, min_det, ro.nms_thresh, float(pad_value))
+            ign = None if ignorey is None else np.asarray(torch.as_tensor(ignorey).cpu().numpy(), dtype=np.float32)
+            t = self.run(x, sizes, scales, max_det, min_det, ro.nms_thresh, float(pad_value), ignorey=ign)
             t.pop("_keepalive")
             keep = t.pop("keep_idx")
             counts = t["preds_per_image"].cpu().to(torch.int64)  # the one sync; int64 like frcnn.py:1985
