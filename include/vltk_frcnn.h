@@ -202,6 +202,14 @@ int64_t vltk_frcnn_launch_count(vltk_frcnn_t* h);
 int vltk_frcnn_profile_enable(vltk_frcnn_t* h, int enable);
 int vltk_frcnn_profile_read(vltk_frcnn_t* h, double* agg, char* csv, size_t cap);
 
+/* Reader side (vltk/abc/adapter.py:186-199 `get(img_id)` over `img_to_row_map`, consumed by
+ * dataset/visnlangdataset.py:370-405): a whole feature column resident in HBM, batches gathered by row index.
+ * out[r, :cols] = table[idx[r], :cols] for r < rows; table [n_rows, ld] f32, idx [rows] int32, out [rows, cols]
+ * f32, all DEVICE, 16-byte aligned; cols, ld multiples of 4.  Rows whose index is outside [0, n_rows) are left
+ * untouched. */
+int vltk_gather_rows_f32(const float* table, int64_t n_rows, int64_t ld, const int32_t* idx, int rows,
+                         int cols, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

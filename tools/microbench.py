@@ -24,6 +24,32 @@ from vltk_b200.frcnn import FRCNN  # noqa: E402
 H, W, STEPS = 800, 1333, 20
 
 
+def gather_bench(hbm):
+    """Device-resident feature column (20 000 images x 36 x 2048 f32 = 5.9 GB), shuffled batches of 256 rows
+    gathered by vltk_gather_rows_f32: algorithmic bytes = read + write of the gathered rows."""
+    from vltk_b200 import _lib
+    L = _lib.lib()
+    n, width, b = 20000, 36 * 2048, 256
+    table = torch.empty((n, width), dtype=torch.float32, device="cuda").normal_()
+    g = torch.Generator().manual_seed(0)
+    idxs = [torch.randperm(n, generator=g)[:b].int().cuda() for _ in range(8)]
+    outb = torch.empty((b, width), dtype=torch.float32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for i in range(3):
+        _lib.check(L.vltk_gather_rows_f32(table.data_ptr(), n, width, idxs[i].data_ptr(), b, width, outb.data_ptr(), st), "gather")
+    assert torch.equal(outb, table[idxs[2].long()])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(40):
+        _lib.check(L.vltk_gather_rows_f32(table.data_ptr(), n, width, idxs[i % 8].data_ptr(), b, width, outb.data_ptr(), st), "gather")
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 40
+    by = 2.0 * b * width * 4
+    return {"rows": b, "row_bytes": width * 4, "ms": ms, "algorithmic_bytes": by, "gbs": by / ms / 1e6,
+            "frac_of_hbm_peak": by / ms / 1e6 / hbm, "images_per_s": b / ms * 1e3}
+
+
 def main():
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm = json.load(open(pk))["hbm_gbs"] if os.path.exists(pk) else 6650.0
@@ -58,6 +84,7 @@ def main():
             "roi_tail": {"ms": ms["roi_tail"]}, "preds": t["preds_per_image"].cpu().tolist(),
         }
         del model
+    out["feature_gather (reader, SURVEY 8 f3)"] = gather_bench(hbm)
     print(json.dumps(out))
 
 

@@ -79,6 +79,8 @@ SYMBOLS = {
     "vltk_frcnn_debug_read": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "vltk_frcnn_launch_count": (C.c_int64, [C.c_void_p]),
     "vltk_frcnn_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "vltk_gather_rows_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p]),
     "vltk_frcnn_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_char_p, C.c_size_t]),
 }
 

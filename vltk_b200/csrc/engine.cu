@@ -1178,6 +1178,36 @@ int vltk_roi_pool_nchw(const float* feat, int n, int c, int hh, int ww, const fl
   return rc;
 }
 
+// one CTA = 16 KB of one output row: 256 threads x 4 independent 16-byte loads (streaming: every byte is used once)
+__global__ void __launch_bounds__(256)
+feature_gather_kernel(const float4* __restrict__ table, int64_t ld4, const int32_t* __restrict__ idx, int64_t n_rows,
+                      int cols4, float4* __restrict__ out) {
+  const int r = blockIdx.y;
+  const int64_t src = idx[r];
+  if (src < 0 || src >= n_rows) return;                 // out-of-range index: row left untouched (host validates)
+  const float4* __restrict__ s = table + src * ld4;
+  float4* __restrict__ d = out + (int64_t)r * cols4;
+  const int c0 = blockIdx.x * 1024 + threadIdx.x;
+  float4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) if (c0 + k * 256 < cols4) v[k] = __ldcs(s + c0 + k * 256);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) if (c0 + k * 256 < cols4) __stcs(d + c0 + k * 256, v[k]);
+}
+
+int vltk_gather_rows_f32(const float* table, int64_t n_rows, int64_t ld, const int32_t* idx, int rows, int cols,
+                         float* out, void* stream) {
+  VLTK_CHECK(table && idx && out, "gather_rows: null argument");
+  VLTK_CHECK(cols % 4 == 0 && ld % 4 == 0 && cols <= ld, "gather_rows: cols and ld must be multiples of 4 floats, cols <= ld");
+  VLTK_CHECK(((uintptr_t)table % 16 == 0) && ((uintptr_t)out % 16 == 0), "gather_rows: pointers must be 16-byte aligned");
+  if (rows <= 0 || cols == 0) return 0;
+  VLTK_CHECK(rows <= 65535, "gather_rows: at most 65535 rows per call");
+  dim3 grid((unsigned)ceil_div(cols / 4, 1024), (unsigned)rows);
+  feature_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)table, ld / 4, idx, n_rows, cols / 4, (float4*)out);
+  VLTK_LAUNCH_CHECK();
+  return 0;
+}
+
 int vltk_roi_outputs(const float* obj_logits, const float* attr_logits, const float* box_deltas, const float* feats,
                      const float* proposals, const int32_t* counts, const int32_t* sizes_hw, const float* scales_yx,
                      int n, int r, int num_classes, int num_attrs, int d, const float weights[4],
