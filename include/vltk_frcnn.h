@@ -210,6 +210,42 @@ int vltk_frcnn_profile_read(vltk_frcnn_t* h, double* agg, char* csv, size_t cap)
 int vltk_gather_rows_f32(const float* table, int64_t n_rows, int64_t ld, const int32_t* idx, int rows,
                          int cols, float* out, void* stream);
 
+/* ---- JPEG front end: replaces the decode inside `cv2.imread` at vltk/compat.py:573-579
+ * (`img_tensorize`, reached from legacy/processing.py:119-129).  The host parses the markers and runs the
+ * (inherently serial) Huffman entropy decoder; dequantisation, the inverse DCT, chroma upsampling and colour
+ * conversion run on the GPU and reproduce libjpeg-turbo's default pipeline (JDCT_ISLOW, fancy upsampling) bit
+ * for bit.  Supported: baseline / extended-sequential Huffman, 8-bit, grayscale or 3 components with 4:4:4,
+ * 4:2:2 or 4:2:0 sampling in one interleaved scan, restart intervals.  Anything else returns -3 (the caller
+ * decides what to do with such a file; nothing is decoded on the CPU behind its back). */
+typedef struct {
+  int width, height, ncomp;
+  int comp_id[3], hs[3], vs[3];
+  int hmax, vmax, mcus_x, mcus_y;
+  int blocks_w[3], blocks_h[3];          /* padded 8x8-block grid of each component                       */
+  int comp_w[3], comp_h[3];              /* real (downsampled) sample extent of each component            */
+  int64_t coef_offset[3], coef_count;    /* int16 elements: component c starts at coef_offset[c]          */
+  int64_t plane_offset[3], plane_bytes;  /* u8 sample planes (row stride blocks_w*8): device scratch      */
+  uint16_t qt[3][64];                    /* quantisation tables, natural (row-major) order                */
+  int restart_interval;
+  int orientation;                       /* EXIF orientation tag (0 = absent); cv2.imread applies it      */
+  int progressive;
+  int color_transform;                   /* Adobe APP14 transform flag, -1 = no Adobe marker              */
+} vltk_jpeg_info;
+
+/* Parses the headers up to the first scan.  0, or -2 (corrupt) / -3 (valid but unsupported). */
+int vltk_jpeg_parse(const uint8_t* data, size_t len, vltk_jpeg_info* info);
+/* Entropy-decodes the scan into `coef` (HOST, >= info.coef_count int16): per component, blocks in raster order
+ * over its padded block grid, 64 coefficients per block in natural order, still quantised. */
+int vltk_jpeg_decode_coefficients(const uint8_t* data, size_t len, int16_t* coef, int64_t coef_capacity);
+/* The same for n images on up to n_threads host threads (images are independent); status[i] per image. */
+int vltk_jpeg_decode_coefficients_batch(int n, const uint8_t* const* datas, const size_t* lens,
+                                        int16_t* const* coefs, const int64_t* capacities, int n_threads,
+                                        int* status);
+/* coef (DEVICE, 16-byte aligned) -> bgr (DEVICE u8 [height, width, 3], the array cv2.imread returns, EXIF
+ * orientation NOT applied); planes = DEVICE scratch of info.plane_bytes.  Stream-ordered, no host sync. */
+int vltk_jpeg_reconstruct(const int16_t* coef, const vltk_jpeg_info* info, uint8_t* planes, uint8_t* bgr,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

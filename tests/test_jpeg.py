@@ -1,0 +1,128 @@
+"""JPEG front end.  Parity chain:
+  cv2.imdecode / PIL (the real libjpeg-turbo the reference calls through cv2.imread, vltk/compat.py:573-579)
+    == oracle/jpeg_oracle.py (numpy + pure-Python restatement)                      [CPU, pins the oracle]
+    == host entropy decoder (C++) coefficients vs the oracle's                       [CPU]
+    == GPU reconstruction / GPU entropy decoder vs cv2.imdecode and the oracle       [GPU, bit-exact]
+Fixtures are encoded on the fly with cv2.imencode from the seeded synthetic images (all sampling modes, qualities,
+odd sizes, restart intervals, grayscale, EXIF orientation)."""
+import io
+
+import numpy as np
+import pytest
+import torch
+
+cv2 = pytest.importorskip("cv2")
+
+SS = {"444": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, "422": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+      "420": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420}
+
+
+def raw_image(h, w, seed):
+    from vltk_b200 import synthetic
+    return synthetic.make_raw_image(max(h, 32), max(w, 32), seed).numpy()[:h, :w].copy()
+
+
+def encode(img, q=85, ss="420", rst=0, gray=False, progressive=False):
+    if gray:
+        img = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+    args = [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, SS[ss]]
+    if rst:
+        args += [cv2.IMWRITE_JPEG_RST_INTERVAL, rst]
+    if progressive:
+        args += [cv2.IMWRITE_JPEG_PROGRESSIVE, 1]
+    ok, buf = cv2.imencode(".jpg", img, args)
+    assert ok
+    return buf.tobytes()
+
+
+def cv2_decode(b):
+    return cv2.imdecode(np.frombuffer(b, np.uint8), cv2.IMREAD_COLOR | cv2.IMREAD_IGNORE_ORIENTATION)
+
+
+SMALL = [(48, 64, "420", 85, 0), (37, 53, "420", 50, 0), (37, 53, "422", 92, 0), (40, 40, "444", 75, 0),
+         (9, 3, "420", 85, 0), (16, 16, "420", 30, 0), (64, 41, "422", 85, 3), (50, 70, "420", 95, 2),
+         (33, 47, "444", 60, 5), (8, 8, "420", 85, 0), (17, 2, "422", 85, 0)]
+
+
+@pytest.mark.parametrize("h,w,ss,q,rst", SMALL)
+def test_oracle_is_bit_exact_with_libjpeg_turbo(h, w, ss, q, rst):
+    from oracle import jpeg_oracle as J
+    b = encode(raw_image(h, w, h * 100 + w), q, ss, rst)
+    ref = cv2_decode(b)
+    assert np.array_equal(J.decode(b), ref)
+    from PIL import Image                       # the other decoder the reference uses (processing/image.py:62-70)
+    pil = np.asarray(Image.open(io.BytesIO(b)).convert("RGB"))[:, :, ::-1]
+    assert np.array_equal(ref, pil)
+
+
+def test_oracle_grayscale():
+    from oracle import jpeg_oracle as J
+    b = encode(raw_image(40, 56, 3), 80, gray=True)
+    assert np.array_equal(J.decode(b), cv2_decode(b))
+
+
+@pytest.mark.parametrize("h,w,ss,q,rst", SMALL + [(120, 200, "420", 98, 0), (120, 200, "420", 20, 7)])
+def test_host_entropy_decoder_matches_oracle(h, w, ss, q, rst):
+    from oracle import jpeg_oracle as J
+    from vltk_b200 import jpeg
+    b = encode(raw_image(h, w, h * 100 + w), q, ss, rst)
+    info, co = jpeg.coefficients(b)
+    I, ref = J.coefficients(b)
+    assert (info.width, info.height, info.ncomp, info.restart_interval) == (w, h, 3, rst)
+    assert np.array_equal(co, np.concatenate([r.reshape(-1) for r in ref]))
+    for c in range(3):
+        assert np.array_equal(np.asarray(info.qt[c][:]), I["qt"][I["comps"][c]["tq"]])
+
+
+def test_unsupported_and_corrupt_files_are_reported_not_decoded():
+    from vltk_b200 import _lib, jpeg
+    with pytest.raises(jpeg.UnsupportedJpeg):
+        jpeg.parse(encode(raw_image(32, 32, 1), progressive=True))
+    with pytest.raises(_lib.LibraryError):
+        jpeg.parse(b"\x89PNG\r\n\x1a\n" + b"\0" * 32)
+    good = encode(raw_image(32, 32, 1))
+    with pytest.raises(_lib.LibraryError):
+        jpeg.coefficients(good[:200])           # truncated inside the tables
+
+
+def test_exif_orientation_is_parsed():
+    from vltk_b200 import jpeg
+    b = encode(raw_image(24, 40, 2))
+    tiff = b"II*\x00\x08\x00\x00\x00" + b"\x01\x00" + b"\x12\x01\x03\x00\x01\x00\x00\x00\x06\x00\x00\x00" + b"\x00\x00\x00\x00"
+    app1 = b"Exif\x00\x00" + tiff
+    seg = b"\xff\xe1" + (len(app1) + 2).to_bytes(2, "big") + app1
+    b6 = b[:2] + seg + b[2:]
+    assert jpeg.parse(b).orientation == 0 and jpeg.parse(b6).orientation == 6
+    ref = cv2.imdecode(np.frombuffer(b6, np.uint8), cv2.IMREAD_COLOR)      # cv2.imread applies the tag
+    plain = torch.from_numpy(cv2_decode(b6))
+    assert np.array_equal(jpeg.apply_orientation(plain, 6).numpy(), ref)
+    for o in range(2, 9):
+        tiff_o = tiff.replace(b"\x06\x00\x00\x00", bytes([o, 0, 0, 0]))
+        bo = b[:2] + b"\xff\xe1" + (len(app1) + 2).to_bytes(2, "big") + b"Exif\x00\x00" + tiff_o + b[2:]
+        ref = cv2.imdecode(np.frombuffer(bo, np.uint8), cv2.IMREAD_COLOR)
+        assert np.array_equal(jpeg.apply_orientation(plain, o).numpy(), ref), o
+
+
+def test_decoder_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from vltk_b200 import _lib, jpeg
+    with pytest.raises(_lib.LibraryError):
+        jpeg.JpegDecoder()
+
+
+GPU_CASES = SMALL + [(600, 1000, "420", 90, 0), (600, 1000, "422", 75, 0), (601, 999, "444", 85, 0),
+                     (800, 1333, "420", 92, 0), (333, 500, "420", 85, 16)]
+
+
+@pytest.mark.gpu
+def test_gpu_decode_is_bit_exact_with_cv2_imread():
+    from vltk_b200 import jpeg
+    dec = jpeg.JpegDecoder()
+    datas = [encode(raw_image(h, w, h * 100 + w), q, ss, rst) for (h, w, ss, q, rst) in GPU_CASES]
+    datas.append(encode(raw_image(40, 56, 3), 80, gray=True))
+    for rep in range(2):                         # second pass reuses the pinned staging buffer
+        outs = dec.decode(datas)
+        for b, o in zip(datas, outs):
+            assert o.is_cuda and o.dtype == torch.uint8
+            assert np.array_equal(o.cpu().numpy(), cv2_decode(b))

@@ -41,6 +41,18 @@ class Out(C.Structure):
         "roi_features", "preds_per_image", "keep_idx")]
 
 
+class JpegInfo(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("ncomp", C.c_int),
+                ("comp_id", C.c_int * 3), ("hs", C.c_int * 3), ("vs", C.c_int * 3),
+                ("hmax", C.c_int), ("vmax", C.c_int), ("mcus_x", C.c_int), ("mcus_y", C.c_int),
+                ("blocks_w", C.c_int * 3), ("blocks_h", C.c_int * 3), ("comp_w", C.c_int * 3), ("comp_h", C.c_int * 3),
+                ("coef_offset", C.c_int64 * 3), ("coef_count", C.c_int64),
+                ("plane_offset", C.c_int64 * 3), ("plane_bytes", C.c_int64),
+                ("qt", (C.c_uint16 * 64) * 3),
+                ("restart_interval", C.c_int), ("orientation", C.c_int), ("progressive", C.c_int),
+                ("color_transform", C.c_int)]
+
+
 class LibraryError(RuntimeError):
     pass
 
@@ -81,6 +93,12 @@ SYMBOLS = {
     "vltk_frcnn_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "vltk_gather_rows_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                        C.c_void_p]),
+    "vltk_jpeg_parse": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(JpegInfo)]),
+    "vltk_jpeg_decode_coefficients": (C.c_int, [C.c_char_p, C.c_size_t, C.c_void_p, C.c_int64]),
+    "vltk_jpeg_decode_coefficients_batch": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t),
+                                                      C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int,
+                                                      C.POINTER(C.c_int)]),
+    "vltk_jpeg_reconstruct": (C.c_int, [C.c_void_p, C.POINTER(JpegInfo), C.c_void_p, C.c_void_p, C.c_void_p]),
     "vltk_frcnn_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_char_p, C.c_size_t]),
 }
 
