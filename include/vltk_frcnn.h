@@ -241,6 +241,20 @@ int vltk_jpeg_decode_coefficients(const uint8_t* data, size_t len, int16_t* coef
 int vltk_jpeg_decode_coefficients_batch(int n, const uint8_t* const* datas, const size_t* lens,
                                         int16_t* const* coefs, const int64_t* capacities, int n_threads,
                                         int* status);
+/* GPU entropy decoding: the host only parses the markers and removes the byte stuffing; the Huffman decoding of
+ * each scan runs on the device (one CTA per image, self-synchronising subsequences — jpeg.cu).
+ *   blob_bound   : bytes of pinned host staging needed for n files of the given lengths
+ *   prepare_batch: fills infos[n], the upload blob (HOST), coef_offsets[n] / coef_total (int16 elements of one
+ *                  batch coefficient buffer, each image 16-byte aligned) and on_gpu[n] (0 for streams with restart
+ *                  intervals: decode those with vltk_jpeg_decode_coefficients and copy them to coef + offset)
+ *   entropy_decode: blob (DEVICE copy, 8-byte aligned) -> coef (DEVICE, zero-filled here); iterations (DEVICE
+ *                  int32[n] or NULL) receives the number of synchronisation iterations per image */
+size_t vltk_jpeg_gpu_blob_bound(int n, const size_t* lens);
+int vltk_jpeg_gpu_prepare_batch(int n, const uint8_t* const* datas, const size_t* lens, vltk_jpeg_info* infos,
+                                uint8_t* blob, size_t cap, size_t* used, int64_t* coef_offsets,
+                                int64_t* coef_total, int* on_gpu);
+int vltk_jpeg_gpu_entropy_decode(int n, const uint8_t* blob, int16_t* coef, int64_t coef_total,
+                                 int32_t* iterations, void* stream);
 /* coef (DEVICE, 16-byte aligned) -> bgr (DEVICE u8 [height, width, 3], the array cv2.imread returns, EXIF
  * orientation NOT applied); planes = DEVICE scratch of info.plane_bytes.  Stream-ordered, no host sync. */
 int vltk_jpeg_reconstruct(const int16_t* coef, const vltk_jpeg_info* info, uint8_t* planes, uint8_t* bgr,

@@ -116,9 +116,32 @@ GPU_CASES = SMALL + [(600, 1000, "420", 90, 0), (600, 1000, "422", 75, 0), (601,
 
 
 @pytest.mark.gpu
-def test_gpu_decode_is_bit_exact_with_cv2_imread():
+def test_gpu_entropy_decoder_matches_host_decoder():
+    """Self-synchronising parallel Huffman decoding on the device == the serial C++ decoder, coefficient for
+    coefficient, on every sampling mode / size / quality (restart-interval files take the host path inside)."""
     from vltk_b200 import jpeg
-    dec = jpeg.JpegDecoder()
+    dec = jpeg.JpegDecoder(entropy="gpu")
+    cases = GPU_CASES + [(600, 1000, "420", 98, 0), (600, 1000, "420", 10, 0), (1333, 800, "444", 95, 0)]
+    datas = [encode(raw_image(h, w, h * 100 + w), q, ss, rst) for (h, w, ss, q, rst) in cases]
+    datas.append(encode(raw_image(40, 56, 3), 80, gray=True))
+    datas.append(encode(np.full((200, 300, 3), 117, np.uint8), 85))          # flat image: the shortest possible codes
+    infos, offs, coef = dec.coefficients(datas)
+    coef = coef.cpu().numpy()
+    iters = dec.last_iterations.cpu().numpy()
+    for i, b in enumerate(datas):
+        _, ref = jpeg.coefficients(b)
+        got = coef[offs[i]: offs[i] + ref.size]
+        bad = np.nonzero(got != ref)[0]
+        assert bad.size == 0, (i, cases[i] if i < len(cases) else "extra", bad[:8], got[bad[:8]], ref[bad[:8]], int(iters[i]))
+    print("sync iterations per image:", iters.tolist())
+    assert iters.max() <= 8      # self-synchronisation: a handful of sweeps, not one per subsequence
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("entropy", ["gpu", "host"])
+def test_gpu_decode_is_bit_exact_with_cv2_imread(entropy):
+    from vltk_b200 import jpeg
+    dec = jpeg.JpegDecoder(entropy=entropy)
     datas = [encode(raw_image(h, w, h * 100 + w), q, ss, rst) for (h, w, ss, q, rst) in GPU_CASES]
     datas.append(encode(raw_image(40, 56, 3), 80, gray=True))
     for rep in range(2):                         # second pass reuses the pinned staging buffer

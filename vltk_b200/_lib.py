@@ -98,6 +98,11 @@ SYMBOLS = {
     "vltk_jpeg_decode_coefficients_batch": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t),
                                                       C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int,
                                                       C.POINTER(C.c_int)]),
+    "vltk_jpeg_gpu_blob_bound": (C.c_size_t, [C.c_int, C.POINTER(C.c_size_t)]),
+    "vltk_jpeg_gpu_prepare_batch": (C.c_int, [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.POINTER(JpegInfo),
+                                              C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int64),
+                                              C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
+    "vltk_jpeg_gpu_entropy_decode": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "vltk_jpeg_reconstruct": (C.c_int, [C.c_void_p, C.POINTER(JpegInfo), C.c_void_p, C.c_void_p, C.c_void_p]),
     "vltk_frcnn_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_char_p, C.c_size_t]),
 }

@@ -6,6 +6,7 @@
 // libjpeg-turbo is specified to produce identical output).
 #include "../../include/vltk_frcnn.h"
 #include "common.cuh"
+#include "jpeg_dev.h"
 
 namespace vltk {
 namespace {
@@ -133,6 +134,249 @@ jpeg_color_kernel(const unsigned char* __restrict__ planes, unsigned char* __res
   o[0] = (unsigned char)B; o[1] = (unsigned char)G; o[2] = (unsigned char)R;
 }
 
+
+// =========================================================================================
+// GPU Huffman entropy decoder.  A JPEG scan is ONE serial bit stream, but Huffman decoders self-synchronise:
+// a decoder started at an arbitrary bit falls into step with the true symbol sequence after a few blocks
+// (Klein & Wiseman 2003; Weissenberger & Schmidt 2018 for JPEG on GPUs).  One CTA per image:
+//   A. the stream is cut into subsequences of S bits; thread t decodes subsequence t from a GUESSED state
+//      (bit t*S, start of a block, first block of an MCU) and records the state in which it crosses into t+1;
+//   B. Jacobi iterations: every thread restarts from its predecessor's recorded end state and re-decodes its own
+//      subsequence; when no recorded state changes any more, every start state is the true one (subsequence 0
+//      starts from the true state, so truth propagates at least one subsequence per iteration and, thanks to
+//      self-synchronisation, usually everywhere at once);
+//   C. a prefix sum over the blocks completed per subsequence gives every thread its first output block, and a
+//      final pass writes the coefficients (DC still as differences);
+// then jpeg_dc_scan_kernel turns the DC differences into values with a per-component prefix sum in scan order.
+// The state machine (including what it does on invalid codes) is identical in all passes, which is what makes
+// the fixed point meaningful.  Output == the host decoder's coefficients, bit for bit (tests/test_jpeg.py).
+struct HState { unsigned int p; unsigned short kb; };   // bit position; k | (block-in-MCU << 8)
+
+__device__ __constant__ unsigned char c_zigzag[64] = {
+    0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+    41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+    30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+__device__ __forceinline__ unsigned int bits_at(const unsigned int* __restrict__ w, unsigned int p) {
+  const unsigned int i = p >> 5, sh = p & 31;
+  return __funnelshift_l(w[i + 1], w[i], sh);
+}
+
+__device__ __forceinline__ void huff_lookup(const DevHuff& T, unsigned int win, int& len, int& sym) {
+  const unsigned int e = T.look[win >> 23];
+  if (e) { len = e >> 8; sym = e & 255; return; }
+  int l = 10;
+  int code = (int)(win >> 22);
+  while (l <= 16 && code > T.maxcode[l]) { ++l; code = (int)(win >> (32 - l)); }
+  if (l > 16) { len = 16; sym = 0; return; }            // invalid code: a fixed, deterministic transition
+  len = l;
+  sym = T.vals[(code + T.valoffset[l]) & 255];
+}
+
+__device__ __forceinline__ int extend_bits(unsigned int win, int len, int s) {
+  const int v = (int)((win << len) >> (32 - s));
+  return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+}
+
+// Decodes symbols that START before end_p.  WRITE: coefficients go to their blocks, starting at scan-order block g.
+template <bool WRITE>
+__device__ __forceinline__ HState decode_range(const unsigned int* __restrict__ words, HState st, unsigned int end_p,
+                                               const DevHuff* __restrict__ T, const DevImage& D, int& nblk, int g,
+                                               short* __restrict__ coef) {
+  unsigned int p = st.p;
+  int k = st.kb & 255, b = st.kb >> 8;
+  nblk = 0;
+  short* out = nullptr;
+  auto locate = [&](int gg) -> short* {
+    const int mcu = gg / D.B, j = gg - mcu * D.B;
+    const int c = D.comp_of_block[j];
+    const int my = mcu / D.mcus_x, mx = mcu - my * D.mcus_x;
+    const long long blk = (long long)(my * D.vs[c] + D.by_of_block[j]) * D.blocks_w[c] + (mx * D.hs[c] + D.bx_of_block[j]);
+    return coef + D.coef_off + D.comp_coef_off[c] + blk * 64;
+  };
+  if (WRITE) { if (g >= D.total_blocks) return st; out = locate(g); }
+  while (p < end_p) {
+    const unsigned int win = bits_at(words, p);
+    const int c = D.comp_of_block[b];
+    if (k == 0) {
+      int len, sym;
+      huff_lookup(T[2 * c], win, len, sym);
+      const int s = sym & 15;
+      if (WRITE && s) out[0] = (short)extend_bits(win, len, s);
+      p += len + s;
+      k = 1;
+    } else {
+      const DevHuff& A = T[2 * c + 1];
+      const int fa = A.fast_ac[win >> 23];
+      if (fa) {
+        k += (fa >> 4) & 15;
+        if (WRITE && k < 64) out[c_zigzag[k]] = (short)(fa >> 8);
+        ++k;
+        p += fa & 15;
+      } else {
+        int len, sym;
+        huff_lookup(A, win, len, sym);
+        const int r = sym >> 4, s = sym & 15;
+        if (s == 0) {
+          k = (r == 15) ? k + 16 : 64;                   // ZRL | EOB
+          p += len;
+        } else {
+          k += r;
+          if (WRITE && k < 64) out[c_zigzag[k]] = (short)extend_bits(win, len, s);
+          ++k;
+          p += len + s;
+        }
+      }
+    }
+    if (k >= 64) {                                       // block complete (or overrun by garbage: same rule)
+      k = 0;
+      b = (b + 1 == D.B) ? 0 : b + 1;
+      ++nblk;
+      if (WRITE) {
+        ++g;
+        if (g >= D.total_blocks) break;                  // the rest of the stream is padding
+        out = locate(g);
+      }
+    }
+  }
+  HState e;
+  e.p = p; e.kb = (unsigned short)(k | (b << 8));
+  return e;
+}
+
+constexpr int HUFF_THREADS = 1024;
+
+__global__ void __launch_bounds__(HUFF_THREADS, 1)
+jpeg_huffman_kernel(const unsigned char* __restrict__ blob, short* __restrict__ coef, int* __restrict__ iters_out) {
+  extern __shared__ __align__(16) unsigned char hsm[];
+  DevHuff* T = reinterpret_cast<DevHuff*>(hsm);
+  unsigned int* Ep = reinterpret_cast<unsigned int*>(hsm + 6 * sizeof(DevHuff));          // [2][MAX]
+  unsigned short* Ekb = reinterpret_cast<unsigned short*>(Ep + 2 * JPEG_MAX_SUBSEQ);     // [2][MAX]
+  int* nb = reinterpret_cast<int*>(Ekb + 2 * JPEG_MAX_SUBSEQ);                           // [MAX] blocks per subsequence
+  __shared__ DevImage D;
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x;
+  const DevImage* imgs = reinterpret_cast<const DevImage*>(blob);
+  if (tid < (int)(sizeof(DevImage) / 4)) reinterpret_cast<int*>(&D)[tid] = reinterpret_cast<const int*>(&imgs[blockIdx.x])[tid];
+  __syncthreads();
+  if (D.nsub == 0) return;                               // host-decoded image (restart intervals) or empty scan
+  {
+    const uint2* src = reinterpret_cast<const uint2*>(blob + D.tables_off);
+    uint2* dst = reinterpret_cast<uint2*>(T);
+    for (int i = tid; i < (int)(6 * sizeof(DevHuff) / 8); i += HUFF_THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
+  const unsigned int* words = reinterpret_cast<const unsigned int*>(blob + D.words_off);
+  const unsigned int total = (unsigned int)D.total_bits, S = (unsigned int)D.S;
+  const int nsub = D.nsub;
+  auto end_of = [&](int t) { const unsigned long long e = (unsigned long long)(t + 1) * S; return e < total ? (unsigned int)e : total; };
+
+  // ---- A: guessed starts
+  for (int t = tid; t < nsub; t += HUFF_THREADS) {
+    HState st; st.p = (unsigned int)t * S; st.kb = 0;
+    int n;
+    const HState e = decode_range<false>(words, st, end_of(t), T, D, n, 0, nullptr);
+    Ep[t] = e.p; Ekb[t] = e.kb; nb[t] = n;
+  }
+  __syncthreads();
+  // ---- B: iterate to the fixed point (double-buffered states: read `cur`, write `cur ^ 1`)
+  int cur = 0, iters = 0;
+  for (;; ++iters) {
+    int changed = 0;
+    for (int t = tid; t < nsub; t += HUFF_THREADS) {
+      HState e;
+      int n = nb[t];
+      if (t == 0) { e.p = Ep[cur * JPEG_MAX_SUBSEQ]; e.kb = Ekb[cur * JPEG_MAX_SUBSEQ]; }
+      else {
+        HState st; st.p = Ep[cur * JPEG_MAX_SUBSEQ + t - 1]; st.kb = Ekb[cur * JPEG_MAX_SUBSEQ + t - 1];
+        e = decode_range<false>(words, st, end_of(t), T, D, n, 0, nullptr);
+        if (e.p != Ep[cur * JPEG_MAX_SUBSEQ + t] || e.kb != Ekb[cur * JPEG_MAX_SUBSEQ + t] || n != nb[t]) changed = 1;
+      }
+      Ep[(cur ^ 1) * JPEG_MAX_SUBSEQ + t] = e.p; Ekb[(cur ^ 1) * JPEG_MAX_SUBSEQ + t] = e.kb; nb[t] = n;
+    }
+    cur ^= 1;
+    if (!__syncthreads_or(changed) || iters > nsub) break;
+  }
+  if (tid == 0 && iters_out) iters_out[blockIdx.x] = iters;
+  // ---- exclusive prefix sum of nb[] (chunks of 1024 with a running carry)
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nsub; base += HUFF_THREADS) {
+    const int t = base + tid;
+    const int v = t < nsub ? nb[t] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((tid & 31) >= o) x += y; }
+    if ((tid & 31) == 31) s_warp[tid >> 5] = x;
+    __syncthreads();
+    if (tid < 32) {
+      int w = s_warp[tid];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (tid >= o) w += y; }
+      s_warp[tid] = w;
+    }
+    __syncthreads();
+    const int incl = x + ((tid >> 5) ? s_warp[(tid >> 5) - 1] : 0) + s_carry;
+    if (t < nsub) nb[t] = incl - v;                      // exclusive
+    __syncthreads();
+    if (tid == HUFF_THREADS - 1) s_carry = incl;
+    __syncthreads();
+  }
+  // ---- C: write
+  for (int t = tid; t < nsub; t += HUFF_THREADS) {
+    HState st;
+    if (t == 0) { st.p = 0; st.kb = 0; }
+    else { st.p = Ep[cur * JPEG_MAX_SUBSEQ + t - 1]; st.kb = Ekb[cur * JPEG_MAX_SUBSEQ + t - 1]; }
+    int n;
+    decode_range<true>(words, st, end_of(t), T, D, n, nb[t], coef);
+  }
+}
+
+// DC differences -> DC values: inclusive prefix sum over each component's blocks in scan order (one CTA each).
+__global__ void __launch_bounds__(1024)
+jpeg_dc_scan_kernel(const unsigned char* __restrict__ blob, short* __restrict__ coef) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const DevImage& D = reinterpret_cast<const DevImage*>(blob)[blockIdx.x];
+  const int c = blockIdx.y, tid = threadIdx.x;
+  if (D.nsub == 0 || c >= D.ncomp) return;
+  const int per_mcu = D.hs[c] * D.vs[c];
+  const int n = (D.total_blocks / D.B) * per_mcu;
+  short* base = coef + D.coef_off + D.comp_coef_off[c];
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < n; b0 += 1024) {
+    const int i = b0 + tid;
+    long long pos = 0;
+    int v = 0;
+    if (i < n) {
+      const int mcu = i / per_mcu, j = i - mcu * per_mcu;
+      const int by = j / D.hs[c], bx = j - by * D.hs[c];
+      const int my = mcu / D.mcus_x, mx = mcu - my * D.mcus_x;
+      pos = ((long long)(my * D.vs[c] + by) * D.blocks_w[c] + (mx * D.hs[c] + bx)) * 64;
+      v = base[pos];
+    }
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((tid & 31) >= o) x += y; }
+    if ((tid & 31) == 31) s_warp[tid >> 5] = x;
+    __syncthreads();
+    if (tid < 32) {
+      int w = s_warp[tid];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (tid >= o) w += y; }
+      s_warp[tid] = w;
+    }
+    __syncthreads();
+    const int incl = x + ((tid >> 5) ? s_warp[(tid >> 5) - 1] : 0) + s_carry;
+    if (i < n) base[pos] = (short)incl;
+    __syncthreads();
+    if (tid == 1023) s_carry = incl;
+    __syncthreads();
+  }
+}
+
 }  // namespace
 }  // namespace vltk
 
@@ -163,6 +407,23 @@ int vltk_jpeg_reconstruct(const int16_t* coef, const vltk_jpeg_info* I, uint8_t*
   VLTK_LAUNCH_CHECK();
   dim3 grid(ceil_div(I->width, 256), I->height);
   jpeg_color_kernel<<<grid, 256, 0, st>>>(planes, bgr, g);
+  VLTK_LAUNCH_CHECK();
+  return 0;
+}
+
+int vltk_jpeg_gpu_entropy_decode(int n, const uint8_t* blob, int16_t* coef, int64_t coef_total, int32_t* iterations,
+                                 void* stream) {
+  VLTK_CHECK(blob && coef && n >= 0, "jpeg_gpu_entropy_decode: null argument");
+  VLTK_CHECK(((uintptr_t)blob % 8 == 0) && ((uintptr_t)coef % 16 == 0), "jpeg_gpu_entropy_decode: blob must be 8-byte and coef 16-byte aligned");
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = 6 * sizeof(DevHuff) + (size_t)JPEG_MAX_SUBSEQ * (2 * 4 + 2 * 2 + 4);
+  static DeviceOnce once;
+  if (once.first()) VLTK_CUDA(cudaFuncSetAttribute(jpeg_huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VLTK_CUDA(cudaMemsetAsync(coef, 0, (size_t)coef_total * sizeof(int16_t), st));
+  jpeg_huffman_kernel<<<n, HUFF_THREADS, smem, st>>>(blob, coef, iterations);
+  VLTK_LAUNCH_CHECK();
+  jpeg_dc_scan_kernel<<<dim3(n, 3), 1024, 0, st>>>(blob, coef);
   VLTK_LAUNCH_CHECK();
   return 0;
 }

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/vltk_frcnn.h"
+#include "jpeg_dev.h"
 
 namespace vltk {
 void set_error(const char* fmt, ...);
@@ -403,6 +404,107 @@ int vltk_jpeg_decode_coefficients_batch(int n, const uint8_t* const* datas, cons
   }
   for (int i = 0; i < n; ++i)
     if (status[i]) { set_error("image %d: %s", i, errs[i].c_str()); return status[i]; }
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- preparation for the GPU entropy decoder: tables + destuffed big-endian words, no Huffman work on the host
+namespace {
+
+void fill_dev_huff(const HuffTable& H, vltk::DevHuff* D) {
+  memset(D, 0, sizeof(*D));
+  memcpy(D->look, H.look, sizeof(D->look));
+  memcpy(D->fast_ac, H.fast_ac, sizeof(D->fast_ac));
+  memcpy(D->maxcode, H.maxcode, sizeof(D->maxcode));
+  memcpy(D->valoffset, H.valoffset, sizeof(D->valoffset));
+  memcpy(D->vals, H.vals, sizeof(D->vals));
+}
+
+// Copies the entropy-coded segment without its stuffed zero bytes, stops at the first real marker, packs the
+// bytes into big-endian 32-bit words (+ 3 zero guard words).  Returns the number of payload bytes.
+size_t destuff(const uint8_t* s, const uint8_t* end, uint32_t* words) {
+  size_t nb = 0;
+  uint8_t* out = reinterpret_cast<uint8_t*>(words);
+  while (s < end) {
+    const uint8_t* f = (const uint8_t*)memchr(s, 0xFF, end - s);
+    const size_t run = (f ? f : end) - s;
+    memcpy(out + nb, s, run);
+    nb += run;
+    if (!f) break;
+    if (f + 1 < end && f[1] == 0) { out[nb++] = 0xFF; s = f + 2; continue; }
+    break;                                               // a marker (EOI): end of the scan
+  }
+  const size_t nw = (nb + 3) / 4 + 3;
+  memset(out + nb, 0, nw * 4 - nb);
+  for (size_t i = 0; i < nw; ++i) words[i] = __builtin_bswap32(words[i]);
+  return nb;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t vltk_jpeg_gpu_blob_bound(int n, const size_t* lens) {
+  size_t tot = (size_t)n * sizeof(vltk::DevImage);
+  for (int i = 0; i < n; ++i) tot += 6 * sizeof(vltk::DevHuff) + ((lens[i] + 3) / 4 + 3) * 4 + 16;
+  return tot + 64;
+}
+
+int vltk_jpeg_gpu_prepare_batch(int n, const uint8_t* const* datas, const size_t* lens, vltk_jpeg_info* infos,
+                                uint8_t* blob, size_t cap, size_t* used, int64_t* coef_offsets, int64_t* coef_total,
+                                int* on_gpu) {
+  if (n < 0 || !datas || !lens || !infos || !blob || !used || !coef_offsets || !coef_total || !on_gpu) {
+    set_error("jpeg_gpu_prepare_batch: null argument"); return -2;
+  }
+  if (vltk_jpeg_gpu_blob_bound(n, lens) > cap) { set_error("jpeg_gpu_prepare_batch: blob capacity %zu is too small", cap); return -2; }
+  vltk::DevImage* imgs = reinterpret_cast<vltk::DevImage*>(blob);
+  size_t off = ((size_t)n * sizeof(vltk::DevImage) + 7) & ~(size_t)7;
+  int64_t coff = 0;
+  for (int i = 0; i < n; ++i) {
+    Parsed P;
+    const int rc = parse(datas[i], lens[i], &P);
+    infos[i] = P.info;
+    if (rc) { const std::string m = vltk_frcnn_last_error(); set_error("image %d: %s", i, m.c_str()); return rc; }
+    const vltk_jpeg_info& I = P.info;
+    vltk::DevImage& D = imgs[i];
+    memset(&D, 0, sizeof(D));
+    coef_offsets[i] = coff;
+    D.coef_off = coff;
+    coff += (I.coef_count + 7) / 8 * 8;
+    on_gpu[i] = I.restart_interval == 0;                 // restart-interval streams stay on the host decoder
+    if (!on_gpu[i]) continue;
+    D.tables_off = (int64_t)off;
+    vltk::DevHuff* T = reinterpret_cast<vltk::DevHuff*>(blob + off);
+    for (int c = 0; c < 3; ++c) {
+      const int cc = c < I.ncomp ? c : 0;
+      fill_dev_huff(P.dc[P.td[cc]], T + 2 * c);
+      fill_dev_huff(P.ac[P.ta[cc]], T + 2 * c + 1);
+    }
+    off += 6 * sizeof(vltk::DevHuff);
+    D.words_off = (int64_t)off;
+    const size_t nb = destuff(datas[i] + P.scan_offset, datas[i] + lens[i], reinterpret_cast<uint32_t*>(blob + off));
+    off += ((nb + 3) / 4 + 3) * 4;
+    off = (off + 7) & ~(size_t)7;
+    D.total_bits = (int64_t)nb * 8;
+    int64_t S = (D.total_bits + 1023) / 1024;            // ~1 subsequence per thread of the 1024-thread CTA
+    S = (S + 31) / 32 * 32;
+    if (S < vltk::JPEG_MIN_SUBSEQ_BITS) S = vltk::JPEG_MIN_SUBSEQ_BITS;
+    D.S = (int32_t)S;
+    D.nsub = (int32_t)((D.total_bits + S - 1) / S);
+    if (D.nsub > vltk::JPEG_MAX_SUBSEQ) { set_error("image %d: internal: too many subsequences", i); return -2; }
+    D.ncomp = I.ncomp; D.mcus_x = I.mcus_x;
+    int B = 0;
+    for (int c = 0; c < I.ncomp; ++c) {
+      D.hs[c] = I.hs[c]; D.vs[c] = I.vs[c]; D.blocks_w[c] = I.blocks_w[c]; D.comp_coef_off[c] = I.coef_offset[c];
+      for (int by = 0; by < I.vs[c]; ++by)
+        for (int bx = 0; bx < I.hs[c]; ++bx) { D.comp_of_block[B] = c; D.bx_of_block[B] = bx; D.by_of_block[B] = by; ++B; }
+    }
+    D.B = B;
+    D.total_blocks = I.mcus_x * I.mcus_y * B;
+  }
+  *used = off;
+  *coef_total = coff;
   return 0;
 }
 
