@@ -149,3 +149,38 @@ def test_gpu_decode_is_bit_exact_with_cv2_imread(entropy):
         for b, o in zip(datas, outs):
             assert o.is_cuda and o.dtype == torch.uint8
             assert np.array_equal(o.cpu().numpy(), cv2_decode(b))
+
+
+@pytest.mark.gpu
+def test_jpeg_bytes_to_features_equals_cv2_decoded_path():
+    """forward_jpeg_stream (JPEG bytes -> GPU entropy decode -> IDCT/colour -> fused resize/normalise/pad -> model)
+    returns exactly what the reference-style path returns for the same files decoded by cv2 on the host: the decoded
+    pixels are bit-identical, so every output is too.  Mixed sizes, 3 batches decoded in groups of 2."""
+    from oracle import cases
+    from vltk_b200.frcnn import FRCNN
+    from vltk_b200.preprocess import Preprocess
+    from tests.util import weights
+    cfg = cases.case_config("mixed")
+    model = FRCNN.from_pretrained(state_dict=weights(0), config=cfg, mode="fp32")
+    model.roi_outputs.min_detections, model.roi_outputs.max_detections = cfg.min_detections, cfg.max_detections
+    model.roi_outputs.nms_thresh = list(cfg.nms_thresh_test)
+    pre = Preprocess(cfg)
+    shapes = [[(150, 200), (240, 160)], [(180, 180), (120, 260)], [(200, 150)]]
+    batches = [[encode(raw_image(h, w, 10 * bi + j), 90, "420") for j, (h, w) in enumerate(b)] for bi, b in enumerate(shapes)]
+    got = list(model.forward_jpeg_stream(iter(batches), pre, group=2))
+    assert len(got) == 3
+    for b, g in zip(batches, got):
+        raws = [torch.from_numpy(cv2_decode(d)) for d in b]
+        ids, images, sizes, scales = pre(raws)
+        ref = model(images, sizes, scales_yx=scales, padding="max_detections", return_tensors="np")
+        for k in ("obj_ids", "attr_ids", "boxes", "roi_features", "obj_probs", "preds_per_image", "normalized_boxes"):
+            assert np.array_equal(g[k], ref[k]), k
+    # Preprocess itself takes encoded bytes / .jpg paths and routes them through the GPU front end
+    ids, images, sizes, scales = pre(batches[0])
+    ids2, images2, _, _ = pre([torch.from_numpy(cv2_decode(d)) for d in batches[0]])
+    assert torch.equal(images, images2)
+    from vltk_b200 import jpeg
+    with pytest.raises(jpeg.UnsupportedJpeg):
+        pre([encode(raw_image(64, 64, 1), progressive=True)])
+    ok = Preprocess(cfg, host_decode_unsupported=True)([encode(raw_image(64, 64, 1), progressive=True)])
+    assert ok[1].shape[0] == 1

@@ -295,6 +295,78 @@ class FRCNN:
             while pending:
                 yield collect(pending.pop(0))
 
+    def forward_jpeg_stream(self, batches, preprocess, group: int = 8, max_detections=None, pad_value=0.0):
+        """Encoded-bytes front door of the extraction path: `batches` yields lists of JPEG byte strings (one list
+        = one model batch).  `group` batches at a time are decoded by ONE call of the GPU JPEG front end (one CTA
+        per image: the more images per call, the better its few-SM kernels amortise), then each batch is
+        resized/normalised/padded by the fused preprocess kernel, run, and read back asynchronously.  Yields one
+        dict of numpy arrays per batch, in order, like `forward_stream` (plus `scales_yx`)."""
+        if not self._finalized:
+            raise RuntimeError("load_state_dict() has not been called")
+        ro = self.roi_outputs
+        md = int(max_detections or ro.max_detections)
+        mind = min(int(ro.min_detections), md)
+        dev = self.device
+        keys = ("obj_ids", "obj_probs", "attr_ids", "attr_probs", "boxes", "roi_features", "preds_per_image",
+                "normalized_boxes", "keep_idx")
+        depth = 2
+        with torch.cuda.device(dev):
+            compute = torch.cuda.current_stream(dev)
+            s_out = torch.cuda.Stream(device=dev)
+            slots = [dict(ev_done=torch.cuda.Event(), ev_out=torch.cuda.Event(), host=None, busy=False) for _ in range(depth)]
+            pending = []
+
+            def collect(sl):
+                sl["ev_out"].synchronize()
+                out = OrderedDict((k, sl["host"][k].numpy().copy()) for k in keys)
+                out["preds_per_image"] = out["preds_per_image"].astype(np.int64)
+                out["sizes"] = sl["sizes"].astype(np.int64)
+                out["scales_yx"] = sl["scales"]
+                sl["busy"] = False
+                return out
+
+            it = iter(batches)
+            i = 0
+            while True:
+                grp = []
+                for _ in range(group):
+                    b = next(it, None)
+                    if b is None:
+                        break
+                    grp.append(list(b))
+                if not grp:
+                    break
+                flat = [d for b in grp for d in b]
+                imgs = preprocess._decode_jpegs(flat)            # one front-end call for the whole group
+                o = 0
+                for b in grp:
+                    sl = slots[i % depth]
+                    i += 1
+                    if sl["busy"]:
+                        yield collect(pending.pop(0))
+                    part = imgs[o:o + len(b)]
+                    o += len(b)
+                    _, x, sizes_t, scales_t = preprocess(part, sync=False)
+                    sizes = np.asarray(sizes_t.numpy(), dtype=np.int32)
+                    scales = np.asarray(scales_t.numpy(), dtype=np.float32)
+                    compute.wait_event(sl["ev_out"])
+                    t = self.run(x, sizes, scales, md, mind, ro.nms_thresh, float(pad_value))
+                    sl["_ka"] = (t.pop("_keepalive"), part)
+                    sl["ev_done"].record(compute)
+                    if sl["host"] is None or sl["host"]["roi_features"].shape != t["roi_features"].shape:
+                        sl["host"] = {k: torch.empty(t[k].shape, dtype=t[k].dtype).pin_memory() for k in keys}
+                    with torch.cuda.stream(s_out):
+                        s_out.wait_event(sl["ev_done"])
+                        for k in keys:
+                            sl["host"][k].copy_(t[k], non_blocking=True)
+                        sl["ev_out"].record(s_out)
+                    sl["dev_out"], sl["sizes"], sl["scales"], sl["busy"] = t, sizes, scales, True
+                    pending.append(sl)
+                    if len(pending) >= depth:
+                        yield collect(pending.pop(0))
+            while pending:
+                yield collect(pending.pop(0))
+
     # ------------------------------------------------------------------ test taps
     def debug_read(self, name: str, dtype=np.float32) -> np.ndarray:
         """Copies an intermediate of the last forward to the host (tests only)."""
