@@ -72,6 +72,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 prefetch of a tiled box: starts the HBM -> L2 transfer without occupying shared memory
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c, int w,
                                                    int h, int n, uint16_t off_w, uint16_t off_h) {
   asm volatile(
@@ -346,6 +352,9 @@ struct TcParams2 {
   // pool_partial[(m_tile*2 + seg) * Cout + c]; pool_finish() adds the 2-3 partials per ROI in a fixed order.
   float* pool_partial;
   int pool_rows;
+  // residual producer: tiles of look-ahead for an L2 prefetch of the shortcut tensor (0 = off, the default: it
+  // measured slower — the layer is bandwidth-bound, see conv_tc_launch)
+  int res_prefetch;
 };
 
 template <int BN, int STAGES, bool HAS_RES, int EG = 1>
@@ -488,9 +497,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (HAS_RES && warp == 3 && lane == 0) {
     // ================= residual producer =================
     int slot = 0; uint32_t phase = 0;
+    if (p.res_prefetch > 0)                            // warm-up: the first tiles of this CTA
+      for (int k = 0, t = blockIdx.x; k < p.res_prefetch && t < p.num_tiles; ++k, t += gridDim.x)
+        for (int s = 0; s < NSLAB; ++s) tma_prefetch_2d(&tmR, (t % p.n_tiles) * BN + s * SLAB, (t / p.n_tiles) * BM);
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       const int n0 = (t % p.n_tiles) * BN;
       const int m0 = (t / p.n_tiles) * BM;
+      if (p.res_prefetch > 0) {
+        const long long tp = (long long)t + (long long)p.res_prefetch * gridDim.x;
+        if (tp < p.num_tiles)
+          for (int s = 0; s < NSLAB; ++s)
+            tma_prefetch_2d(&tmR, (int)(tp % p.n_tiles) * BN + s * SLAB, (int)(tp / p.n_tiles) * BM);
+      }
       for (int s = 0; s < NSLAB; ++s) {
         mbar_wait(rempty_bar(slot), phase ^ 1u);
         mbar_expect_tx(rfull_bar(slot), SLAB_BYTES);
@@ -923,6 +941,10 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
     t2.OH = p.OH; t2.OW = p.OW; t2.stride = p.stride; t2.pad = p.pad; t2.dil = p.dil; t2.KW = p.KW;
     t2.taps = p.KH * p.KW; t2.cblocks = p.Cin / BK; t2.n_tiles = 0; t2.num_tiles = 0;
     t2.pool_partial = nullptr; t2.pool_rows = 1;
+    // measured on B200 (profiles/r01_summary.md §19): the residual layers are DRAM-bandwidth-bound, not latency-bound —
+    // prefetching 2 / 4 tiles ahead made res5 conv3 SLOWER (1.10 -> 1.19 / 1.29 ms).  Off by default; knob kept.
+    static const int res_pf = [] { const char* e = getenv("VLTK_RES_PF"); return e ? atoi(e) : 0; }();
+    t2.res_prefetch = p.residual ? res_pf : 0;
     t2.npass = is_split ? 3 : 1;                       // hi*hi, lo*hi, hi*lo
     t2.pass_a[0] = 0; t2.pass_a[1] = 1; t2.pass_a[2] = 0;
     t2.pass_b[0] = 0; t2.pass_b[1] = 0; t2.pass_b[2] = 1;
