@@ -57,19 +57,18 @@ def test_extract_writes_arrow_rows_equal_to_direct_calls(engine, tmp_path):
     model, cfg = engine
     pre = Preprocess(cfg)
     ids = [f"img{i:03d}" for i in range(7)]
-    path = extract(_source, ids, model, pre, str(tmp_path), split="train", batch_size=3,
+    path = extract(_source, ids, model, pre, str(tmp_path), split="train", batch_size=3, bucket=False,
                    meta={"dataset": "synthetic", "model_config": {"max_detections": cfg.max_detections}})
     table, meta = read_arrow(path)
     assert table.num_rows == 7
     assert json.loads(meta["img_to_row_map"]) == {k: i for i, k in enumerate(ids)}
     rows = table.to_pylist()
 
-    def check_against_direct_batches(rows, order, batch):
+    def check_against_direct_batches(rows, order, batch, batches=None):
         """Every Arrow row must equal a direct model call on THE SAME BATCH.  (Not on the image
         alone: like the reference's Preprocess.pad, a batch is zero-padded to its largest member,
         and the padded border legitimately changes features near the image edge.)"""
-        for s0 in range(0, len(order), batch):
-            idx = order[s0:s0 + batch]
+        for idx in (batches or [order[s0:s0 + batch] for s0 in range(0, len(order), batch)]):
             _, images, sizes, scales = pre([torch.from_numpy(_source(i)) for i in idx])
             d = model(images, sizes, scales_yx=scales, padding="max_detections", return_tensors="np")
             for j, i in enumerate(idx):
@@ -89,8 +88,17 @@ def test_extract_writes_arrow_rows_equal_to_direct_calls(engine, tmp_path):
     check_against_direct_batches({r["imgid"]: r for r in rows}, list(range(7)), 3)
     # sharding: rank r of 2 owns images i with i mod 2 == r and writes exactly those rows
     for rank in range(2):
-        pth = extract(_source, ids, model, pre, str(tmp_path / "s"), batch_size=2, rank=rank, world=2)
+        pth = extract(_source, ids, model, pre, str(tmp_path / "s"), batch_size=2, rank=rank, world=2, bucket=False)
         t, _ = read_arrow(pth)
         part = t.to_pylist()
         assert [r["imgid"] for r in part] == ids[rank::2]
         check_against_direct_batches({r["imgid"]: r for r in part}, list(range(rank, 7, 2)), 2)
+    # default bucketing: batches are formed by plan_batches (equal resized sizes together); rows stay in id order
+    from vltk_b200.extract import plan_batches
+    pth = extract(_source, ids, model, pre, str(tmp_path / "b"), batch_size=3)
+    t, _ = read_arrow(pth)
+    rows_b = t.to_pylist()
+    assert [r["imgid"] for r in rows_b] == ids
+    plan = plan_batches([_source(i).shape[:2] for i in range(7)], cfg, 3, True)
+    assert sorted(j for b in plan for j in b) == list(range(7))
+    check_against_direct_batches({r["imgid"]: r for r in rows_b}, None, 3, batches=plan)

@@ -296,11 +296,12 @@ class FRCNN:
                 yield collect(pending.pop(0))
 
     def forward_jpeg_stream(self, batches, preprocess, group: int = 8, max_detections=None, pad_value=0.0):
-        """Encoded-bytes front door of the extraction path: `batches` yields lists of JPEG byte strings (one list
-        = one model batch).  `group` batches at a time are decoded by ONE call of the GPU JPEG front end (one CTA
-        per image: the more images per call, the better its few-SM kernels amortise), then each batch is
-        resized/normalised/padded by the fused preprocess kernel, run, and read back asynchronously.  Yields one
-        dict of numpy arrays per batch, in order, like `forward_stream` (plus `scales_yx`)."""
+        """Raw-image front door of the extraction path: `batches` yields lists whose entries are JPEG byte strings
+        and/or decoded BGR u8 [h,w,3] arrays/tensors (one list = one model batch).  The encoded entries of `group`
+        batches at a time are decoded by ONE call of the GPU JPEG front end (one CTA per image: the more images
+        per call, the better its few-SM kernels amortise), then each batch is resized/normalised/padded by the
+        fused preprocess kernel, run, and read back asynchronously.  Yields one dict of numpy arrays per batch,
+        in order, like `forward_stream` (plus `scales_yx`)."""
         if not self._finalized:
             raise RuntimeError("load_state_dict() has not been called")
         ro = self.roi_outputs
@@ -337,7 +338,11 @@ class FRCNN:
                 if not grp:
                     break
                 flat = [d for b in grp for d in b]
-                imgs = preprocess._decode_jpegs(flat)            # one front-end call for the whole group
+                enc = [j for j, d in enumerate(flat) if isinstance(d, (bytes, bytearray, memoryview))]
+                imgs = list(flat)
+                if enc:                                          # one front-end call for the whole group
+                    for j, t in zip(enc, preprocess._decode_jpegs([bytes(flat[j]) for j in enc])):
+                        imgs[j] = t
                 o = 0
                 for b in grp:
                     sl = slots[i % depth]
@@ -366,6 +371,8 @@ class FRCNN:
                         yield collect(pending.pop(0))
             while pending:
                 yield collect(pending.pop(0))
+
+    forward_raw_stream = forward_jpeg_stream
 
     # ------------------------------------------------------------------ test taps
     def debug_read(self, name: str, dtype=np.float32) -> np.ndarray:
