@@ -245,8 +245,8 @@ int vltk_jpeg_decode_coefficients_batch(int n, const uint8_t* const* datas, cons
  * each scan runs on the device (one CTA per image, self-synchronising subsequences — jpeg.cu).
  *   blob_bound   : bytes of pinned host staging needed for n files of the given lengths
  *   prepare_batch: fills infos[n], the upload blob (HOST), coef_offsets[n] / coef_total (int16 elements of one
- *                  batch coefficient buffer, each image 16-byte aligned) and on_gpu[n] (0 for streams with restart
- *                  intervals: decode those with vltk_jpeg_decode_coefficients and copy them to coef + offset)
+ *                  batch coefficient buffer, each image 16-byte aligned) and on_gpu[n] (1 = decoded by
+ *                  entropy_decode; reserved for stream kinds that must take vltk_jpeg_decode_coefficients instead)
  *   entropy_decode: blob (DEVICE copy, 8-byte aligned) -> coef (DEVICE, zero-filled here); iterations (DEVICE
  *                  int32[n] or NULL) receives the number of synchronisation iterations per image */
 size_t vltk_jpeg_gpu_blob_bound(int n, const size_t* lens);

@@ -179,13 +179,17 @@ __device__ __forceinline__ int extend_bits(unsigned int win, int len, int s) {
 }
 
 // Decodes symbols that START before end_p.  WRITE: coefficients go to their blocks, starting at scan-order block g.
-template <bool WRITE>
+// DCPRED (restart-interval streams): the thread owns whole intervals, so it integrates the DC differences itself
+// (prediction starts at 0) and stops after `max_blocks` blocks.
+template <bool WRITE, bool DCPRED = false>
 __device__ __forceinline__ HState decode_range(const unsigned int* __restrict__ words, HState st, unsigned int end_p,
                                                const DevHuff* __restrict__ T, const DevImage& D, int& nblk, int g,
-                                               short* __restrict__ coef) {
+                                               short* __restrict__ coef, int max_blocks = 0x7fffffff) {
   unsigned int p = st.p;
   int k = st.kb & 255, b = st.kb >> 8;
   nblk = 0;
+  int pred[3] = {0, 0, 0};
+  (void)pred;
   short* out = nullptr;
   auto locate = [&](int gg) -> short* {
     const int mcu = gg / D.B, j = gg - mcu * D.B;
@@ -202,7 +206,10 @@ __device__ __forceinline__ HState decode_range(const unsigned int* __restrict__ 
       int len, sym;
       huff_lookup(T[2 * c], win, len, sym);
       const int s = sym & 15;
-      if (WRITE && s) out[0] = (short)extend_bits(win, len, s);
+      if (DCPRED) {
+        if (s) pred[c] += extend_bits(win, len, s);
+        out[0] = (short)pred[c];
+      } else if (WRITE && s) out[0] = (short)extend_bits(win, len, s);
       p += len + s;
       k = 1;
     } else {
@@ -234,7 +241,7 @@ __device__ __forceinline__ HState decode_range(const unsigned int* __restrict__ 
       ++nblk;
       if (WRITE) {
         ++g;
-        if (g >= D.total_blocks) break;                  // the rest of the stream is padding
+        if (g >= D.total_blocks || nblk >= max_blocks) break;   // the rest of the stream / interval is padding
         out = locate(g);
       }
     }
@@ -260,7 +267,25 @@ jpeg_huffman_kernel(const unsigned char* __restrict__ blob, short* __restrict__ 
   const DevImage* imgs = reinterpret_cast<const DevImage*>(blob);
   if (tid < (int)(sizeof(DevImage) / 4)) reinterpret_cast<int*>(&D)[tid] = reinterpret_cast<const int*>(&imgs[blockIdx.x])[tid];
   __syncthreads();
-  if (D.nsub == 0) return;                               // host-decoded image (restart intervals) or empty scan
+  if (D.restart_interval > 0) {                          // exact start states: one pass, no synchronisation
+    {
+      const uint2* src = reinterpret_cast<const uint2*>(blob + D.tables_off);
+      uint2* dst = reinterpret_cast<uint2*>(T);
+      for (int i = tid; i < (int)(6 * sizeof(DevHuff) / 8); i += HUFF_THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+    const unsigned int* words = reinterpret_cast<const unsigned int*>(blob + D.words_off);
+    const unsigned int* starts = reinterpret_cast<const unsigned int*>(blob + D.starts_off);
+    const int per = D.restart_interval * D.B;
+    for (int t = tid; t < D.n_intervals; t += HUFF_THREADS) {
+      HState st; st.p = starts[t]; st.kb = 0;
+      int n;
+      decode_range<true, true>(words, st, (unsigned int)D.total_bits, T, D, n, t * per, coef, per);
+    }
+    if (tid == 0 && iters_out) iters_out[blockIdx.x] = 0;
+    return;
+  }
+  if (D.nsub == 0) return;                               // empty scan
   {
     const uint2* src = reinterpret_cast<const uint2*>(blob + D.tables_off);
     uint2* dst = reinterpret_cast<uint2*>(T);
@@ -340,7 +365,7 @@ jpeg_dc_scan_kernel(const unsigned char* __restrict__ blob, short* __restrict__ 
   __shared__ int s_carry;
   const DevImage& D = reinterpret_cast<const DevImage*>(blob)[blockIdx.x];
   const int c = blockIdx.y, tid = threadIdx.x;
-  if (D.nsub == 0 || c >= D.ncomp) return;
+  if (D.nsub == 0 || c >= D.ncomp || D.restart_interval > 0) return;   // interval streams carry final DC values already
   const int per_mcu = D.hs[c] * D.vs[c];
   const int n = (D.total_blocks / D.B) * per_mcu;
   short* base = coef + D.coef_off + D.comp_coef_off[c];

@@ -27,6 +27,10 @@ struct DevImage {
   int32_t ncomp, B, total_blocks, mcus_x;
   int32_t hs[3], vs[3], blocks_w[3];
   int32_t comp_of_block[12], bx_of_block[12], by_of_block[12];
+  // restart-interval streams: every interval starts byte-aligned in a known state, so no synchronisation is needed —
+  // thread t decodes interval t from starts[t] (bit offsets in the destuffed stream, n_intervals entries at starts_off)
+  int32_t restart_interval, n_intervals;
+  int64_t starts_off;
 };
 
 }  // namespace vltk

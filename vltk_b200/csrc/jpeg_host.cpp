@@ -421,11 +421,13 @@ void fill_dev_huff(const HuffTable& H, vltk::DevHuff* D) {
   memcpy(D->vals, H.vals, sizeof(D->vals));
 }
 
-// Copies the entropy-coded segment without its stuffed zero bytes, stops at the first real marker, packs the
-// bytes into big-endian 32-bit words (+ 3 zero guard words).  Returns the number of payload bytes.
-size_t destuff(const uint8_t* s, const uint8_t* end, uint32_t* words) {
+// Copies the entropy-coded segment without its stuffed zero bytes, stops at the first marker that is not RSTn, packs
+// the bytes into big-endian 32-bit words (+ 3 zero guard words).  RSTn markers are dropped and the byte offset of the
+// interval that follows each of them is appended to `starts` (the first interval starts at 0).  Returns the payload bytes.
+size_t destuff(const uint8_t* s, const uint8_t* end, uint32_t* words, std::vector<uint32_t>* starts) {
   size_t nb = 0;
   uint8_t* out = reinterpret_cast<uint8_t*>(words);
+  if (starts) starts->push_back(0);
   while (s < end) {
     const uint8_t* f = (const uint8_t*)memchr(s, 0xFF, end - s);
     const size_t run = (f ? f : end) - s;
@@ -433,6 +435,8 @@ size_t destuff(const uint8_t* s, const uint8_t* end, uint32_t* words) {
     nb += run;
     if (!f) break;
     if (f + 1 < end && f[1] == 0) { out[nb++] = 0xFF; s = f + 2; continue; }
+    if (f + 1 < end && f[1] == 0xFF) { s = f + 1; continue; }                    // fill byte
+    if (starts && f + 1 < end && f[1] >= 0xD0 && f[1] <= 0xD7) { starts->push_back((uint32_t)nb); s = f + 2; continue; }
     break;                                               // a marker (EOI): end of the scan
   }
   const size_t nw = (nb + 3) / 4 + 3;
@@ -447,7 +451,8 @@ extern "C" {
 
 size_t vltk_jpeg_gpu_blob_bound(int n, const size_t* lens) {
   size_t tot = (size_t)n * sizeof(vltk::DevImage);
-  for (int i = 0; i < n; ++i) tot += 6 * sizeof(vltk::DevHuff) + ((lens[i] + 3) / 4 + 3) * 4 + 16;
+  // tables + destuffed words + (worst case: one restart interval every 2 bytes of scan data) interval starts
+  for (int i = 0; i < n; ++i) tot += 6 * sizeof(vltk::DevHuff) + ((lens[i] + 3) / 4 + 3) * 4 + (lens[i] / 2 + 2) * 4 + 32;
   return tot + 64;
 }
 
@@ -472,8 +477,7 @@ int vltk_jpeg_gpu_prepare_batch(int n, const uint8_t* const* datas, const size_t
     coef_offsets[i] = coff;
     D.coef_off = coff;
     coff += (I.coef_count + 7) / 8 * 8;
-    on_gpu[i] = I.restart_interval == 0;                 // restart-interval streams stay on the host decoder
-    if (!on_gpu[i]) continue;
+    on_gpu[i] = 1;
     D.tables_off = (int64_t)off;
     vltk::DevHuff* T = reinterpret_cast<vltk::DevHuff*>(blob + off);
     for (int c = 0; c < 3; ++c) {
@@ -483,10 +487,24 @@ int vltk_jpeg_gpu_prepare_batch(int n, const uint8_t* const* datas, const size_t
     }
     off += 6 * sizeof(vltk::DevHuff);
     D.words_off = (int64_t)off;
-    const size_t nb = destuff(datas[i] + P.scan_offset, datas[i] + lens[i], reinterpret_cast<uint32_t*>(blob + off));
+    std::vector<uint32_t> starts;
+    const size_t nb = destuff(datas[i] + P.scan_offset, datas[i] + lens[i], reinterpret_cast<uint32_t*>(blob + off),
+                              I.restart_interval ? &starts : nullptr);
     off += ((nb + 3) / 4 + 3) * 4;
     off = (off + 7) & ~(size_t)7;
     D.total_bits = (int64_t)nb * 8;
+    if (I.restart_interval) {
+      const int64_t mcus = (int64_t)I.mcus_x * I.mcus_y;
+      const int64_t need = (mcus + I.restart_interval - 1) / I.restart_interval;
+      if ((int64_t)starts.size() < need) { set_error("image %d: jpeg: %zu restart intervals found, %lld expected", i, starts.size(), (long long)need); return -2; }
+      D.restart_interval = I.restart_interval;
+      D.n_intervals = (int32_t)need;
+      D.starts_off = (int64_t)off;
+      uint32_t* so = reinterpret_cast<uint32_t*>(blob + off);
+      for (int64_t k = 0; k < need; ++k) so[k] = starts[k] * 8u;
+      off += (size_t)need * 4;
+      off = (off + 7) & ~(size_t)7;
+    }
     int64_t S = (D.total_bits + 1023) / 1024;            // ~1 subsequence per thread of the 1024-thread CTA
     S = (S + 31) / 32 * 32;
     if (S < vltk::JPEG_MIN_SUBSEQ_BITS) S = vltk::JPEG_MIN_SUBSEQ_BITS;

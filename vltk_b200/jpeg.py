@@ -75,8 +75,8 @@ class JpegDecoder:
     stream; `decode(list_of_bytes)` returns one device tensor per image.
 
     entropy="gpu" (default): the host only parses markers and strips the byte stuffing (~0.1 ms per image); the
-    Huffman decoding runs on the device, one CTA per image (self-synchronising subsequences).  Streams with
-    restart intervals are entropy-decoded by the C++ host decoder instead.
+    Huffman decoding runs on the device, one CTA per image (self-synchronising subsequences; streams with restart
+    intervals need no synchronisation: one thread per interval).
     entropy="host": every image is Huffman-decoded on `threads` C++ host threads (GIL released)."""
 
     def __init__(self, device=None, threads: Optional[int] = None, honor_orientation: bool = True, entropy: str = "gpu"):
