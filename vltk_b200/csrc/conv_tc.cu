@@ -862,8 +862,9 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
                    const TcSplit* split, const TcPool* pool, const TcConcat* concat) {
   const bool out_f32 = p.out_dtype == DT_F32;
   const bool is_split = split && split->x_lo && split->w_lo;
+  const bool is_wsplit = split && !split->x_lo && split->w_lo;      // exact bf16 activations, weights = hi + lo
   const bool is_concat = concat && concat->x2 && concat->w2;
-  VLTK_CHECK(!(is_concat && (is_split || (pool && pool->out))), "conv_tc: concat excludes split / pooled epilogue");
+  VLTK_CHECK(!(is_concat && (is_split || is_wsplit || (pool && pool->out))), "conv_tc: concat excludes split / pooled epilogue");
   VLTK_CHECK(!is_concat || (p.KH == 1 && p.KW == 1 && p.pad == 0 && concat->Cin2 % BK == 0 && concat->ldx2 % 8 == 0 &&
                             (concat->H2 - 1) / concat->stride2 + 1 == p.OH && (concat->W2 - 1) / concat->stride2 + 1 == p.OW),
              "conv_tc: concat needs a 1x1 primary conv and a second operand on the same output grid");
@@ -901,7 +902,7 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
 
   static const bool use_v1 = [] { const char* e = getenv("VLTK_TC_V1"); return e && e[0] == '1'; }();
   VLTK_CHECK(!(use_v1 && is_concat), "conv_tc: the v1 kernel has no concat path");
-  if (!use_v1 || out_f32 || is_split) {
+  if (!use_v1 || out_f32 || is_split || is_wsplit) {
     VLTK_CHECK(p.Cout % 64 == 0 && cout_pad == p.Cout, "conv_tc: Cout=%d must be a multiple of 64", p.Cout);
     Maps m;
     m.a = ta; m.b = tb; m.a2 = ta; m.b2 = tb;
@@ -927,6 +928,9 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
       if (cached(TensorMapCache::Key(split->w_lo, K, cout_pad, bn, 0, 0, 0, 0, 0, 0, 1), &m.b2,
                  [&](CUtensorMap* d) { return make_b_map(split->w_lo, K, cout_pad, bn, d); })) return -1;
     }
+    if (is_wsplit &&
+        cached(TensorMapCache::Key(split->w_lo, K, cout_pad, bn, 0, 0, 0, 0, 0, 0, 1), &m.b2,
+               [&](CUtensorMap* d) { return make_b_map(split->w_lo, K, cout_pad, bn, d); })) return -1;
     if (is_concat) {
       ConvProblem p2 = p;
       p2.x = concat->x2; p2.ldx = concat->ldx2; p2.H = concat->H2; p2.W = concat->W2; p2.Cin = concat->Cin2;
@@ -949,6 +953,7 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
     t2.pass_a[0] = 0; t2.pass_a[1] = 1; t2.pass_a[2] = 0;
     t2.pass_b[0] = 0; t2.pass_b[1] = 0; t2.pass_b[2] = 1;
     for (int i = 0; i < 3; ++i) { t2.pass_cblocks[i] = t2.cblocks; t2.pass_stride[i] = p.stride; }
+    if (is_wsplit) { t2.npass = 2; t2.pass_a[1] = 0; t2.pass_b[1] = 1; }   // x*w_hi + x*w_lo
     if (is_concat) {                                   // pass 1 = the second operand pair
       t2.npass = 2; t2.pass_a[1] = 1; t2.pass_b[1] = 1;
       t2.pass_cblocks[1] = concat->Cin2 / BK; t2.pass_stride[1] = concat->stride2;

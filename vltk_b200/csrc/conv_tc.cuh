@@ -21,6 +21,7 @@ struct TensorMapCache {
 //   requires Cin % 64 == 0; scale/shift must hold cout_pad entries.
 // Optional split-precision operands: x = x_hi + x_lo, w = w_hi + w_lo (bf16 pairs).  When given, the
 // kernel accumulates x_hi*w_hi + x_lo*w_hi + x_hi*w_lo in one TMEM tile (fp32-faithful, ~2^-17 rel).
+// With x_lo == nullptr the activations are taken as exact bf16 and only the weights are split: x*w_hi + x*w_lo.
 struct TcSplit {
   const void* x_lo = nullptr;   // same geometry as p.x
   const bf16* w_lo = nullptr;   // same geometry as w_nk

@@ -68,6 +68,7 @@ struct vltk_frcnn {
   std::vector<std::vector<Block>> stages;  // res2, res3, res4
   std::vector<Block> res5;
   LayerW rpn_conv, rpn_head, cls_score, bbox_pred, fc_attr, attr_score;
+  float* rpn_head_shift_simt = nullptr;   // ldw-sized bias of the CUDA-core RPN head (the tensor-pipe copy is padded to 64)
   float* attr_table = nullptr;  // [C+1][512] = emb @ fc_attr.W[:, D:]^T  (bias stays in fc_attr.shift)
   float* cell = nullptr;        // [A,4]
   std::map<std::string, Tap> taps;
@@ -514,6 +515,14 @@ int vltk_frcnn_finalize(vltk_frcnn_t* h) {
     for (int o = 0; o < 4 * A; ++o) sh[o] = (*bd)[o];
     for (int o = 0; o < A; ++o) sh[4 * A + o] = (*bo)[o];
     if (upload(h, kn, &L.w_kn) || upload(h, sh, &L.shift)) return -1;
+    if (tc && hid % 64 == 0) {   // tensor pipe: exact bf16 activations x (w_hi + w_lo), fp32 out, rows padded to 64
+      std::vector<float> wrow((size_t)5 * A * hid), brow(5 * A);
+      for (int o = 0; o < 4 * A; ++o) { brow[o] = (*bd)[o]; for (int k = 0; k < hid; ++k) wrow[(size_t)o * hid + k] = (*wd)[(size_t)o * hid + k]; }
+      for (int o = 0; o < A; ++o) { brow[4 * A + o] = (*bo)[o]; for (int k = 0; k < hid; ++k) wrow[(size_t)(4 * A + o) * hid + k] = (*wo)[(size_t)o * hid + k]; }
+      float* simt_shift = L.shift;
+      if (pack_split_linear(h, L, wrow, 5 * A, hid, hid, brow)) return -1;   // sets w_nk / w_lo / cout_pad and a padded shift
+      h->rpn_head_shift_simt = simt_shift;
+    }
   }
   {
     const auto* ca = find(h, "proposal_generator.anchor_generator.cell_anchors.0", 4 * A);
@@ -585,7 +594,7 @@ static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void*
   p[B_A] = b.take(big * e); p[B_B] = b.take(big * e); p[B_S] = b.take(big * e);
   p[B_T1] = b.take(midsz * e); p[B_T2] = b.take(midsz * e);
   p[B_RPNH] = b.take((size_t)N * s.h4 * s.w4 * c.rpn_hidden * e);
-  p[B_HEAD] = b.take((size_t)N * s.h4 * s.w4 * h->rpn_head.ldw * 4);
+  p[B_HEAD] = b.take((size_t)N * s.h4 * s.w4 * std::max(h->rpn_head.ldw, h->rpn_head.cout_pad) * 4);
   p[B_SIZES] = b.take((size_t)N * 2 * 4); p[B_SCALES] = b.take((size_t)N * 2 * 4);
   p[B_SBOX] = b.take((size_t)N * s.K * 16); p[B_SSCORE] = b.take((size_t)N * s.K * 4);
   p[B_SIDX] = b.take((size_t)N * s.K * 4); p[B_SVALID] = b.take((size_t)N * s.K);
@@ -739,11 +748,35 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
 
   // ---- RPN head + proposal selection (frcnn.py:1561-1572, 264-390)
   if (run_conv(h, h->rpn_conv, res4, d, n, s.h4, s.w4, p[B_RPNH], d, h->rpn_conv.ldw, nullptr, 0, 1, st)) return -1;
-  if (run_conv(h, h->rpn_head, p[B_RPNH], d, n, s.h4, s.w4, p[B_HEAD], DT_F32, h->rpn_head.ldw, nullptr, 0, 0, st)) return -1;
-  tap(h, "rpn_head", p[B_HEAD], (int64_t)n * s.h4 * s.w4 * h->rpn_head.ldw, DT_F32);
+  int ldh = h->rpn_head.ldw;
+  if (h->use_tc && h->rpn_head.w_lo && d == DT_BF16) {
+    // 1x1 head on the tensor pipe, fp32-faithful: the RPN conv output IS bf16, so x*(w_hi + w_lo) in one fp32 TMEM tile
+    const LayerW& L = h->rpn_head;
+    const int64_t Mh = (int64_t)n * s.h4 * s.w4;
+    ldh = L.cout_pad;
+    ConvProblem q;
+    memset(&q, 0, sizeof(q));
+    q.x = p[B_RPNH]; q.ldx = L.cin_pad; q.y = p[B_HEAD]; q.ldy = ldh; q.N = (int)Mh; q.H = q.W = q.OH = q.OW = 1;
+    q.Cin = L.cin_pad; q.Cout = L.cout_pad; q.KH = q.KW = 1; q.stride = 1; q.dil = 1; q.shift = L.shift; q.relu = 0;
+    q.in_dtype = DT_BF16; q.out_dtype = DT_F32;
+    TcSplit sp; sp.x_lo = nullptr; sp.w_lo = L.w_lo;
+    vltk_frcnn::ProfRec rec;
+    if (h->profiling) {
+      rec.kind = 0; rec.M = Mh; rec.K = L.cin; rec.Cout = L.cout; rec.flops = 2.0 * (double)Mh * L.cin * L.cout;
+      cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1); cudaEventRecord(rec.e0, st);
+    }
+    h->launches++;
+    if (conv_tc_launch(q, L.w_nk, L.cout_pad, &h->tmaps, st, &sp)) return -1;
+    if (h->profiling) { cudaEventRecord(rec.e1, st); h->prof.push_back(rec); }
+  } else {
+    LayerW L = h->rpn_head;
+    if (h->rpn_head_shift_simt) L.shift = h->rpn_head_shift_simt;
+    if (run_conv(h, L, p[B_RPNH], d, n, s.h4, s.w4, p[B_HEAD], DT_F32, L.ldw, nullptr, 0, 0, st)) return -1;
+  }
+  tap(h, "rpn_head", p[B_HEAD], (int64_t)n * s.h4 * s.w4 * ldh, DT_F32);
   RpnSelectArgs ra;
   memset(&ra, 0, sizeof(ra));
-  ra.head = (const float*)p[B_HEAD]; ra.ldh = h->rpn_head.ldw; ra.delta_off = 0; ra.logit_off = 4 * A;
+  ra.head = (const float*)p[B_HEAD]; ra.ldh = ldh; ra.delta_off = 0; ra.logit_off = 4 * A;
   ra.N = n; ra.H4 = s.h4; ra.W4 = s.w4; ra.A = A; ra.stride = c.anchor_stride; ra.cell = h->cell;
   ra.sizes_hw = (const int*)p[B_SIZES]; ra.pre_topk = c.rpn_pre_nms_topk; ra.min_size = c.rpn_min_size;
   ra.wx = c.rpn_bbox_weights[0]; ra.wy = c.rpn_bbox_weights[1]; ra.ww = c.rpn_bbox_weights[2]; ra.wh = c.rpn_bbox_weights[3];
@@ -828,7 +861,7 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
     { StageTimer t(h, K_GLUE, (double)NR * D * 8.0, st);
       if (split_f32((const float*)p[B_FEATS], nullptr, 0, (bf16*)p[B_FHI], (bf16*)p[B_FLO], (int64_t)NR * D, st)) return -1; }
     if (split_gemm(h->cls_score, p[B_FHI], p[B_FLO], D, p[B_CLS], 0)) return -1;
-    if (split_gemm(h->bbox_pred, p[B_FHI], p[B_FLO], D, p[B_BBOX], 0)) return -1;
+    // bbox_pred: only the winning class's 4 rows are ever used (frcnn.py:116-131) -> evaluated inside roi_stats_kernel
     if (row_argmax((const float*)p[B_CLS], ldc, NR, c.num_classes + 1, (int*)p[B_ARGMAX], st)) return -1;
     if (gather_rows(h->attr_table, D / 4, (const int*)p[B_ARGMAX], NR, D / 4, (float*)p[B_TG], D / 4, st)) return -1;
     if (split_gemm(h->fc_attr, p[B_FHI], p[B_FLO], D, p[B_AH], 0)) return -1;   // W[:, :D] x + b
@@ -846,14 +879,15 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
     h->launches += 2;
   }
   tap(h, "cls_logits", p[B_CLS], (int64_t)NR * ldc, DT_F32);
-  tap(h, "bbox_deltas", p[B_BBOX], (int64_t)NR * ldb, DT_F32);
+  if (!ptc) tap(h, "bbox_deltas", p[B_BBOX], (int64_t)NR * ldb, DT_F32);
   tap(h, "attr_logits", p[B_ATTR], (int64_t)NR * lda, DT_F32);
 
   // ---- detection tail (frcnn.py:1262-1294)
   TailArgs ta;
   memset(&ta, 0, sizeof(ta));
   ta.N = n; ta.R = s.R; ta.cls_logits = (const float*)p[B_CLS]; ta.ldc = ldc;
-  ta.bbox_deltas = (const float*)p[B_BBOX]; ta.ldb = ldb;
+  ta.bbox_deltas = ptc ? nullptr : (const float*)p[B_BBOX]; ta.ldb = ldb;
+  if (ptc) { ta.bbox_w_hi = h->bbox_pred.w_nk; ta.bbox_w_lo = h->bbox_pred.w_lo; ta.bbox_bias = h->bbox_pred.shift; }
   ta.attr_logits = (const float*)p[B_ATTR]; ta.lda = lda;
   ta.feats = (const float*)p[B_FEATS]; ta.D = D; ta.proposals = (const float*)p[B_PROP];
   ta.count = (const int*)p[B_COUNT]; ta.sizes_hw = (const int*)p[B_SIZES];

@@ -80,8 +80,11 @@ struct TailArgs {
   int N, R;                    // images, proposal slots per image
   const float* cls_logits;     // [N*R, ldc]  (num_classes+1 valid)
   int ldc;
-  const float* bbox_deltas;    // [N*R, ldb]  (num_classes*4 valid)
+  const float* bbox_deltas;    // [N*R, ldb]  (num_classes*4 valid), or nullptr when the weights below are given
   int ldb;
+  // bbox_pred evaluated ONLY for each ROI's winning class (4 of its 6400 rows; frcnn.py:1244-1250 computes all,
+  // 116-131 keeps one): deltas = W[4c..4c+3, :] . feats + b with W = hi + lo bf16 planes [rows][D] (fp32-faithful)
+  const bf16* bbox_w_hi; const bf16* bbox_w_lo; const float* bbox_bias;
   const float* attr_logits;    // [N*R, lda]  (num_attrs+1 valid)
   int lda;
   const float* feats;          // [N*R, D]

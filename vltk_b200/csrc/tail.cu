@@ -73,8 +73,24 @@ roi_stats_kernel(TailArgs a, float* __restrict__ stats) {
   for (int i = lane; i < NA; i += 32) as += expf(al[i] - ab);
   as = warp_sum(as);
 
+  float4 d;
+  if (a.bbox_deltas) d = *reinterpret_cast<const float4*>(a.bbox_deltas + row * a.ldb + 4 * bi);
+  else {                                   // the winning class's four regression outputs, straight from the weights
+    const float* __restrict__ f = a.feats + row * a.D;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = lane * 4; k < a.D; k += 128) {
+      const float4 x = *reinterpret_cast<const float4*>(f + k);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t o = (int64_t)(4 * bi + j) * a.D + k;
+        const float4 wh = load4(a.bbox_w_hi + o), wl = load4(a.bbox_w_lo + o);
+        acc[j] += x.x * (wh.x + wl.x) + x.y * (wh.y + wl.y) + x.z * (wh.z + wl.z) + x.w * (wh.w + wl.w);
+      }
+    }
+    d = make_float4(warp_sum(acc[0]) + a.bbox_bias[4 * bi], warp_sum(acc[1]) + a.bbox_bias[4 * bi + 1],
+                    warp_sum(acc[2]) + a.bbox_bias[4 * bi + 2], warp_sum(acc[3]) + a.bbox_bias[4 * bi + 3]);
+  }
   if (lane == 0) {
-    const float4 d = *reinterpret_cast<const float4*>(a.bbox_deltas + row * a.ldb + 4 * bi);
     const float4 p = reinterpret_cast<const float4*>(a.proposals)[row];
     const float w = p.z - p.x, h = p.w - p.y;
     const float cx = p.x + 0.5f * w, cy = p.y + 0.5f * h;
