@@ -59,6 +59,66 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, bf16* __restrict
   *reinterpret_cast<uint4*>(a + m * 192 + chunk * 8) = o;
 }
 
+// Same A matrix straight from the NCHW f32 image (no NHWC4 intermediate): one CTA = 64 consecutive output pixels of
+// one output row.  The 7 input rows x 3 channels x 133 columns it needs are loaded once (coalesced along W, zero
+// outside the image), rounded to bf16 into shared memory, and every thread then assembles 16-byte chunks of A rows
+// (8 consecutive k = (kh*7+kw)*3+c) from shared memory through a constant offset table.
+constexpr int IM_OW = 64, IM_COLS = IM_OW * 2 + 5 + 3;   // 136: 133 columns + padding
+__constant__ short c_stem_lut[192];                     // k -> (kh*3+c)*IM_COLS + kw, -1 for the zero tail k >= 147
+
+__global__ void __launch_bounds__(256)
+stem_im2col_nchw_kernel(const float* __restrict__ x, bf16* __restrict__ a, int H, int W, int OH, int OW) {
+  __shared__ bf16 s[21 * IM_COLS + 8];
+  __shared__ short lut[192];             // per-thread-divergent lookups: shared memory, not the constant cache
+  if (threadIdx.x < 192) lut[threadIdx.x] = c_stem_lut[threadIdx.x];
+  const int ow0 = blockIdx.x * IM_OW, oh = blockIdx.y, n = blockIdx.z;
+  const int ih0 = oh * 2 - 3, iw0 = ow0 * 2 - 3;
+  const float* xb = x + (int64_t)n * 3 * H * W;
+  for (int e = threadIdx.x; e < 21 * IM_COLS; e += 256) {
+    const int rc = e / IM_COLS, col = e - rc * IM_COLS;   // rc = kh*3 + c
+    const int kh = rc / 3, c = rc - kh * 3;
+    const int ih = ih0 + kh, iw = iw0 + col;
+    float v = 0.f;
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = xb[((int64_t)c * H + ih) * W + iw];
+    s[e] = __float2bfloat16_rn(v);
+  }
+  if (threadIdx.x < 8) s[21 * IM_COLS + threadIdx.x] = __float2bfloat16_rn(0.f);
+  __syncthreads();
+  const int nout = min(IM_OW, OW - ow0);
+  const int64_t m0 = ((int64_t)n * OH + oh) * OW + ow0;
+  const unsigned short* su = reinterpret_cast<const unsigned short*>(s);
+  for (int t = threadIdx.x; t < nout * 24; t += 256) {
+    const int owl = t / 24, chunk = t - owl * 24;
+    unsigned int w4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int l0 = lut[chunk * 8 + 2 * j], l1 = lut[chunk * 8 + 2 * j + 1];
+      const unsigned int v0 = l0 >= 0 ? su[l0 + 2 * owl] : 0u, v1 = l1 >= 0 ? su[l1 + 2 * owl] : 0u;
+      w4[j] = v0 | (v1 << 16);
+    }
+    *reinterpret_cast<uint4*>(a + (m0 + owl) * 192 + chunk * 8) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+  }
+}
+
+int stem_im2col_nchw(const float* x_nchw, void* a, int N, int H, int W, int OH, int OW, cudaStream_t st) {
+  if ((int64_t)N * OH * OW == 0) return 0;
+  VLTK_CHECK(OH <= 65535 && N <= 65535, "stem_im2col: image too tall / batch too large for the grid");
+  static DeviceOnce once;
+  if (once.first()) {
+    short lut[192];
+    for (int k = 0; k < 192; ++k) {
+      if (k >= 147) { lut[k] = -1; continue; }
+      const int tap = k / 3, c = k - tap * 3, kh = tap / 7, kw = tap - kh * 7;
+      lut[k] = (short)((kh * 3 + c) * IM_COLS + kw);
+    }
+    VLTK_CUDA(cudaMemcpyToSymbol(c_stem_lut, lut, sizeof(lut)));
+  }
+  dim3 grid(ceil_div(OW, IM_OW), OH, N);
+  stem_im2col_nchw_kernel<<<grid, 256, 0, st>>>(x_nchw, (bf16*)a, H, W, OH, OW);
+  VLTK_LAUNCH_CHECK();
+  return 0;
+}
+
 int stem_im2col(const float* x_nhwc4, void* a, int N, int H, int W, int OH, int OW, cudaStream_t st) {
   if ((int64_t)N * OH * OW == 0) return 0;
   VLTK_CHECK(OH <= 65535 && N <= 65535, "stem_im2col: image too tall / batch too large for the grid");

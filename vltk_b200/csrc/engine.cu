@@ -659,13 +659,18 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   }
 
   // ---- backbone (frcnn.py:1076-1090)
-  { StageTimer t(h, K_LAYOUT, (double)n * height * width * (12 + 16), st);
-    if (nchw3_to_nhwc4(images, p[B_IN4], DT_F32, n, height, width, st)) return -1; }
-  h->launches++;
-  if (h->use_tc && h->stem_tc.w_nk) {
+  const bool stem_on_tc = h->use_tc && h->stem_tc.w_nk;
+  static const bool im2col_direct = [] { const char* e = getenv("VLTK_STEM_NHWC4"); return !(e && e[0] == '1'); }();
+  if (!(stem_on_tc && im2col_direct)) {
+    StageTimer t(h, K_LAYOUT, (double)n * height * width * (12 + 16), st);
+    if (nchw3_to_nhwc4(images, p[B_IN4], DT_F32, n, height, width, st)) return -1;
+    h->launches++;
+  }
+  if (stem_on_tc) {
     const int64_t Ms = (int64_t)n * s.Hs * s.Ws;
-    { StageTimer t(h, K_LAYOUT, (double)n * height * width * 16.0 + (double)Ms * 384.0, st);
-      if (stem_im2col((const float*)p[B_IN4], p[B_STEMA], n, height, width, s.Hs, s.Ws, st)) return -1; }
+    { StageTimer t(h, K_LAYOUT, (double)n * height * width * 12.0 + (double)Ms * 384.0, st);
+      if (im2col_direct ? stem_im2col_nchw(images, p[B_STEMA], n, height, width, s.Hs, s.Ws, st)
+                        : stem_im2col((const float*)p[B_IN4], p[B_STEMA], n, height, width, s.Hs, s.Ws, st)) return -1; }
     h->launches++;
     ConvProblem q;
     memset(&q, 0, sizeof(q));

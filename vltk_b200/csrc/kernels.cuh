@@ -10,6 +10,8 @@ namespace vltk {
 int nchw3_to_nhwc4(const float* x, void* y, DType dt, int N, int H, int W, cudaStream_t st);
 // 7x7 s2 p3 patches of the NHWC4 f32 image -> bf16 rows of 192 (147 + zero pad), bf16 mode stem
 int stem_im2col(const float* x_nhwc4, void* a, int N, int H, int W, int OH, int OW, cudaStream_t st);
+// the same matrix straight from the NCHW f32 image (shared-memory staged, no NHWC4 intermediate)
+int stem_im2col_nchw(const float* x_nchw, void* a, int N, int H, int W, int OH, int OW, cudaStream_t st);
 int maxpool3x3s2_ceil(const void* x, void* y, DType dt, int N, int H, int W, int C, int OH, int OW,
                       cudaStream_t st);
 int mean_rows(const void* x, float* y, DType dt, int R, int P, int C, cudaStream_t st);
