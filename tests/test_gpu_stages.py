@@ -126,6 +126,9 @@ def test_fused_meanpool_epilogue_matches_conv_then_mean(dev, rois, cin, cout):
     np.testing.assert_allclose(pooled.numpy(), ref.numpy(), rtol=2e-5, atol=2e-5)
     again = stages.conv2d_meanpool_nhwc(x, wt, sc, sh, res, 196).cpu()
     assert torch.equal(pooled, again)          # fixed reduction order: bit-reproducible, no atomics
+    if rois >= 3:                              # ROI-aligned tiles: an ROI's mean does not depend on its position
+        part = stages.conv2d_meanpool_nhwc(x[2:].contiguous(), wt, sc, sh, res[2:].contiguous(), 196).cpu()
+        assert torch.equal(part, pooled[2:])
 
 
 @pytest.mark.parametrize("n,h,w,mid,cin,cout,stride", [(2, 14, 14, 512, 1024, 2048, 1), (1, 19, 32, 128, 256, 512, 2),

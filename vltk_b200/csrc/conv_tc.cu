@@ -72,12 +72,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-// L2 prefetch of a tiled box: starts the HBM -> L2 transfer without occupying shared memory
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
-               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
-               : "memory");
-}
 __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c, int w,
                                                    int h, int n, uint16_t off_w, uint16_t off_h) {
   asm volatile(
@@ -347,14 +341,13 @@ struct TcParams2 {
   // npass = 1 is the plain bf16 product; {hi*hi, lo*hi, hi*lo} gives an fp32-faithful product.
   // Each pass has its own K extent and sampling stride (K-concatenated dual GEMM, TcConcat).
   int npass, pass_a[3], pass_b[3], pass_cblocks[3], pass_stride[3];
-  // POOL epilogue (res5 tail, frcnn.py:1401): rows are grouped in ROIs of `pool_rows` consecutive pixels;
-  // instead of storing the tile, each row tile writes fp32 column sums of its (at most two) ROI segments to
-  // pool_partial[(m_tile*2 + seg) * Cout + c]; pool_finish() adds the 2-3 partials per ROI in a fixed order.
+  // POOL epilogue (res5 tail, frcnn.py:1401): rows are grouped in ROIs of `pool_rows` consecutive pixels
+  // (128 < pool_rows <= 256).  Row tiles are ROI-ALIGNED — tile mt covers rows [0,128) (mt even) or [128,pool_rows)
+  // (mt odd) of ROI mt/2; rows past the ROI are computed and masked — so a tile never mixes ROIs and an ROI's sums
+  // do not depend on where it sits in the batch.  Instead of storing the tile, each tile writes the fp32 column
+  // sums of its valid rows to pool_partial[mt * Cout + c]; pool_finish() adds an ROI's two partials and divides.
   float* pool_partial;
   int pool_rows;
-  // residual producer: tiles of look-ahead for an L2 prefetch of the shortcut tensor (0 = off, the default: it
-  // measured slower — the layer is bandwidth-bound, see conv_tc_launch)
-  int res_prefetch;
 };
 
 template <int BN, int STAGES, bool HAS_RES, int EG = 1>
@@ -381,7 +374,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   static_assert(!(HAS_RES && OUT_F32), "fp32 output has no residual path");
   static_assert(!POOL || !OUT_F32, "the pooled epilogue reduces the bf16-path tile");
   static_assert(EG == 1 || EG == 2, "one or two epilogue warpgroups");
-  static_assert(!POOL || EG == 1, "the pooled epilogue runs on one warpgroup");
   constexpr int SLABC = OUT_F32 ? 32 : SLAB;   // columns per 128 B staging row (fp32: 32, bf16: 64)
   constexpr int NSLAB = BN / SLABC;
   // EG epilogue warpgroups (warps 4-7, 8-11) share the slabs round-robin over the CTA's global slab sequence
@@ -448,7 +440,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int stage = 0; uint32_t phase = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       const int n0 = (t % p.n_tiles) * BN;
-      const int64_t m0 = (int64_t)(t / p.n_tiles) * BM;
+      const int mt = t / p.n_tiles;
+      const int64_t m0 = POOL ? (int64_t)(mt >> 1) * p.pool_rows + (mt & 1) * BM : (int64_t)mt * BM;
       const int ow0 = (int)(m0 % p.OW);
       const int64_t q = m0 / p.OW;
       const int oh0 = (int)(q % p.OH), img0 = (int)(q / p.OH);
@@ -497,18 +490,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (HAS_RES && warp == 3 && lane == 0) {
     // ================= residual producer =================
     int slot = 0; uint32_t phase = 0;
-    if (p.res_prefetch > 0)                            // warm-up: the first tiles of this CTA
-      for (int k = 0, t = blockIdx.x; k < p.res_prefetch && t < p.num_tiles; ++k, t += gridDim.x)
-        for (int s = 0; s < NSLAB; ++s) tma_prefetch_2d(&tmR, (t % p.n_tiles) * BN + s * SLAB, (t / p.n_tiles) * BM);
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       const int n0 = (t % p.n_tiles) * BN;
-      const int m0 = (t / p.n_tiles) * BM;
-      if (p.res_prefetch > 0) {
-        const long long tp = (long long)t + (long long)p.res_prefetch * gridDim.x;
-        if (tp < p.num_tiles)
-          for (int s = 0; s < NSLAB; ++s)
-            tma_prefetch_2d(&tmR, (int)(tp % p.n_tiles) * BN + s * SLAB, (int)(tp / p.n_tiles) * BM);
-      }
+      const int mt = t / p.n_tiles;
+      const int m0 = POOL ? (mt >> 1) * p.pool_rows + (mt & 1) * BM : mt * BM;
       for (int s = 0; s < NSLAB; ++s) {
         mbar_wait(rempty_bar(slot), phase ^ 1u);
         mbar_expect_tx(rfull_bar(slot), SLAB_BYTES);
@@ -531,7 +516,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int obuf = 0, it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int n0 = (t % p.n_tiles) * BN;
-      const int m0 = (t / p.n_tiles) * BM;
+      const int mt = t / p.n_tiles;
+      const int m0 = POOL ? (mt >> 1) * p.pool_rows + (mt & 1) * BM : mt * BM;
+      (void)m0;
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1) & 1u;
       const int c0 = it * NSLAB;              // global index of this tile's first slab
@@ -593,7 +580,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         group_barrier();                      // sOutG[obuf] reusable (POOL: last slab's column readers done); scale/shift visible
         const uint32_t orow = sOutG + obuf * SLAB_BYTES + (uint32_t)row * 128u;
         const uint32_t rrow = sRes + slot * SLAB_BYTES + (uint32_t)row * 128u;
-        float pv[POOL ? 64 : 1];              // POOL: this row's 64 fp32 epilogue values of the slab
+        float pv[POOL ? 64 : 1];              // POOL: this row's 64 fp32 epilogue values of the slab (then its column sums)
         (void)pv;
         if constexpr (OUT_F32) {
 #pragma unroll
@@ -649,40 +636,25 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (lane == 0) mbar_arrive(rempty_bar(slot));
         }
         if constexpr (POOL) {
-          // per-ROI column sums of this slab without staging the tile: rows of this warp that belong to the
-          // tile's first ROI (segment A) / second ROI (segment B) are reduced by a 62-shuffle butterfly
-          const int roi0 = m0 / p.pool_rows;
-          const int bnd = min(BM, (roi0 + 1) * p.pool_rows - m0);          // tile rows [0,bnd) belong to roi0
-          const int64_t left = p.M - (int64_t)m0;                          // rows past M do not exist
-          const int rmax = left < (int64_t)BM ? (int)left : BM;
-          const int w0 = e * 32;                                           // this warp's first tile row
-          const bool in_a = row < bnd && row < rmax, in_b = row >= bnd && row < rmax;
-          float* comb = reinterpret_cast<float*>(gbase + S::OFF_OUT) + (s & 1) * 512;   // [seg][warp][64], double buffered
-          const bool warp_has_a = w0 < bnd && w0 < rmax, warp_has_b = w0 + 31 >= bnd && bnd < rmax;
-          float2 ta = make_float2(0.f, 0.f), tb = make_float2(0.f, 0.f);
-          if (warp_has_a) {                                                // warp-uniform branches
-            float va[64];
+          // column sums of this slab's valid rows without staging the tile: each warp reduces its 32 rows with a
+          // 62-shuffle butterfly, the group's 4 warps are combined through (double-buffered) staging memory in a
+          // fixed order, 64 threads write the tile's partial sums
+          const int valid = (mt & 1) ? p.pool_rows - BM : BM;             // rows of this tile that belong to its ROI
+          float* comb = reinterpret_cast<float*>(gbase + S::OFF_OUT + (size_t)(g * NBUF) * SLAB_BYTES) + (j & 1) * 256;
+          float2 ts = make_float2(0.f, 0.f);
+          if (e * 32 < valid) {                                            // warp-uniform
+            const bool in = row < valid;
 #pragma unroll
-            for (int j = 0; j < 64; ++j) va[j] = in_a ? pv[j] : 0.f;
-            warp_colsum64(va, lane);
-            ta = make_float2(va[0], va[1]);
+            for (int q = 0; q < 64; ++q) pv[q] = in ? pv[q] : 0.f;
+            warp_colsum64(pv, lane);
+            ts = make_float2(pv[0], pv[1]);
           }
-          if (warp_has_b) {
-            float vb[64];
-#pragma unroll
-            for (int j = 0; j < 64; ++j) vb[j] = in_b ? pv[j] : 0.f;
-            warp_colsum64(vb, lane);
-            tb = make_float2(vb[0], vb[1]);
-          }
-          *reinterpret_cast<float2*>(comb + (0 * 4 + e) * 64 + 2 * lane) = ta;   // lane L owns columns 2L, 2L+1
-          *reinterpret_cast<float2*>(comb + (1 * 4 + e) * 64 + 2 * lane) = tb;
+          *reinterpret_cast<float2*>(comb + e * 64 + 2 * lane) = ts;       // lane L owns columns 2L, 2L+1
           group_barrier();
-          {                                                                // 128 threads = 2 segments x 64 columns
-            const int col = et & 63, seg = et >> 6;
-            const float* c4 = comb + seg * 256 + col;
+          if (et < 64) {
+            const float* c4 = comb + et;
             const float tot = ((c4[0] + c4[64]) + c4[128]) + c4[192];      // fixed warp order
-            const int64_t mt = m0 / BM;
-            p.pool_partial[(mt * 2 + seg) * (int64_t)p.Cout + n0 + s * SLABC + col] = tot;
+            p.pool_partial[(int64_t)mt * p.Cout + n0 + s * SLABC + et] = tot;
           }
         } else {
           fence_proxy_async_smem();           // generic-proxy smem writes -> visible to the TMA unit
@@ -786,21 +758,16 @@ int num_sms() {            // of the CURRENT device (a process may drive several
   return cache[dev];
 }
 
-// feats[roi][c] = (sum of the row tiles' partial sums for that ROI, ascending tile order) / rows
+// feats[roi][c] = (partial of the ROI's first tile + partial of its second tile) / rows
 __global__ void pool_finish_kernel(const float* __restrict__ partial, float* __restrict__ out, int rois, int rows, int C) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int c4n = C / 4;
   if (i >= (int64_t)rois * c4n) return;
   const int c = (int)(i % c4n) * 4, r = (int)(i / c4n);
-  const int t0 = (int)(((int64_t)r * rows) / BM), t1 = (int)(((int64_t)r * rows + rows - 1) / BM);
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int t = t0; t <= t1; ++t) {
-    const int seg = r - (int)(((int64_t)t * BM) / rows);   // 0: the tile's first ROI, 1: its second
-    const float4 v = *reinterpret_cast<const float4*>(partial + ((int64_t)t * 2 + seg) * C + c);
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-  }
+  const float4 a = *reinterpret_cast<const float4*>(partial + ((int64_t)r * 2) * C + c);
+  const float4 b = *reinterpret_cast<const float4*>(partial + ((int64_t)r * 2 + 1) * C + c);
   const float d = (float)rows;
-  *reinterpret_cast<float4*>(out + (int64_t)r * C + c) = make_float4(s.x / d, s.y / d, s.z / d, s.w / d);
+  *reinterpret_cast<float4*>(out + (int64_t)r * C + c) = make_float4((a.x + b.x) / d, (a.y + b.y) / d, (a.z + b.z) / d, (a.w + b.w) / d);
 }
 
 struct Maps { CUtensorMap a, a2, b, b2, y, r; };
@@ -813,7 +780,7 @@ int launch2e(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
     VLTK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STAGES, HAS_RES, OUT_F32, POOL, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   }
   tp.n_tiles = cout_pad / BN;
-  const int64_t tiles = ceil_div64(tp.M, BM) * tp.n_tiles;
+  const int64_t tiles = (POOL ? 2 * (tp.M / tp.pool_rows) : ceil_div64(tp.M, BM)) * tp.n_tiles;
   VLTK_CHECK(tiles < (1ll << 31), "conv_tc: too many tiles");
   tp.num_tiles = (int)tiles;
   const int grid = (int)std::min<int64_t>(tiles, num_sms());  // persistent: one CTA per SM
@@ -830,15 +797,12 @@ int launch2e(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
   return 0;
 }
 
-// Two epilogue warpgroups unless VLTK_EPI_GROUPS=1 (A/B switch; the pooled epilogue always runs on one).
+// Two epilogue warpgroups unless VLTK_EPI_GROUPS=1 (A/B switch).
 template <int BN, int STAGES, bool HAS_RES, bool OUT_F32, bool POOL = false>
 int launch2(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
   static const bool one = [] { const char* e = getenv("VLTK_EPI_GROUPS"); return e && e[0] == '1'; }();
-  if constexpr (POOL) return launch2e<BN, STAGES, HAS_RES, OUT_F32, POOL, 1>(m, tp, cout_pad, st);
-  else {
-    if (one) return launch2e<BN, STAGES, HAS_RES, OUT_F32, false, 1>(m, tp, cout_pad, st);
-    return launch2e<BN, STAGES, HAS_RES, OUT_F32, false, 2>(m, tp, cout_pad, st);
-  }
+  if (one) return launch2e<BN, STAGES, HAS_RES, OUT_F32, POOL, 1>(m, tp, cout_pad, st);
+  return launch2e<BN, STAGES, HAS_RES, OUT_F32, POOL, 2>(m, tp, cout_pad, st);
 }
 
 template <int BN, int STAGES>
@@ -856,7 +820,7 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const TcParams& tp, int c
 
 }  // namespace
 
-size_t conv_tc_pool_partial_bytes(int64_t M, int cout) { return (size_t)ceil_div64(M, BM) * 2 * cout * sizeof(float); }
+size_t conv_tc_pool_partial_bytes(int64_t M, int cout) { return ((size_t)(M / (BM + 1)) + 1) * 2 * cout * sizeof(float); }   // 2 tiles per ROI, rows > BM
 
 int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorMapCache* cache, cudaStream_t st,
                    const TcSplit* split, const TcPool* pool, const TcConcat* concat) {
@@ -945,10 +909,8 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
     t2.OH = p.OH; t2.OW = p.OW; t2.stride = p.stride; t2.pad = p.pad; t2.dil = p.dil; t2.KW = p.KW;
     t2.taps = p.KH * p.KW; t2.cblocks = p.Cin / BK; t2.n_tiles = 0; t2.num_tiles = 0;
     t2.pool_partial = nullptr; t2.pool_rows = 1;
-    // measured on B200 (profiles/r01_summary.md §19): the residual layers are DRAM-bandwidth-bound, not latency-bound —
-    // prefetching 2 / 4 tiles ahead made res5 conv3 SLOWER (1.10 -> 1.19 / 1.29 ms).  Off by default; knob kept.
-    static const int res_pf = [] { const char* e = getenv("VLTK_RES_PF"); return e ? atoi(e) : 0; }();
-    t2.res_prefetch = p.residual ? res_pf : 0;
+    // (an L2 prefetch of the residual tensor was tried and measured slower: the residual layers are DRAM-bandwidth-
+    // bound, not latency-bound — profiles/r01_summary.md §19)
     t2.npass = is_split ? 3 : 1;                       // hi*hi, lo*hi, hi*lo
     t2.pass_a[0] = 0; t2.pass_a[1] = 1; t2.pass_a[2] = 0;
     t2.pass_b[0] = 0; t2.pass_b[1] = 0; t2.pass_b[2] = 1;
@@ -965,7 +927,8 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
     }
     if (pool && pool->out) {
       VLTK_CHECK(p.residual && bn == 256 && !out_f32 && !is_split, "conv_tc: the pooled epilogue is built for the res5 conv3 shape (residual, Cout %% 256 == 0, K > 256)");
-      VLTK_CHECK(pool->rows >= BM && M % pool->rows == 0 && p.Cout % 4 == 0, "conv_tc: pool_rows=%d must be >= %d and divide M", pool->rows, BM);
+      VLTK_CHECK(pool->rows > BM && pool->rows <= 2 * BM && M % pool->rows == 0 && p.Cout % 4 == 0,
+                 "conv_tc: pool_rows=%d must be in (%d, %d] and divide M", pool->rows, BM, 2 * BM);
       t2.pool_partial = pool->partial; t2.pool_rows = pool->rows;
       if (launch2<256, 3, true, false, true>(m, t2, cout_pad, st)) return -1;
       const int rois = (int)(M / pool->rows);

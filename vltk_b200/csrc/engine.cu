@@ -814,15 +814,14 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   x = p[B_POOLED];
   void* r5[2] = {p[B_R5A], p[B_R5B]};
   flip = 0;
-  // The last block's output is only ever consumed by the 14x14 mean (frcnn.py:1401).  On the tensor pipe its
-  // conv3 epilogue CAN reduce the fp32 tile per ROI instead of storing 2 GB that is read straight back
-  // (conv_tc.cu POOL, tested in test_fused_meanpool_epilogue_matches_conv_then_mean).  It is OPT-IN
-  // (VLTK_FUSE_MEAN=1): measured +0.7 % (last conv3 1.10 + mean 0.32 ms -> 1.29 ms), but the per-tile partial
-  // sums group an ROI's 196 rows by where it falls on the 128-row tile grid, so an image's features would
-  // differ in the last bit depending on its position in the batch.  The default keeps the separate mean, whose
-  // fixed order makes every image bit-independent of its batch neighbours (test_full_batch8_equals_smaller_batches).
-  static const bool want_fuse = [] { const char* e = getenv("VLTK_FUSE_MEAN"); return e && e[0] == '1'; }();
-  const bool fuse_mean = want_fuse && h->use_tc && h->res5.back().c3.w_nk && PP >= 128 && D % 256 == 0 && h->res5.back().c3.cin > 256;
+  // The last block's output is only ever consumed by the 14x14 mean (frcnn.py:1401).  On the tensor pipe its conv3
+  // epilogue reduces the fp32 tile per ROI instead of storing 2 GB that is read straight back (conv_tc.cu POOL,
+  // tested in test_fused_meanpool_epilogue_matches_conv_then_mean).  Row tiles are ROI-aligned (two per ROI: rows
+  // [0,128) and [128,196)), so an ROI's sums do not depend on its position in the batch and every image stays
+  // bit-independent of its batch neighbours (test_full_batch8_equals_smaller_batches).  VLTK_FUSE_MEAN=0 restores the
+  // separate mean_rows pass over the stored bf16 tensor.
+  static const bool want_fuse = [] { const char* e = getenv("VLTK_FUSE_MEAN"); return !(e && e[0] == '0'); }();
+  const bool fuse_mean = want_fuse && h->use_tc && h->res5.back().c3.w_nk && PP > 128 && PP <= 256 && D % 256 == 0 && h->res5.back().c3.cin > 256;
   TcPool pool;
   pool.out = (float*)p[B_FEATS]; pool.partial = (float*)p[B_PARTIAL]; pool.rows = PP;
   for (size_t bi = 0; bi < h->res5.size(); ++bi) {
