@@ -328,7 +328,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // clipped on store by the TMA unit: no tail code.
 constexpr int SLAB = 64;                       // epilogue column slab: 64 bf16 = one 128 B swizzle row
 constexpr int SLAB_BYTES = BM * SLAB * 2;      // 16 KB
-constexpr int RS = 3;                          // residual ring depth
+// residual ring depth: 3 slabs (48 KB) next to BN=256 operand stages; 5 slabs (80 KB) with the smaller BN=128 stages.
+template <int BN, bool HAS_RES> struct ResRing { static constexpr int DEPTH = (HAS_RES && BN == 128) ? 5 : 3; };
 
 struct TcParams2 {
   const float* scale; const float* shift;
@@ -358,6 +359,7 @@ struct Smem2 {
   static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
   static constexpr int OFF_OUT = STAGES * STAGE_BYTES;
   static constexpr int OFF_RES = OFF_OUT + 2 * SLAB_BYTES;
+  static constexpr int RS = ResRing<BN, HAS_RES>::DEPTH;
   static constexpr int OFF_SCALE = OFF_RES + (HAS_RES ? RS * SLAB_BYTES : 0);
   static constexpr int OFF_BARS = OFF_SCALE + 2 * EG * GSC * 4;
   static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * RS;
@@ -374,6 +376,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   static_assert(!(HAS_RES && OUT_F32), "fp32 output has no residual path");
   static_assert(!POOL || !OUT_F32, "the pooled epilogue reduces the bf16-path tile");
   static_assert(EG == 1 || EG == 2, "one or two epilogue warpgroups");
+  constexpr int RS = S::RS;
   constexpr int SLABC = OUT_F32 ? 32 : SLAB;   // columns per 128 B staging row (fp32: 32, bf16: 64)
   constexpr int NSLAB = BN / SLABC;
   // EG epilogue warpgroups (warps 4-7, 8-11) share the slabs round-robin over the CTA's global slab sequence
@@ -849,6 +852,8 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
   int bn = (cout_pad % 256 == 0) ? 256 : (cout_pad % 128 == 0 ? 128 : 64);
   static const int smallk = [] { const char* e = getenv("VLTK_SMALLK"); return e ? atoi(e) : 256; }();   // tuning knob
   if (K + (is_concat ? concat->Cin2 : 0) <= smallk && cout_pad % 128 == 0) bn = 128;
+  // (BN=128 + a 5-slab residual ring for the K=512 residual layers of res5 was measured: 1.07 -> 1.21 ms, slower — the
+  //  doubled A traffic and the N=128 MMA rate cost more than the deeper ring returns; profiles/r01_summary.md §25)
   if (cache->maps.size() > 8192) cache->maps.clear();   // keys hold buffer addresses: bound growth across reallocations
   CUtensorMap ta, tb;
   TensorMapCache::Key ka(p.x, p.N, p.H, p.W, p.Cin, p.ldx, p.KH, p.stride, p.pad, p.dil, 0);
@@ -939,7 +944,7 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
     }
     if (p.residual) {
       if (bn == 256) return launch2<256, 3, true, false>(m, t2, cout_pad, st);
-      if (bn == 128) return launch2<128, 4, true, false>(m, t2, cout_pad, st);
+      if (bn == 128) return launch2<128, 3, true, false>(m, t2, cout_pad, st);
       return launch2<64, 4, true, false>(m, t2, cout_pad, st);
     }
     if (bn == 256) return launch2<256, 4, false, false>(m, t2, cout_pad, st);
