@@ -184,3 +184,41 @@ def test_jpeg_bytes_to_features_equals_cv2_decoded_path():
         pre([encode(raw_image(64, 64, 1), progressive=True)])
     ok = Preprocess(cfg, host_decode_unsupported=True)([encode(raw_image(64, 64, 1), progressive=True)])
     assert ok[1].shape[0] == 1
+
+
+@pytest.mark.gpu
+def test_gpu_decode_randomised_sweep():
+    """40 random (size, quality, sampling, restart interval) combinations, decoded in two front-end calls and
+    compared bit-for-bit with cv2: exercises block-grid padding, every MCU geometry, tiny and odd images, both
+    entropy paths of the device decoder (self-synchronising and per-interval)."""
+    from vltk_b200 import jpeg
+    rng = np.random.default_rng(20261018)
+    datas = []
+    for i in range(40):
+        h, w = int(rng.integers(1, 260)), int(rng.integers(1, 340))
+        ss = ["444", "422", "420"][int(rng.integers(0, 3))]
+        q = int(rng.integers(5, 100))
+        rst = int(rng.choice([0, 0, 1, 2, 5, 11]))
+        datas.append(encode(raw_image(h, w, 7000 + i), q, ss, rst))
+    dec = jpeg.JpegDecoder()
+    for part in (datas[:23], datas[23:]):
+        for b, o in zip(part, dec.decode(part)):
+            ref = cv2_decode(b)
+            assert o.shape == ref.shape and np.array_equal(o.cpu().numpy(), ref)
+
+
+@pytest.mark.gpu
+def test_preprocess_reads_jpeg_files_from_disk(tmp_path):
+    """Preprocess(paths): .jpg files go through the GPU front end (EXIF orientation honoured like cv2.imread), other
+    formats are read with cv2 on the host as in the reference (compat.py:573-579); both give cv2.imread's pixels."""
+    from oracle import cases
+    from vltk_b200.preprocess import Preprocess
+    cfg = cases.case_config("mixed")
+    pre = Preprocess(cfg)
+    img = raw_image(150, 200, 42)
+    pj, pp = str(tmp_path / "a.jpg"), str(tmp_path / "b.png")
+    cv2.imwrite(pj, img, [cv2.IMWRITE_JPEG_QUALITY, 88])
+    cv2.imwrite(pp, img)
+    ids, images, sizes, scales = pre([pj, pp], ["a", "b"])
+    ref = pre([torch.from_numpy(cv2.imread(pj)), torch.from_numpy(cv2.imread(pp))], ["a", "b"])
+    assert ids == ["a", "b"] and torch.equal(images, ref[1]) and torch.equal(sizes, ref[2])
