@@ -947,6 +947,8 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
       if (bn == 128) return launch2<128, 3, true, false>(m, t2, cout_pad, st);
       return launch2<64, 4, true, false>(m, t2, cout_pad, st);
     }
+    static const bool probe3 = [] { const char* e = getenv("VLTK_PROBE_STAGES3"); return e && e[0] == '1'; }();
+    if (bn == 256 && probe3) return launch2<256, 3, false, false>(m, t2, cout_pad, st);   // diagnosis knob: 3 instead of 4 stages
     if (bn == 256) return launch2<256, 4, false, false>(m, t2, cout_pad, st);
     if (bn == 128) return launch2<128, 4, false, false>(m, t2, cout_pad, st);
     return launch2<64, 4, false, false>(m, t2, cout_pad, st);
