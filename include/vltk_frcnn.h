@@ -214,8 +214,9 @@ int vltk_gather_rows_f32(const float* table, int64_t n_rows, int64_t ld, const i
  * (`img_tensorize`, reached from legacy/processing.py:119-129).  The host parses the markers and runs the
  * (inherently serial) Huffman entropy decoder; dequantisation, the inverse DCT, chroma upsampling and colour
  * conversion run on the GPU and reproduce libjpeg-turbo's default pipeline (JDCT_ISLOW, fancy upsampling) bit
- * for bit.  Supported: baseline / extended-sequential Huffman, 8-bit, grayscale or 3 components with 4:4:4,
- * 4:2:2 or 4:2:0 sampling in one interleaved scan, restart intervals.  Anything else returns -3 (the caller
+ * for bit.  Supported: baseline / extended-sequential (one interleaved scan; entropy decoding on the device) and
+ * progressive (entropy decoding of its scans on the host) Huffman JPEG, 8-bit, grayscale or 3 components with 4:4:4,
+ * 4:2:2 or 4:2:0 sampling, restart intervals.  Anything else returns -3 (the caller
  * decides what to do with such a file; nothing is decoded on the CPU behind its back). */
 typedef struct {
   int width, height, ncomp;

@@ -60,18 +60,22 @@ def parse(data: bytes):
                 n = sum(bits)
                 dht[(tc, th)] = _huff_table(bits, list(seg[o:o + n]))
                 o += n
-        elif m in (0xC0, 0xC1):
+        elif m in (0xC0, 0xC1, 0xC2):
+            info["progressive"] = m == 0xC2
             assert seg[0] == 8
             info["h"], info["w"] = (seg[1] << 8) | seg[2], (seg[3] << 8) | seg[4]
             info["comps"] = [dict(id=seg[6 + 3 * c], hs=seg[7 + 3 * c] >> 4, vs=seg[7 + 3 * c] & 15, tq=seg[8 + 3 * c])
                              for c in range(seg[5])]
-        elif 0xC2 <= m <= 0xCF and m not in (0xC4, 0xC8, 0xCC):
+        elif 0xC3 <= m <= 0xCF and m not in (0xC4, 0xC8, 0xCC):
             raise NotImplementedError(f"SOF{m - 0xC0}")
         elif m == 0xDD:
             info["dri"] = (seg[0] << 8) | seg[1]
         elif m == 0xEE and seg[:5] == b"Adobe":
             info["adobe"] = seg[11]
         elif m == 0xDA:
+            if info.get("progressive"):     # geometry + tables only: the scans are not restated in Python
+                info["scan"] = pos - 2
+                break
             ns = seg[0]
             assert ns == len(info["comps"])
             for k in range(ns):
@@ -253,6 +257,16 @@ def ycc_to_bgr(Y, Cb, Cr):
     b = Y + ((116130 * cb + 32768) >> 16)
     g = Y + ((-22554 * cb - 46802 * cr + 32768) >> 16)
     return np.clip(np.stack([b, g, r], -1), 0, 255).astype(np.uint8)
+
+
+def geometry(I):
+    """Adds hmax/vmax/mcus_x/mcus_y to a parsed header (what coefficients() does for baseline files)."""
+    comps = I["comps"]
+    if len(comps) == 1:
+        comps[0]["hs"] = comps[0]["vs"] = 1
+    hmax, vmax = max(c["hs"] for c in comps), max(c["vs"] for c in comps)
+    I.update(hmax=hmax, vmax=vmax, mcus_x=-(-I["w"] // (8 * hmax)), mcus_y=-(-I["h"] // (8 * vmax)))
+    return I
 
 
 def reconstruct(I, coefs):

@@ -74,10 +74,43 @@ def test_host_entropy_decoder_matches_oracle(h, w, ss, q, rst):
         assert np.array_equal(np.asarray(info.qt[c][:]), I["qt"][I["comps"][c]["tq"]])
 
 
+def cmyk_jpeg():
+    from PIL import Image
+    buf = io.BytesIO()
+    Image.new("CMYK", (32, 32), (10, 20, 30, 40)).save(buf, format="JPEG")
+    return buf.getvalue()
+
+
+@pytest.mark.parametrize("h,w,ss,q,rst", [(48, 64, "420", 85, 0), (37, 53, "422", 60, 0), (40, 40, "444", 92, 0),
+                                          (9, 3, "420", 85, 0), (120, 200, "420", 30, 0), (120, 200, "420", 97, 5),
+                                          (65, 129, "420", 75, 2)])
+def test_progressive_host_decoder_is_bit_exact_with_libjpeg_turbo(h, w, ss, q, rst):
+    """Progressive (SOF2) files: the C++ host entropy decoder walks every scan (DC/AC, first/refinement, EOB runs);
+    its coefficients pushed through the oracle's IDCT/upsampling/colour stages must give cv2.imdecode's pixels."""
+    from oracle import jpeg_oracle as J
+    from vltk_b200 import jpeg
+    b = encode(raw_image(h, w, h * 100 + w), q, ss, rst, progressive=True)
+    info, co = jpeg.coefficients(b)
+    assert info.progressive == 1 and (info.width, info.height) == (w, h)
+    I = J.geometry(J.parse(b))
+    coefs = [co[int(info.coef_offset[c]): int(info.coef_offset[c]) + info.blocks_w[c] * info.blocks_h[c] * 64]
+             .reshape(info.blocks_h[c], info.blocks_w[c], 64) for c in range(info.ncomp)]
+    assert np.array_equal(J.reconstruct(I, coefs), cv2_decode(b))
+
+
+def test_progressive_grayscale_host_decoder():
+    from oracle import jpeg_oracle as J
+    from vltk_b200 import jpeg
+    b = encode(raw_image(50, 70, 9), 80, gray=True, progressive=True)
+    info, co = jpeg.coefficients(b)
+    I = J.geometry(J.parse(b))
+    assert np.array_equal(J.reconstruct(I, [co.reshape(info.blocks_h[0], info.blocks_w[0], 64)]), cv2_decode(b))
+
+
 def test_unsupported_and_corrupt_files_are_reported_not_decoded():
     from vltk_b200 import _lib, jpeg
     with pytest.raises(jpeg.UnsupportedJpeg):
-        jpeg.parse(encode(raw_image(32, 32, 1), progressive=True))
+        jpeg.parse(cmyk_jpeg())
     with pytest.raises(_lib.LibraryError):
         jpeg.parse(b"\x89PNG\r\n\x1a\n" + b"\0" * 32)
     good = encode(raw_image(32, 32, 1))
@@ -144,6 +177,8 @@ def test_gpu_decode_is_bit_exact_with_cv2_imread(entropy):
     dec = jpeg.JpegDecoder(entropy=entropy)
     datas = [encode(raw_image(h, w, h * 100 + w), q, ss, rst) for (h, w, ss, q, rst) in GPU_CASES]
     datas.append(encode(raw_image(40, 56, 3), 80, gray=True))
+    datas.append(encode(raw_image(333, 500, 77), 85, "420", progressive=True))   # host entropy decode, GPU IDCT/colour
+    datas.append(encode(raw_image(61, 47, 78), 50, "444", 3, progressive=True))
     for rep in range(2):                         # second pass reuses the pinned staging buffer
         outs = dec.decode(datas)
         for b, o in zip(datas, outs):
@@ -181,9 +216,12 @@ def test_jpeg_bytes_to_features_equals_cv2_decoded_path():
     assert torch.equal(images, images2)
     from vltk_b200 import jpeg
     with pytest.raises(jpeg.UnsupportedJpeg):
-        pre([encode(raw_image(64, 64, 1), progressive=True)])
-    ok = Preprocess(cfg, host_decode_unsupported=True)([encode(raw_image(64, 64, 1), progressive=True)])
+        pre([cmyk_jpeg()])
+    ok = Preprocess(cfg, host_decode_unsupported=True)([cmyk_jpeg()])
     assert ok[1].shape[0] == 1
+    # progressive files: entropy-decoded by the C++ host decoder, everything else on the GPU as usual
+    prog = encode(raw_image(150, 200, 0), 90, "420", progressive=True)
+    assert torch.equal(pre([prog])[1], pre([torch.from_numpy(cv2_decode(prog))])[1])
 
 
 @pytest.mark.gpu

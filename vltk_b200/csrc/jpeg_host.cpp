@@ -109,6 +109,25 @@ int exif_orientation(const uint8_t* p, int len) {
   return 0;
 }
 
+int parse_dht(const uint8_t* s, int n, Parsed* P) {
+  int o = 0;
+  while (o + 17 <= n) {
+    const int tc = s[o] >> 4, th = s[o] & 15;
+    if (tc > 1 || th > 3) { set_error("jpeg: bad DHT id"); return -2; }
+    HuffTable& H = tc ? P->ac[th] : P->dc[th];
+    int cnt = 0;
+    H.bits[0] = 0;
+    for (int i = 1; i <= 16; ++i) { H.bits[i] = s[o + i]; cnt += s[o + i]; }
+    o += 17;
+    if (cnt > 256 || o + cnt > n) { set_error("jpeg: bad DHT length"); return -2; }
+    memcpy(H.vals, s + o, cnt);
+    o += cnt;
+    if (!H.build()) { set_error("jpeg: invalid Huffman table"); return -2; }
+    H.present = true;
+  }
+  return 0;
+}
+
 int parse(const uint8_t* d, size_t len, Parsed* P) {
   vltk_jpeg_info& I = P->info;
   memset(&I, 0, sizeof(I));
@@ -142,22 +161,10 @@ int parse(const uint8_t* d, size_t len, Parsed* P) {
         qt_ok[t] = true;
       }
     } else if (m == 0xC4) {                              // DHT
-      int o = 0;
-      while (o + 17 <= n) {
-        const int tc = s[o] >> 4, th = s[o] & 15;
-        if (tc > 1 || th > 3) { set_error("jpeg: bad DHT id"); return -2; }
-        HuffTable& H = tc ? P->ac[th] : P->dc[th];
-        int cnt = 0;
-        H.bits[0] = 0;
-        for (int i = 1; i <= 16; ++i) { H.bits[i] = s[o + i]; cnt += s[o + i]; }
-        o += 17;
-        if (cnt > 256 || o + cnt > n) { set_error("jpeg: bad DHT length"); return -2; }
-        memcpy(H.vals, s + o, cnt);
-        o += cnt;
-        if (!H.build()) { set_error("jpeg: invalid Huffman table"); return -2; }
-        H.present = true;
-      }
-    } else if (m == 0xC0 || m == 0xC1) {                 // SOF0 / SOF1 (Huffman, sequential)
+      const int rc = parse_dht(s, n, P);
+      if (rc) return rc;
+    } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {    // SOF0 / SOF1 (sequential) / SOF2 (progressive), Huffman
+      I.progressive = m == 0xC2;
       if (n < 6) { set_error("jpeg: bad SOF"); return -2; }
       if (s[0] != 8) { set_error("jpeg: %d-bit samples are not supported (8 only)", s[0]); return -3; }
       I.height = rd16(s + 1); I.width = rd16(s + 3); I.ncomp = s[5];
@@ -171,9 +178,8 @@ int parse(const uint8_t* d, size_t len, Parsed* P) {
         if (tq[c] > 3) { set_error("jpeg: bad quantisation table id"); return -2; }
       }
       have_sof = true;
-    } else if (m == 0xC2 || (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC)) {
-      I.progressive = 1;
-      set_error("jpeg: SOF%d (progressive / lossless / arithmetic) is not supported by the GPU front end", m - 0xC0);
+    } else if (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+      set_error("jpeg: SOF%d (lossless / hierarchical / arithmetic coding) is not supported", m - 0xC0);
       return -3;
     } else if (m == 0xDD) {
       if (n >= 2) I.restart_interval = rd16(s);
@@ -184,6 +190,7 @@ int parse(const uint8_t* d, size_t len, Parsed* P) {
       if (n >= 12 && memcmp(s, "Adobe", 5) == 0) I.color_transform = s[11];
     } else if (m == 0xDA) {                              // SOS
       if (!have_sof) { set_error("jpeg: SOS before SOF"); return -2; }
+      if (I.progressive) { P->scan_offset = pos - 2; break; }   // the scans are walked by decode_progressive()
       const int ns = s[0];
       if (ns != I.ncomp || n < 1 + 2 * ns + 3) {
         set_error("jpeg: only one interleaved scan covering all components is supported (scan has %d of %d)", ns, I.ncomp);
@@ -307,6 +314,143 @@ struct BitReader {
   }
 };
 
+// ---- progressive JPEG (SOF2, T.81 Annex G): several scans refine one coefficient array.  Entropy decoding is
+// serial per scan and runs here on the host; the GPU stages that follow are the same as for baseline files.
+inline int get_bits(BitReader& br, int n) {
+  if (!n) return 0;
+  if (br.nbits < n) br.fill();
+  const int v = (int)br.peek(n);
+  br.skip(n);
+  return v;
+}
+
+int decode_progressive(const uint8_t* d, size_t len, Parsed& P, int16_t* coef) {
+  const vltk_jpeg_info& I = P.info;
+  memset(coef, 0, (size_t)I.coef_count * sizeof(int16_t));
+  size_t pos = P.scan_offset;                            // at the 0xFF of the first SOS
+  int restart_interval = I.restart_interval;
+  while (pos + 4 <= len) {
+    if (d[pos] != 0xFF) { ++pos; continue; }
+    while (pos < len && d[pos] == 0xFF) ++pos;
+    if (pos >= len) break;
+    const int m = d[pos++];
+    if (m == 0xD9) break;
+    if (m == 0 || (m >= 0xD0 && m <= 0xD7) || m == 0x01) continue;
+    if (pos + 2 > len) break;
+    const int L = rd16(d + pos);
+    if (L < 2 || pos + L > len) { set_error("jpeg: truncated segment 0xFF%02X", m); return -2; }
+    const uint8_t* s = d + pos + 2;
+    const int n = L - 2;
+    if (m == 0xC4) { const int rc = parse_dht(s, n, &P); if (rc) return rc; pos += L; continue; }
+    if (m == 0xDD) { if (n >= 2) restart_interval = rd16(s); pos += L; continue; }
+    if (m != 0xDA) { pos += L; continue; }
+    // ---- one scan
+    const int ns = s[0];
+    if (ns < 1 || ns > I.ncomp || n < 1 + 2 * ns + 3) { set_error("jpeg: bad SOS"); return -2; }
+    int comp[3], td[3], ta[3];
+    for (int k = 0; k < ns; ++k) {
+      int c = -1;
+      for (int j = 0; j < I.ncomp; ++j) if (I.comp_id[j] == s[1 + 2 * k]) c = j;
+      if (c < 0) { set_error("jpeg: scan names an unknown component"); return -2; }
+      comp[k] = c; td[k] = s[2 + 2 * k] >> 4; ta[k] = s[2 + 2 * k] & 15;
+      if (td[k] > 3 || ta[k] > 3) { set_error("jpeg: bad table id in SOS"); return -2; }
+    }
+    const int Ss = s[1 + 2 * ns], Se = s[2 + 2 * ns], Ah = s[3 + 2 * ns] >> 4, Al = s[3 + 2 * ns] & 15;
+    if (Ss > Se || Se > 63 || (Ss == 0 && Se != 0) || (Ss > 0 && ns != 1) || Al > 13) { set_error("jpeg: invalid progressive scan parameters"); return -2; }
+    for (int k = 0; k < ns; ++k) {
+      if (Ss == 0 && Ah == 0 && !P.dc[td[k]].present) { set_error("jpeg: scan references a missing DC table"); return -2; }
+      if (Ss > 0 && !P.ac[ta[k]].present) { set_error("jpeg: scan references a missing AC table"); return -2; }
+    }
+    BitReader br(d + pos + L, d + len);
+    int pred[3] = {0, 0, 0};
+    int eobrun = 0;
+    int until_restart = restart_interval;
+    // block iteration: interleaved scans walk MCUs; a single-component scan walks that component's own block grid
+    const bool inter = ns > 1;
+    const int c0 = comp[0];
+    const int bw = inter ? I.mcus_x : (I.comp_w[c0] + 7) / 8, bh = inter ? I.mcus_y : (I.comp_h[c0] + 7) / 8;
+    for (int uy = 0; uy < bh; ++uy)
+      for (int ux = 0; ux < bw; ++ux) {
+        if (restart_interval && until_restart == 0) {
+          if (!br.restart()) { set_error("jpeg: missing restart marker in a progressive scan"); return -2; }
+          pred[0] = pred[1] = pred[2] = 0; eobrun = 0;
+          until_restart = restart_interval;
+        }
+        for (int k = 0; k < ns; ++k) {
+          const int c = comp[k];
+          const int nby = inter ? I.vs[c] : 1, nbx = inter ? I.hs[c] : 1;
+          for (int by = 0; by < nby; ++by)
+            for (int bx = 0; bx < nbx; ++bx) {
+              const int64_t blk = inter ? (int64_t)(uy * I.vs[c] + by) * I.blocks_w[c] + (ux * I.hs[c] + bx)
+                                        : (int64_t)uy * I.blocks_w[c] + ux;
+              int16_t* out = coef + I.coef_offset[c] + blk * 64;
+              if (Ss == 0) {
+                if (Ah == 0) {                           // DC first (G.1.2.1)
+                  const int t = br.decode(P.dc[td[k]]);
+                  if (t < 0 || t > 15) { set_error("jpeg: corrupt DC code in a progressive scan"); return -2; }
+                  pred[c] += br.receive_extend(t);
+                  out[0] = (int16_t)(pred[c] * (1 << Al));
+                } else if (get_bits(br, 1)) out[0] |= (int16_t)(1 << Al);   // DC refinement
+              } else if (Ah == 0) {                      // AC first (G.1.2.2)
+                if (eobrun > 0) { --eobrun; continue; }
+                const HuffTable& A = P.ac[ta[k]];
+                for (int kk = Ss; kk <= Se;) {
+                  const int rs = br.decode(A);
+                  if (rs < 0) { set_error("jpeg: corrupt AC code in a progressive scan"); return -2; }
+                  const int r = rs >> 4, sz = rs & 15;
+                  if (sz == 0) {
+                    if (r < 15) { eobrun = (1 << r) - 1; if (r) eobrun += get_bits(br, r); break; }
+                    kk += 16;
+                  } else {
+                    kk += r;
+                    if (kk > 63) { set_error("jpeg: AC run past the block in a progressive scan"); return -2; }
+                    out[kZigzag[kk]] = (int16_t)(br.receive_extend(sz) * (1 << Al));
+                    ++kk;
+                  }
+                }
+              } else {                                   // AC refinement (G.1.2.3)
+                const HuffTable& A = P.ac[ta[k]];
+                const int p1 = 1 << Al, m1 = -(1 << Al);
+                int kk = Ss;
+                if (eobrun == 0) {
+                  for (; kk <= Se; ++kk) {
+                    const int rs = br.decode(A);
+                    if (rs < 0) { set_error("jpeg: corrupt AC code in a progressive scan"); return -2; }
+                    int r = rs >> 4, sz = rs & 15, val = 0;
+                    if (sz) val = get_bits(br, 1) ? p1 : m1;
+                    else if (r != 15) { eobrun = 1 << r; if (r) eobrun += get_bits(br, r); break; }
+                    do {                                 // skip r zero-history coefficients, refining the others
+                      int16_t* cf = out + kZigzag[kk];
+                      if (*cf) {
+                        if (get_bits(br, 1) && (*cf & p1) == 0) *cf = (int16_t)(*cf + (*cf >= 0 ? p1 : m1));
+                      } else if (--r < 0) break;
+                      ++kk;
+                    } while (kk <= Se);
+                    if (val && kk <= 63) out[kZigzag[kk]] = (int16_t)val;
+                  }
+                }
+                if (eobrun > 0) {
+                  for (; kk <= Se; ++kk) {
+                    int16_t* cf = out + kZigzag[kk];
+                    if (*cf && get_bits(br, 1) && (*cf & p1) == 0) *cf = (int16_t)(*cf + (*cf >= 0 ? p1 : m1));
+                  }
+                  --eobrun;
+                }
+              }
+            }
+        }
+        --until_restart;
+      }
+    // continue after this scan's entropy-coded data: the next marker that is not RSTn / stuffing
+    size_t q = (size_t)(br.p - d);
+    if (q > pos + L + 8) q -= 8;                         // the reader may have run up to 8 bytes ahead
+    else q = pos + L;
+    while (q + 1 < len && !(d[q] == 0xFF && d[q + 1] != 0 && d[q + 1] != 0xFF && !(d[q + 1] >= 0xD0 && d[q + 1] <= 0xD7))) ++q;
+    pos = q;
+  }
+  return 0;
+}
+
 int decode_scan(const uint8_t* d, size_t len, const Parsed& P, int16_t* coef) {
   const vltk_jpeg_info& I = P.info;
   memset(coef, 0, (size_t)I.coef_count * sizeof(int16_t));
@@ -381,7 +525,7 @@ int vltk_jpeg_decode_coefficients(const uint8_t* data, size_t len, int16_t* coef
   int rc = parse(data, len, &P);
   if (rc) return rc;
   if (P.info.coef_count > coef_capacity) { set_error("jpeg_decode_coefficients: buffer holds %lld of %lld coefficients", (long long)coef_capacity, (long long)P.info.coef_count); return -2; }
-  return decode_scan(data, len, P, coef);
+  return P.info.progressive ? decode_progressive(data, len, P, coef) : decode_scan(data, len, P, coef);
 }
 
 int vltk_jpeg_decode_coefficients_batch(int n, const uint8_t* const* datas, const size_t* lens, int16_t* const* coefs,
@@ -477,7 +621,8 @@ int vltk_jpeg_gpu_prepare_batch(int n, const uint8_t* const* datas, const size_t
     coef_offsets[i] = coff;
     D.coef_off = coff;
     coff += (I.coef_count + 7) / 8 * 8;
-    on_gpu[i] = 1;
+    on_gpu[i] = I.progressive ? 0 : 1;                   // progressive scans are entropy-decoded on the host
+    if (!on_gpu[i]) continue;
     D.tables_off = (int64_t)off;
     vltk::DevHuff* T = reinterpret_cast<vltk::DevHuff*>(blob + off);
     for (int c = 0; c < 3; ++c) {

@@ -5,7 +5,8 @@ inverse DCT + chroma upsampling + colour conversion on the GPU (vltk_b200/csrc/j
 libjpeg-turbo's default pipeline.  The decoded BGR u8 image never exists in host memory: coefficients go up
 (int16, about the size of the u8 image), the existing fused resize/normalise/pad kernel consumes the device image.
 
-Files the front end does not cover (progressive, 12-bit, CMYK, exotic sampling) raise `UnsupportedJpeg`: the
+Progressive files take the host entropy decoder (their scans are serial) and the same GPU stages.  Files the front end
+does not cover (12-bit, CMYK, arithmetic coding, exotic sampling) raise `UnsupportedJpeg`: the
 caller decides (there is no silent CPU decode behind this API).
 """
 from __future__ import annotations
@@ -24,7 +25,7 @@ JpegInfo = _lib.JpegInfo
 
 
 class UnsupportedJpeg(ValueError):
-    """A valid JPEG outside the front end's coverage (progressive, 12-bit, CMYK, unusual sampling)."""
+    """A valid JPEG outside the front end's coverage (12-bit, CMYK, arithmetic coding, unusual sampling)."""
 
 
 def _check(rc: int, what: str):

@@ -36,7 +36,7 @@ def _is_jpeg(head: bytes) -> bool:
 class Preprocess:
     """images: list of decoded BGR u8 tensors/arrays [h,w,3] (host or device), file paths, or encoded JPEG bytes.
 
-    host_decode_unsupported: JPEG files outside the GPU front end's coverage (progressive, CMYK, ...) raise
+    host_decode_unsupported: JPEG files outside the GPU front end's coverage (CMYK, 12-bit, ...) raise
     `jpeg.UnsupportedJpeg` by default; set True to read those files with cv2 on the host like the reference."""
 
     def __init__(self, cfg: FRCNNConfig = None, device: int = 0, host_decode_unsupported: bool = False):
