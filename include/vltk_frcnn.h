@@ -148,6 +148,14 @@ int vltk_conv2d_dual_nhwc(const void* x, const float* weight, const void* x2, co
                           const float* shift, void* y, int n, int h, int w, int cin, int h2, int w2,
                           int cin2, int stride2, int cout, int relu, void* stream);
 
+/* Kernel selection for the tcgen05 convolutions (process-wide; A/B measurements and the kernel-equivalence tests).
+ * Layers with a 256-wide cout tile, bf16 output and at least `min_pixels` output pixels run on CTA pairs
+ * (tcgen05 cta_group::2: two SMs share one W tile); 0 = never.  `residual_layers` = 0 keeps the layers with a
+ * shortcut / fused-mean epilogue on the single-CTA kernel.  A negative argument leaves that setting unchanged.
+ * Defaults: 32768 and 0 (environment: VLTK_CTA2, VLTK_CTA2_RES).  Both kernels accumulate in the same order and
+ * produce bit-identical outputs.  Always returns 0. */
+int vltk_conv_tc_set_cta_pairs(int min_pixels, int residual_layers);
+
 /* nn.Linear on the tensor pipe with fp32-faithful arithmetic (frcnn.py:1729-1737 in bf16 mode):
  * y[m,n] = act(x[m,k] . weight[n,k]^T + bias), all DEVICE f32; operands are split into bf16
  * hi+lo planes and accumulated as hi*hi + lo*hi + hi*lo in one fp32 TMEM tile.  k,n % 64 == 0. */

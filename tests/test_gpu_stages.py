@@ -83,8 +83,10 @@ def test_conv_tcgen05_matches_simt_and_reference(dev, case):
     assert ((y_tc - ref).abs() <= ulp * (ref.abs() + 1e-2)).all()
 
 
-def test_residual_ring_two_epilogue_groups_is_deterministic_under_hbm_load(dev):
-    """res5 conv3 shape at HBM scale (M = 600*196 rows, K=512 -> 2048, +residual, ~1.4 GB of traffic): the two
+@pytest.mark.parametrize("pairs", [0, 1])
+def test_residual_ring_two_epilogue_groups_is_deterministic_under_hbm_load(dev, pairs):
+    """(run on the single-CTA kernel, pairs=0, and on the CTA-pair kernel, whose ring is group-private, pairs=1)
+    res5 conv3 shape at HBM scale (M = 600*196 rows, K=512 -> 2048, +residual, ~1.4 GB of traffic): the two
     epilogue warpgroups share ONE residual TMA ring, whose boxes land out of order under load.  Without the ring
     guard in conv_tc.cu a parity wait could pass on the other group's stale phase (wrong data, then a hung
     pipeline).  Ten back-to-back runs must be bit-identical and match an fp64 evaluation on sampled rows."""
@@ -96,16 +98,88 @@ def test_residual_ring_two_epilogue_groups_is_deterministic_under_hbm_load(dev):
     sc = (torch.rand(cout, generator=g) * 0.2 + 0.9).to(dev)
     sh = (torch.randn(cout, generator=g) * 0.1).to(dev)
     res = torch.randn(rois, 14, 14, cout, generator=g).to(dev).bfloat16()
-    y0 = stages.conv2d_nhwc(x, wt, sc, sh, res, 1, 0, 1, True, mode="bf16", tensor_cores=True)
-    for _ in range(9):
-        y = stages.conv2d_nhwc(x, wt, sc, sh, res, 1, 0, 1, True, mode="bf16", tensor_cores=True)
-        assert torch.equal(y, y0)
+    stages.set_cta_pairs(1 if pairs else 0, pairs)
+    try:
+        y0 = stages.conv2d_nhwc(x, wt, sc, sh, res, 1, 0, 1, True, mode="bf16", tensor_cores=True)
+        for _ in range(9):
+            y = stages.conv2d_nhwc(x, wt, sc, sh, res, 1, 0, 1, True, mode="bf16", tensor_cores=True)
+            assert torch.equal(y, y0)
+    finally:
+        stages.set_cta_pairs(CTA_PAIRS_DEFAULT, 0)
     rows = torch.randint(0, rois * 196, (512,), generator=g)
     xs = x.reshape(-1, cin)[rows.to(dev)].double()
     ref = torch.relu(xs @ wt.reshape(cout, cin).double().T * sc.double() + sh.double()
                      + res.reshape(-1, cout)[rows.to(dev)].double()).cpu()
     got = y0.reshape(-1, cout)[rows.to(dev)].double().cpu()
     assert ((got - ref).abs() <= 2.0 ** -7 * (ref.abs() + 1e-2)).all()
+
+
+CTA_PAIRS_DEFAULT = 32768       # include/vltk_frcnn.h, vltk_conv_tc_set_cta_pairs
+
+
+# n, h, w, cin, cout, k, pad, dil, residual
+PAIR_CASES = [
+    (8, 14, 14, 1024, 512, 1, 0, 1, False),      # res5 conv1 (even number of row tiles)
+    (5, 14, 14, 512, 512, 3, 2, 2, False),       # res5 conv2, dilated 3x3: 980 rows = 7.66 row tiles (odd pair tail)
+    (3, 20, 33, 256, 256, 3, 1, 1, False),       # ragged rows: a tile spans image rows and images
+    (1, 7, 9, 128, 256, 1, 0, 1, False),         # 63 rows: one pair whose second CTA is entirely out of range
+    (9, 14, 14, 512, 2048, 1, 0, 1, True),       # res5 conv3 + shortcut ring, 8 cout tiles, odd row-tile count
+    (1, 5, 5, 64, 256, 1, 0, 1, True),           # 25 rows, residual
+    (40, 14, 14, 512, 1024, 1, 0, 1, True),      # more pair tiles than CTA pairs: accumulator + ring phases wrap
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_cta_pair_kernel_is_bit_identical_to_single_cta_kernel(dev, case):
+    """conv_tc3_kernel (tcgen05 cta_group::2, a CTA pair per 256 x 256 tile, half a W tile per CTA) accumulates the
+    same k-blocks in the same order as conv_tc2_kernel and shares its epilogue arithmetic: outputs must be
+    bit-identical, and within 1 bf16 ulp of an fp64 evaluation."""
+    from vltk_b200 import stages
+    n, h, w, cin, cout, k, pad, dil, has_res = case
+    g = torch.Generator().manual_seed(n * 1000 + cin + k)
+    x = torch.randn(n, h, w, cin, generator=g).to(dev).bfloat16()
+    wt = (torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5).bfloat16().float().to(dev)
+    sc = (torch.rand(cout, generator=g) * 0.5 + 0.75).to(dev)
+    sh = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    res = torch.randn(n, h, w, cout, generator=g).to(dev).bfloat16() if has_res else None
+    try:
+        stages.set_cta_pairs(0, 0)
+        y2 = stages.conv2d_nhwc(x, wt, sc, sh, res, 1, pad, dil, True, mode="bf16", tensor_cores=True)
+        stages.set_cta_pairs(1, 1)
+        y3 = stages.conv2d_nhwc(x, wt, sc, sh, res, 1, pad, dil, True, mode="bf16", tensor_cores=True)
+        y3b = stages.conv2d_nhwc(x, wt, sc, sh, res, 1, pad, dil, True, mode="bf16", tensor_cores=True)
+    finally:
+        stages.set_cta_pairs(CTA_PAIRS_DEFAULT, 0)
+    assert torch.equal(y3, y2) and torch.equal(y3b, y3)
+    ref = _ref_conv(x, wt, sc, sh, res, 1, pad, dil, True)
+    assert ((y3.float().cpu().double() - ref.double()).abs() <= 2.0 ** -7 * (ref.double().abs() + 1e-2)).all()
+
+
+@pytest.mark.parametrize("rois,cin,cout", [(1, 512, 256), (3, 512, 2048), (80, 512, 2048)])
+def test_cta_pair_fused_meanpool_and_concat_are_bit_identical_to_single_cta(dev, rois, cin, cout):
+    """The ROI-aligned fused 14x14 mean (one ROI per CTA pair: rank 0 rows [0,128), rank 1 rows [128,196)) and the
+    K-concatenated projection tail on CTA pairs: same partial sums / same tiles as the single-CTA kernel."""
+    from vltk_b200 import stages
+    g = torch.Generator().manual_seed(rois * 13 + cout)
+    x = torch.randn(rois, 14, 14, cin, generator=g).to(dev).bfloat16()
+    wt = (torch.randn(cout, cin, 1, 1, generator=g) * (2.0 / cin) ** 0.5).bfloat16().float().to(dev)
+    sc = (torch.rand(cout, generator=g) * 0.2 + 0.1).to(dev)
+    sh = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    res = torch.randn(rois, 14, 14, cout, generator=g).abs().to(dev).bfloat16()
+    x2 = torch.randn(rois, 14, 14, 2 * cin, generator=g).abs().to(dev).bfloat16()
+    w2 = (torch.randn(cout, 2 * cin, generator=g) * (0.5 / cin) ** 0.5).bfloat16().float().to(dev)
+    out = {}
+    try:
+        for pairs in (0, 1):
+            stages.set_cta_pairs(pairs, pairs)
+            out[pairs] = (stages.conv2d_meanpool_nhwc(x, wt, sc, sh, res, 196),
+                          stages.conv2d_dual_nhwc(x, wt.reshape(cout, cin), x2, w2, sh, stride2=1, relu=True))
+    finally:
+        stages.set_cta_pairs(CTA_PAIRS_DEFAULT, 0)
+    assert torch.equal(out[1][0], out[0][0])
+    assert torch.equal(out[1][1], out[0][1])
+    ref = _ref_conv(x, wt, sc, sh, res, 1, 0, 1, True).double().reshape(rois, 196, cout).mean(1)
+    np.testing.assert_allclose(out[1][0].cpu().numpy(), ref.numpy(), rtol=2e-5, atol=2e-5)
 
 
 @pytest.mark.parametrize("rois,cin,cout", [(1, 512, 256), (5, 512, 2048), (37, 1024, 512)])

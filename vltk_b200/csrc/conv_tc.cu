@@ -14,6 +14,7 @@
 // Reference layers replaced: every Conv2d+BN(+ReLU) of res2-res5 and the RPN 3x3
 // (frcnn.py:794-822, 963-979, 1345-1355, 1569).
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
@@ -677,6 +678,333 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 2) tmem_dealloc<2 * BN>(tmem_base);
 }
 
+
+// =========================================================================================
+// v3: CTA pairs (tcgen05 cta_group::2).  Two CTAs of a cluster compute a 256 x 256 output tile with ONE
+// tcgen05.mma stream issued by the leader CTA (rank 0): each CTA stages its own 128 pixel rows of A and only HALF of
+// the W tile (128 of the 256 couts), the tensor cores of both SMs read both halves.  A stage is 16 + 16 KB instead
+// of 16 + 32 KB, so the same 192 KB hold SIX stages instead of four — the mainloop is bound by how many operand
+// bytes it keeps in flight (profiles/r01_summary.md §26) — and the W operand crosses L2 -> SM once per pair.
+//   * both CTAs' TMA loads complete on the LEADER's full barrier (cta_group::2 loads, peer bit cleared);
+//   * tcgen05.commit multicasts to both CTAs' empty / tmem-full barriers;
+//   * each CTA drains its own TMEM half; the peer's epilogue warps release the accumulator on the leader's barrier.
+// Scope: bf16 out, BN = 256 (the multi-pass K loop of TcConcat is supported).  HAS_RES adds the shortcut tensor through
+// a CTA-local 4-slab ring (4 operand stages instead of 6 make room for it); each epilogue group owns two fixed slots of
+// the ring, so — unlike v2's shared odd-depth ring — a slot's previous occupant was consumed by the SAME group and plain
+// parity waits are sound.  POOL is v2's ROI-aligned fused 14x14 mean: the pair covers one ROI (rank 0 rows [0,128),
+// rank 1 rows [128, pool_rows)), so tile numbering and the partial-sum layout are identical to v2's.
+constexpr int B3_STAGE_BYTES = 128 * BK * 2;   // half a 256-cout W tile
+template <int STAGES, bool HAS_RES>
+struct Smem3 {
+  static constexpr int RS = HAS_RES ? 4 : 0;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B3_STAGE_BYTES;   // 32 KB
+  static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
+  static constexpr int OFF_OUT = STAGES * STAGE_BYTES;
+  static constexpr int OFF_RES = OFF_OUT + 2 * SLAB_BYTES;
+  static constexpr int OFF_SCALE = OFF_RES + RS * SLAB_BYTES;
+  static constexpr int OFF_BARS = OFF_SCALE + 2 * 2 * 128 * 4;
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * RS;
+  static constexpr int TOTAL = OFF_BARS + NUM_BARS * 8 + 16;
+  static_assert(TOTAL <= 232448, "exceeds the 227 KB shared memory of one sm_100 CTA");
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;        // shared::cluster address of the same offset in CTA rank 0
+constexpr uint64_t TMA_DESC_DEFAULT = 0x1000000000000000ull;
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "l"(TMA_DESC_DEFAULT)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_im2col_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c, int w, int h,
+                                                    int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & PEER_BIT_MASK), "r"(c), "r"(w), "r"(h), "r"(n),
+        "h"(off_w), "h"(off_h), "l"(TMA_DESC_DEFAULT)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {          // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {       // arrive on the same barrier of CTA rank 0
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
+}
+
+template <int STAGES, bool HAS_RES, bool POOL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2,
+                const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, TcParams2 p) {
+  using S = Smem3<STAGES, HAS_RES>;
+  static_assert(!POOL || HAS_RES, "the pooled epilogue is the res5 conv3 tail (has a shortcut)");
+  constexpr int BN = 256, NSLAB = BN / SLAB, EG = 2, RS = S::RS;
+  extern __shared__ __align__(1024) unsigned char smem_dyn3[];
+  const uint32_t base = smem_u32(smem_dyn3);
+  if (base & 1023u) { if (threadIdx.x == 0) printf("conv_tc3: dynamic smem base %u is not 1024 B aligned\n", base); __trap(); }
+  unsigned char* gbase = smem_dyn3;
+  const uint32_t sA = base, sB = base + S::OFF_B, sOut = base + S::OFF_OUT, sRes = base + S::OFF_RES;
+  float* s_scale_all = reinterpret_cast<float*>(gbase + S::OFF_SCALE);
+  const uint32_t bars = base + S::OFF_BARS;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+  auto rfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + 4 + s); };
+  auto rempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + 4 + RS + s); };
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + S::OFF_BARS + S::NUM_BARS * 8);
+  const uint32_t tmem_slot = bars + S::NUM_BARS * 8;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  int num_kb = 0;
+  for (int ps = 0; ps < p.npass; ++ps) num_kb += p.taps * p.pass_cblocks[ps];
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int num_pair_tiles = p.num_tiles;              // (row-tile pairs) x (cout tiles)
+  // first output row of this CTA's half of pair tile t (POOL: one ROI per pair, second half starts at row 128 of the ROI)
+  auto tile_m0 = [&](int t) -> int64_t {
+    const int64_t pt = t / p.n_tiles;
+    return POOL ? pt * p.pool_rows + (int64_t)rank * BM : (pt * 2 + rank) * BM;
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY);
+    if (p.npass > 1) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
+    if (HAS_RES) tma_prefetch_desc(&tmR);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * 4 * EG); }
+    for (int s = 0; s < RS; ++s) { mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), 4); }
+    fence_barrier_init();
+  }
+  cluster_sync_all();                                  // barriers of both CTAs are initialised before anyone signals them
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  cluster_sync_all();
+
+  // Programmatic dependent launch, as in v2: nothing above touched an activation.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  if (warp == 0 && lane == 0) {
+    // ================= TMA producer (both CTAs: own A rows, own half of W) =================
+    int stage = 0; uint32_t phase = 0;
+    for (int t = pair; t < num_pair_tiles; t += npairs) {
+      const int n0 = (t % p.n_tiles) * BN;
+      const int64_t m0 = tile_m0(t);
+      const int ow0 = (int)(m0 % p.OW);
+      const int64_t q = m0 / p.OW;
+      const int oh0 = (int)(q % p.OH), img0 = (int)(q / p.OH);
+      for (int ps = 0; ps < p.npass; ++ps) {
+        const CUtensorMap* ma = p.pass_a[ps] ? &tmA2 : &tmA;
+        const CUtensorMap* mb = p.pass_b[ps] ? &tmB2 : &tmB;
+        const int cblocks = p.pass_cblocks[ps];
+        const int bw = ow0 * p.pass_stride[ps] - p.pad, bh = oh0 * p.pass_stride[ps] - p.pad;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int kh = tap / p.KW, kw = tap - kh * p.KW;
+          for (int cb = 0; cb < cblocks; ++cb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            if (leader) mbar_expect_tx(full_bar(stage), 2 * S::STAGE_BYTES);   // both CTAs' bytes land on this barrier
+            tma2_load_im2col_4d(sA + stage * A_STAGE_BYTES, ma, full_bar(stage), cb * BK, bw, bh, img0,
+                                (uint16_t)(kw * p.dil), (uint16_t)(kh * p.dil));
+            tma2_load_2d(sB + stage * B3_STAGE_BYTES, mb, full_bar(stage), (tap * cblocks + cb) * BK, n0 + (int)rank * 128);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ================= MMA issuer (leader CTA only) =================
+    constexpr uint32_t idesc = make_idesc(256, BN);
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int t = pair; t < num_pair_tiles; t += npairs, ++it) {
+      const int acc = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), use ^ 1u);            // both CTAs' epilogues have drained this accumulator
+      tc_fence_after();
+      const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t a = sA + stage * A_STAGE_BYTES, b = sB + stage * B3_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k)
+          umma2_bf16(d, make_smem_desc(a + k * UMMA_K * 2), make_smem_desc(b + k * UMMA_K * 2), idesc, (kb | k) ? 1u : 0u);
+        umma2_commit_mc(empty_bar(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma2_commit_mc(tfull_bar(acc));
+    }
+  } else if (HAS_RES && warp == 3 && lane == 0) {
+    // ================= residual producer (CTA-local ring; slab s of a tile -> slot (s % 2) * 2 + s / 2) =================
+    int it = 0;
+    for (int t = pair; t < num_pair_tiles; t += npairs, ++it) {
+      const int n0 = (t % p.n_tiles) * BN;
+      const int m0 = (int)tile_m0(t);
+      const uint32_t rphase = (uint32_t)it & 1u;
+      for (int s = 0; s < NSLAB; ++s) {
+        const int slot = (s & 1) * 2 + (s >> 1);
+        mbar_wait(rempty_bar(slot), rphase ^ 1u);
+        mbar_expect_tx(rfull_bar(slot), SLAB_BYTES);
+        tma_load_2d(sRes + slot * SLAB_BYTES, &tmR, rfull_bar(slot), n0 + s * SLAB, m0);
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue (each CTA: its own 128 rows) =================
+    const int g = (warp - 4) >> 2, e = warp & 3;
+    const int row = e * 32 + lane;
+    const int et = threadIdx.x - 128 - g * 128;
+    const bool issuer = et == 0;
+    const uint32_t swz = (uint32_t)(row & 7);
+    const uint32_t sOutG = sOut + (uint32_t)g * SLAB_BYTES;
+    float* s_scale = s_scale_all + g * 2 * 128;
+    float* s_shift = s_scale + 128;
+    auto group_barrier = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
+    int it = 0;
+    for (int t = pair; t < num_pair_tiles; t += npairs, ++it) {
+      const int n0 = (t % p.n_tiles) * BN;
+      const int m0 = (int)tile_m0(t);
+      (void)m0;
+      const int acc = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1) & 1u;
+      for (int i = et; i < 128; i += 128) {            // my slabs (s = g, g + 2): 2 x 64 columns
+        const int j = i >> 6, s = g + j * EG;
+        const int col = n0 + s * SLAB + (i & 63);
+        s_scale[i] = p.scale ? p.scale[col] : 1.f;
+        s_shift[i] = p.shift ? p.shift[col] : 0.f;
+      }
+      mbar_wait(tfull_bar(acc), use);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int s = g, j = 0; s < NSLAB; s += EG, ++j) {
+        const int slot = g * 2 + j;
+        (void)slot;
+        uint32_t v[64];
+        {
+          uint32_t lo[32], hi[32];
+          tmem_ld32(tacc + (uint32_t)(s * SLAB), lo);
+          tmem_ld32(tacc + (uint32_t)(s * SLAB + 32), hi);
+          tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) { v[jj] = lo[jj]; v[32 + jj] = hi[jj]; }
+        }
+        if (s + EG >= NSLAB) {                         // my last slab: release the accumulator on the LEADER's barrier
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_leader(tempty_bar(acc)); }
+        }
+        if (HAS_RES) mbar_wait(rfull_bar(slot), (uint32_t)it & 1u);
+        if (!POOL && issuer) bulk_wait_read<0>();      // the store that last read sOutG has drained it
+        group_barrier();                               // sOutG reusable (POOL: last slab's column readers done); scale/shift visible
+        const uint32_t orow = sOutG + (uint32_t)row * 128u;
+        const uint32_t rrow = sRes + (uint32_t)slot * SLAB_BYTES + (uint32_t)row * 128u;
+        (void)rrow;
+        float pv[POOL ? 64 : 1];
+        (void)pv;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t coff = ((uint32_t)q ^ swz) << 4;
+          const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + j * SLAB + q * 8);
+          const float4 sc1 = *reinterpret_cast<const float4*>(s_scale + j * SLAB + q * 8 + 4);
+          const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + j * SLAB + q * 8);
+          const float4 sh1 = *reinterpret_cast<const float4*>(s_shift + j * SLAB + q * 8 + 4);
+          float f[8];
+          f[0] = fmaf(__uint_as_float(v[q * 8 + 0]), sc0.x, sh0.x); f[1] = fmaf(__uint_as_float(v[q * 8 + 1]), sc0.y, sh0.y);
+          f[2] = fmaf(__uint_as_float(v[q * 8 + 2]), sc0.z, sh0.z); f[3] = fmaf(__uint_as_float(v[q * 8 + 3]), sc0.w, sh0.w);
+          f[4] = fmaf(__uint_as_float(v[q * 8 + 4]), sc1.x, sh1.x); f[5] = fmaf(__uint_as_float(v[q * 8 + 5]), sc1.y, sh1.y);
+          f[6] = fmaf(__uint_as_float(v[q * 8 + 6]), sc1.z, sh1.z); f[7] = fmaf(__uint_as_float(v[q * 8 + 7]), sc1.w, sh1.w);
+          if (HAS_RES) {
+            uint4 r = lds128(rrow + coff);
+            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              float2 rf = __bfloat1622float2(rb[jj]);
+              f[2 * jj] += rf.x; f[2 * jj + 1] += rf.y;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) f[jj] = fmaxf(f[jj], 0.f);
+          }
+          if constexpr (POOL) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) pv[q * 8 + jj] = f[jj];
+          } else {
+            uint4 o;
+            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) ob[jj] = __floats2bfloat162_rn(f[2 * jj], f[2 * jj + 1]);
+            sts128(orow + coff, o);
+          }
+        }
+        if (HAS_RES) {                                 // this warp is done with the residual slab
+          __syncwarp();
+          if (lane == 0) mbar_arrive(rempty_bar(slot));
+        }
+        if constexpr (POOL) {
+          // same reduction tree as v2's POOL epilogue (bit-identical partial sums)
+          const int mt = (t / p.n_tiles) * 2 + (int)rank;
+          const int valid = rank ? p.pool_rows - BM : BM;
+          float* comb = reinterpret_cast<float*>(gbase + S::OFF_OUT + (size_t)g * SLAB_BYTES) + (j & 1) * 256;
+          float2 ts = make_float2(0.f, 0.f);
+          if (e * 32 < valid) {                        // warp-uniform
+            const bool in = row < valid;
+#pragma unroll
+            for (int q = 0; q < 64; ++q) pv[q] = in ? pv[q] : 0.f;
+            warp_colsum64(pv, lane);
+            ts = make_float2(pv[0], pv[1]);
+          }
+          *reinterpret_cast<float2*>(comb + e * 64 + 2 * lane) = ts;
+          group_barrier();
+          if (et < 64) {
+            const float* c4 = comb + et;
+            const float tot = ((c4[0] + c4[64]) + c4[128]) + c4[192];
+            p.pool_partial[(int64_t)mt * p.Cout + n0 + s * SLAB + et] = tot;
+          }
+        } else {
+          fence_proxy_async_smem();
+          group_barrier();
+          if (issuer) {
+            tma_store_2d(&tmY, sOutG, n0 + s * SLAB, m0);
+            bulk_commit();
+          }
+        }
+      }
+    }
+    if (!POOL && issuer) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                  // the peer may still be reading / the leader still issuing into its TMEM
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -800,6 +1128,31 @@ int launch2e(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
   return 0;
 }
 
+template <int STAGES, bool HAS_RES, bool POOL>
+int launch3(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
+  using S = Smem3<STAGES, HAS_RES>;
+  static DeviceOnce once;
+  if (once.first()) {
+    VLTK_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<STAGES, HAS_RES, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+  }
+  tp.n_tiles = cout_pad / 256;
+  const int64_t pair_tiles = (POOL ? tp.M / tp.pool_rows : ceil_div64(ceil_div64(tp.M, BM), 2)) * tp.n_tiles;
+  VLTK_CHECK(pair_tiles < (1ll << 31), "conv_tc: too many tiles");
+  tp.num_tiles = (int)pair_tiles;
+  const int pairs = (int)std::min<int64_t>(pair_tiles, num_sms() / 2);
+  static const bool use_pdl = [] { const char* e = getenv("VLTK_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;   // cluster dims are compiled in
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+  VLTK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc3_kernel<STAGES, HAS_RES, POOL>, m.a, m.a2, m.b, m.b2, m.y, m.r, tp));
+  VLTK_LAUNCH_CHECK();
+  return 0;
+}
+
 // Two epilogue warpgroups unless VLTK_EPI_GROUPS=1 (A/B switch).
 template <int BN, int STAGES, bool HAS_RES, bool OUT_F32, bool POOL = false>
 int launch2(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
@@ -822,6 +1175,15 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const TcParams& tp, int c
 }
 
 }  // namespace
+
+// cta_group::2 dispatch knobs: environment defaults, overridable at run time (vltk_conv_tc_set_cta_pairs)
+std::atomic<int> g_cta2_min_m{[] { const char* e = getenv("VLTK_CTA2"); return e ? atoi(e) : 32768; }()};
+std::atomic<int> g_cta2_res{[] { const char* e = getenv("VLTK_CTA2_RES"); return (e && e[0] == '1') ? 1 : 0; }()};
+
+void conv_tc_set_cta_pairs(int min_pixels, int residual_layers) {
+  if (min_pixels >= 0) g_cta2_min_m.store(min_pixels);
+  if (residual_layers >= 0) g_cta2_res.store(residual_layers ? 1 : 0);
+}
 
 size_t conv_tc_pool_partial_bytes(int64_t M, int cout) { return ((size_t)(M / (BM + 1)) + 1) * 2 * cout * sizeof(float); }   // 2 tiles per ROI, rows > BM
 
@@ -925,17 +1287,35 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
       t2.npass = 2; t2.pass_a[1] = 1; t2.pass_b[1] = 1;
       t2.pass_cblocks[1] = concat->Cin2 / BK; t2.pass_stride[1] = concat->stride2;
     }
+    // CTA pairs (cta_group::2, conv_tc3_kernel) for the BN = 256 bf16-out layers with at least VLTK_CTA2 output pixels
+    // (default 32768; 0 = never): +5 % on the whole step (profiles/r01_summary.md §27).  The residual / pooled layers
+    // stay on v2 unless VLTK_CTA2_RES=1: measured 3 % slower on pairs (K = 512 leaves 8 k-blocks per tile, and the
+    // accumulator hand-off then waits for the slower of TWO residual streams; §27).
+    const int cta2 = g_cta2_min_m.load(std::memory_order_relaxed);
+    const bool cta2_res = g_cta2_res.load(std::memory_order_relaxed) != 0;
+    const bool pooled = pool && pool->out;
+    const bool use3 = cta2 > 0 && bn == 256 && !out_f32 && !is_split && !is_wsplit && M >= cta2 &&
+                      (cta2_res || !(p.residual || pooled));
+    Maps m3 = m;
+    if (use3) {                                        // each CTA of the pair loads half of the W tile
+      if (cached(TensorMapCache::Key(w_nk, K, cout_pad, 128, 0, 0, 0, 0, 0, 0, 1), &m3.b,
+                 [&](CUtensorMap* d) { return make_b_map(w_nk, K, cout_pad, 128, d); })) return -1;
+      m3.b2 = m3.b;
+      if (is_concat &&
+          cached(TensorMapCache::Key(concat->w2, concat->Cin2, cout_pad, 128, 0, 0, 0, 0, 0, 0, 1), &m3.b2,
+                 [&](CUtensorMap* d) { return make_b_map(concat->w2, concat->Cin2, cout_pad, 128, d); })) return -1;
+    }
     if (out_f32) {
       if (bn == 256) return launch2<256, 4, false, true>(m, t2, cout_pad, st);
       if (bn == 128) return launch2<128, 4, false, true>(m, t2, cout_pad, st);
       return launch2<64, 4, false, true>(m, t2, cout_pad, st);
     }
-    if (pool && pool->out) {
+    if (pooled) {
       VLTK_CHECK(p.residual && bn == 256 && !out_f32 && !is_split, "conv_tc: the pooled epilogue is built for the res5 conv3 shape (residual, Cout %% 256 == 0, K > 256)");
       VLTK_CHECK(pool->rows > BM && pool->rows <= 2 * BM && M % pool->rows == 0 && p.Cout % 4 == 0,
                  "conv_tc: pool_rows=%d must be in (%d, %d] and divide M", pool->rows, BM, 2 * BM);
       t2.pool_partial = pool->partial; t2.pool_rows = pool->rows;
-      if (launch2<256, 3, true, false, true>(m, t2, cout_pad, st)) return -1;
+      if (use3 ? launch3<4, true, true>(m3, t2, cout_pad, st) : launch2<256, 3, true, false, true>(m, t2, cout_pad, st)) return -1;
       const int rois = (int)(M / pool->rows);
       const int64_t tot = (int64_t)rois * (p.Cout / 4);
       pool_finish_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(pool->partial, pool->out, rois, pool->rows, p.Cout);
@@ -943,10 +1323,12 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
       return 0;
     }
     if (p.residual) {
+      if (use3) return launch3<4, true, false>(m3, t2, cout_pad, st);
       if (bn == 256) return launch2<256, 3, true, false>(m, t2, cout_pad, st);
       if (bn == 128) return launch2<128, 3, true, false>(m, t2, cout_pad, st);
       return launch2<64, 4, true, false>(m, t2, cout_pad, st);
     }
+    if (use3) return launch3<6, false, false>(m3, t2, cout_pad, st);
     static const bool probe3 = [] { const char* e = getenv("VLTK_PROBE_STAGES3"); return e && e[0] == '1'; }();
     if (bn == 256 && probe3) return launch2<256, 3, false, false>(m, t2, cout_pad, st);   // diagnosis knob: 3 instead of 4 stages
     if (bn == 256) return launch2<256, 4, false, false>(m, t2, cout_pad, st);

@@ -53,6 +53,10 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
                    cudaStream_t st, const TcSplit* split = nullptr, const TcPool* pool = nullptr,
                    const TcConcat* concat = nullptr);
 
+// CTA-pair (tcgen05 cta_group::2) dispatch: layers with BN = 256, bf16 output and at least `min_pixels` output pixels
+// run on conv_tc3_kernel (0 = never); `residual_layers` = 0 keeps residual / pooled layers on v2.  Negative = unchanged.
+void conv_tc_set_cta_pairs(int min_pixels, int residual_layers);
+
 // ---- pack.cu: reference-layout weights [cout][cin][taps] (DEVICE f32) -> kernel layouts
 int pack_weight_kn(const float* w, float* w_kn, int cout, int cin, int taps, int ldw, bool round_bf16,
                    cudaStream_t st);

@@ -91,6 +91,13 @@ def conv2d_dual_nhwc(x, weight, x2, weight2, shift=None, stride2=1, relu=True):
     return y
 
 
+def set_cta_pairs(min_pixels=-1, residual_layers=-1):
+    """Process-wide kernel selection for the tcgen05 convolutions (include/vltk_frcnn.h,
+    vltk_conv_tc_set_cta_pairs): layers with >= `min_pixels` output pixels run on CTA pairs (0 = never);
+    `residual_layers`=0 keeps shortcut / fused-mean layers on the single-CTA kernel.  -1 = unchanged."""
+    _lib.lib().vltk_conv_tc_set_cta_pairs(int(min_pixels), int(residual_layers))
+
+
 def linear_tc3(x, weight, bias=None, relu=False):
     """F.linear(x, weight, bias) on the tensor pipe with split-bf16 (hi*hi + lo*hi + hi*lo) operands
     and fp32 accumulate/output — how the predictor linears (frcnn.py:1729-1737) run in bf16 mode."""
