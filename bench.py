@@ -353,7 +353,7 @@ def main():
         achieved = d_fl / (d_ms / 1e3) / 1e12 if d_ms else 0.0
         peak = pk["bf16_tflops_sustained"] if "bf16_tflops_sustained" in pk else pk["bf16_tflops"]
         traffic, traffic_note = None, None
-        ncu_json = os.path.join(ROOT, "profiles", "r01_conv_tc2_traffic_v13.json")
+        ncu_json = os.path.join(ROOT, "profiles", "r01_conv_tc_traffic_v16.json")
         if dom == "tcgen05" and os.path.exists(ncu_json):  # dram bytes/launch from the committed ncu --set full capture
             nj = json.load(open(ncu_json))
             traffic = nj["traffic_bytes_per_launch"]
@@ -378,7 +378,7 @@ def main():
                     "sync_api": "FRCNN.forward(host pinned f32, padding='max_detections', return_tensors='np'), one call per step"},
             "e2e_jpeg": jpeg_info,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "conv_tc2_kernel (tcgen05/TMEM implicit GEMM, TMA im2col)" if dom == "tcgen05" else "conv_simt_kernel",
+            "roofline": {"bound": "tensor", "kernel": "conv_tc3_kernel (CTA pairs, tcgen05 cta_group::2) + conv_tc2_kernel: tcgen05/TMEM implicit GEMM, TMA im2col" if dom == "tcgen05" else "conv_simt_kernel",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                          "traffic": traffic, "traffic_source": traffic_note, "peak_source": pk_src + (", sustained bf16" if "bf16_tflops_sustained" in pk else ""),
                          "timing": "CUDA events around every launch on its own stream; busy time = union of the launch intervals (res2-res4 run as two image halves on two streams, overlapped time counted once)",
