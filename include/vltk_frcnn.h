@@ -151,10 +151,19 @@ int vltk_conv2d_dual_nhwc(const void* x, const float* weight, const void* x2, co
 /* Kernel selection for the tcgen05 convolutions (process-wide; A/B measurements and the kernel-equivalence tests).
  * Layers with a 256-wide cout tile, bf16 output and at least `min_pixels` output pixels run on CTA pairs
  * (tcgen05 cta_group::2: two SMs share one W tile); 0 = never.  `residual_layers` = 0 keeps the layers with a
- * shortcut / fused-mean epilogue on the single-CTA kernel.  A negative argument leaves that setting unchanged.
+ * shortcut / fused-mean epilogue on the single-CTA kernel; 1 runs them on pairs (4 operand stages + 4-slab shortcut
+ * ring); 2 runs the shortcut layers on pairs with 3 stages + a 6-slab ring.  A negative argument leaves that setting
+ * unchanged.
  * Defaults: 32768 and 0 (environment: VLTK_CTA2, VLTK_CTA2_RES).  Both kernels accumulate in the same order and
  * produce bit-identical outputs.  Always returns 0. */
 int vltk_conv_tc_set_cta_pairs(int min_pixels, int residual_layers);
+
+/* Pipeline trace of the single-CTA tcgen05 kernel (diagnosis only; tools/tc_trace.py).  In a library built with
+ * VLTK_TRACE=1 csrc/build.sh, the following conv launches make CTA `cta` append (tag, clock64) records per role
+ * (0 TMA producer, 1 MMA issuer, 2 residual producer, 3/4 the two epilogue groups) to dev_buf, a DEVICE array of
+ * 5 * cap_per_role * 2 int64; dev_buf = NULL switches tracing off.  The shipped library has the hooks compiled out and
+ * returns -1 (vltk_frcnn_last_error says so). */
+int vltk_conv_tc_set_trace(void* dev_buf, int cap_per_role, int cta);
 
 /* nn.Linear on the tensor pipe with fp32-faithful arithmetic (frcnn.py:1729-1737 in bf16 mode):
  * y[m,n] = act(x[m,k] . weight[n,k]^T + bias), all DEVICE f32; operands are split into bf16

@@ -148,9 +148,11 @@ def test_cta_pair_kernel_is_bit_identical_to_single_cta_kernel(dev, case):
         stages.set_cta_pairs(1, 1)
         y3 = stages.conv2d_nhwc(x, wt, sc, sh, res, 1, pad, dil, True, mode="bf16", tensor_cores=True)
         y3b = stages.conv2d_nhwc(x, wt, sc, sh, res, 1, pad, dil, True, mode="bf16", tensor_cores=True)
+        stages.set_cta_pairs(1, 2)         # shortcut layers: 3 operand stages + a 6-slab ring instead of 4 + 4
+        y3c = stages.conv2d_nhwc(x, wt, sc, sh, res, 1, pad, dil, True, mode="bf16", tensor_cores=True)
     finally:
         stages.set_cta_pairs(CTA_PAIRS_DEFAULT, 0)
-    assert torch.equal(y3, y2) and torch.equal(y3b, y3)
+    assert torch.equal(y3, y2) and torch.equal(y3b, y3) and torch.equal(y3c, y2)
     ref = _ref_conv(x, wt, sc, sh, res, 1, pad, dil, True)
     assert ((y3.float().cpu().double() - ref.double()).abs() <= 2.0 ** -7 * (ref.double().abs() + 1e-2)).all()
 

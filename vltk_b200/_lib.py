@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvltk_frcnn.so")
+# VLTK_LIB selects another in-tree build of the same sources (the -DVLTK_TC_TRACE diagnosis build); never a fallback
+LIB_PATH = os.path.join(_HERE, os.environ.get("VLTK_LIB", "libvltk_frcnn.so"))
 
 MODE_FP32 = 0
 MODE_BF16 = 1
@@ -77,6 +78,7 @@ SYMBOLS = {
     "vltk_conv2d_nhwc": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 13 + [C.c_void_p]),
     "vltk_conv2d_dual_nhwc": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 10 + [C.c_void_p]),
     "vltk_conv_tc_set_cta_pairs": (C.c_int, [C.c_int, C.c_int]),
+    "vltk_conv_tc_set_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "vltk_conv2d_meanpool_nhwc": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 11 + [C.c_void_p]),
     "vltk_linear_tc3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_void_p]),

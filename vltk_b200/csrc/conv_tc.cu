@@ -350,7 +350,28 @@ struct TcParams2 {
   // sums of its valid rows to pool_partial[mt * Cout + c]; pool_finish() adds an ROI's two partials and divides.
   float* pool_partial;
   int pool_rows;
+  // pipeline trace (diagnosis builds only, -DVLTK_TC_TRACE): per-role (tag, clock64) records of CTA `trace_cta`
+  long long* trace;
+  int trace_cap, trace_cta;
 };
+
+// Pipeline trace of one CTA (tools/tc_trace.py): role r appends (tag, clock64) pairs to trace[r * cap ...].  Compiled out
+// of the shipped library.  tag = event << 40 | tile iteration << 16 | index (k-block / slab).
+#ifdef VLTK_TC_TRACE
+#define TC_TRACE_DECL(role) int tr_n = 0; const bool tr_on = p.trace && (int)blockIdx.x == p.trace_cta; const int tr_role = (role);
+#define TC_TRACE(ev, it, idx)                                                                                      \
+  do {                                                                                                             \
+    if (tr_on && tr_n < p.trace_cap) {                                                                             \
+      long long* tq = p.trace + ((size_t)tr_role * p.trace_cap + tr_n) * 2;                                        \
+      tq[0] = ((long long)(ev) << 40) | ((long long)(it) << 16) | (long long)(idx);                                \
+      tq[1] = clock64();                                                                                           \
+      ++tr_n;                                                                                                      \
+    }                                                                                                              \
+  } while (0)
+#else
+#define TC_TRACE_DECL(role)
+#define TC_TRACE(ev, it, idx) do {} while (0)
+#endif
 
 template <int BN, int STAGES, bool HAS_RES, int EG = 1>
 struct Smem2 {
@@ -442,6 +463,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     // ================= TMA producer =================
     int stage = 0; uint32_t phase = 0;
+    TC_TRACE_DECL(0)
+    int tr_kb = 0; (void)tr_kb;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       const int n0 = (t % p.n_tiles) * BN;
       const int mt = t / p.n_tiles;
@@ -458,6 +481,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int kh = tap / p.KW, kw = tap - kh * p.KW;
           for (int cb = 0; cb < cblocks; ++cb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
+            TC_TRACE(1, 0, tr_kb++);
             mbar_expect_tx(full_bar(stage), S::STAGE_BYTES);
             tma_load_im2col_4d(sA + stage * A_STAGE_BYTES, ma, full_bar(stage), cb * BK, bw, bh, img0,
                                (uint16_t)(kw * p.dil), (uint16_t)(kh * p.dil));
@@ -472,14 +496,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr uint32_t idesc = make_idesc(BM, BN);
     int stage = 0; uint32_t phase = 0;
     int it = 0;
+    TC_TRACE_DECL(1)
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1) & 1u;
+      TC_TRACE(0, it, 0);
       mbar_wait(tempty_bar(acc), use ^ 1u);   // epilogue has drained this accumulator
+      TC_TRACE(1, it, 0);
       tc_fence_after();
       const uint32_t d = tmem_base + (uint32_t)(acc * BN);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(stage), phase);
+        TC_TRACE(2, it, kb);
         tc_fence_after();
         const uint32_t a = sA + stage * A_STAGE_BYTES, b = sB + stage * S::B_STAGE_BYTES;
 #pragma unroll
@@ -490,16 +518,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       umma_commit(tfull_bar(acc));
+      TC_TRACE(3, it, 0);
     }
   } else if (HAS_RES && warp == 3 && lane == 0) {
     // ================= residual producer =================
     int slot = 0; uint32_t phase = 0;
+    TC_TRACE_DECL(2)
+    int tr_c = 0; (void)tr_c;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       const int n0 = (t % p.n_tiles) * BN;
       const int mt = t / p.n_tiles;
       const int m0 = POOL ? (mt >> 1) * p.pool_rows + (mt & 1) * BM : mt * BM;
       for (int s = 0; s < NSLAB; ++s) {
         mbar_wait(rempty_bar(slot), phase ^ 1u);
+        TC_TRACE(1, 0, tr_c++);
         mbar_expect_tx(rfull_bar(slot), SLAB_BYTES);
         tma_load_2d(sRes + slot * SLAB_BYTES, &tmR, rfull_bar(slot), n0 + s * SLAB, m0);
         if (++slot == RS) { slot = 0; phase ^= 1u; }
@@ -518,6 +550,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     float* s_shift = s_scale + S::GSC;
     auto group_barrier = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
     int obuf = 0, it = 0;
+#ifdef VLTK_TC_TRACE
+    int tr_n = 0; const bool tr_on = p.trace && (int)blockIdx.x == p.trace_cta && issuer; const int tr_role = 3 + g;
+#endif
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int n0 = (t % p.n_tiles) * BN;
       const int mt = t / p.n_tiles;
@@ -537,7 +572,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           s_shift[i] = p.shift ? p.shift[col] : 0.f;
         }
       }
+      TC_TRACE(0, it, 0);
       mbar_wait(tfull_bar(acc), use);
+      TC_TRACE(1, it, 0);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
@@ -558,6 +595,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) { v[jj] = lo[jj]; v[32 + jj] = hi[jj]; }
         }
+        TC_TRACE(2, it, s);
         if (s + EG >= NSLAB) {                // my last slab of this accumulator: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -580,8 +618,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_wait(rfull_bar(slot), rphase);
           if (EG == 2 && issuer) seen[g] = c;
         }
+        TC_TRACE(3, it, s);
         if (!POOL && issuer) bulk_wait_read<NBUF - 1>();   // the store that last read sOutG[obuf] has drained it
+        TC_TRACE(4, it, s);
         group_barrier();                      // sOutG[obuf] reusable (POOL: last slab's column readers done); scale/shift visible
+        TC_TRACE(5, it, s);
         const uint32_t orow = sOutG + obuf * SLAB_BYTES + (uint32_t)row * 128u;
         const uint32_t rrow = sRes + slot * SLAB_BYTES + (uint32_t)row * 128u;
         float pv[POOL ? 64 : 1];              // POOL: this row's 64 fp32 epilogue values of the slab (then its column sums)
@@ -635,6 +676,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
         }
+        TC_TRACE(6, it, s);
         if (HAS_RES) {                        // this warp is done with the residual slab
           __syncwarp();
           if (lane == 0) mbar_arrive(rempty_bar(slot));
@@ -667,6 +709,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             tma_store_2d(&tmY, sOutG + obuf * SLAB_BYTES, n0 + s * SLABC, m0);
             bulk_commit();
           }
+          TC_TRACE(7, it, s);
           if (NBUF > 1) obuf ^= 1;
         }
       }
@@ -694,9 +737,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // parity waits are sound.  POOL is v2's ROI-aligned fused 14x14 mean: the pair covers one ROI (rank 0 rows [0,128),
 // rank 1 rows [128, pool_rows)), so tile numbering and the partial-sum layout are identical to v2's.
 constexpr int B3_STAGE_BYTES = 128 * BK * 2;   // half a 256-cout W tile
-template <int STAGES, bool HAS_RES>
+template <int STAGES, bool HAS_RES, int RING = 4>
 struct Smem3 {
-  static constexpr int RS = HAS_RES ? 4 : 0;
+  static constexpr int RS = HAS_RES ? RING : 0;     // residual ring slots (half of them private to each epilogue group)
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B3_STAGE_BYTES;   // 32 KB
   static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
   static constexpr int OFF_OUT = STAGES * STAGE_BYTES;
@@ -715,20 +758,21 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;        // shared::cluster address of the same offset in CTA rank 0
 constexpr uint64_t TMA_DESC_DEFAULT = 0x1000000000000000ull;
-__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                             uint64_t hint = TMA_DESC_DEFAULT) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
       " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "l"(TMA_DESC_DEFAULT)
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
 __device__ __forceinline__ void tma2_load_im2col_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c, int w, int h,
-                                                    int n, uint16_t off_w, uint16_t off_h) {
+                                                    int n, uint16_t off_w, uint16_t off_h, uint64_t hint = TMA_DESC_DEFAULT) {
   asm volatile(
       "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
       " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & PEER_BIT_MASK), "r"(c), "r"(w), "r"(h), "r"(n),
-        "h"(off_w), "h"(off_h), "l"(TMA_DESC_DEFAULT)
+        "h"(off_w), "h"(off_h), "l"(hint)
       : "memory");
 }
 __device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -747,14 +791,15 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {       // arri
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
 }
 
-template <int STAGES, bool HAS_RES, bool POOL>
+template <int STAGES, bool HAS_RES, bool POOL, int RING = 4>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2,
                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, TcParams2 p) {
-  using S = Smem3<STAGES, HAS_RES>;
+  using S = Smem3<STAGES, HAS_RES, RING>;
   static_assert(!POOL || HAS_RES, "the pooled epilogue is the res5 conv3 tail (has a shortcut)");
-  constexpr int BN = 256, NSLAB = BN / SLAB, EG = 2, RS = S::RS;
+  static_assert(RING % 2 == 0, "each epilogue group owns half of the ring");
+  constexpr int BN = 256, NSLAB = BN / SLAB, EG = 2, RS = S::RS, GRS = RING / 2;
   extern __shared__ __align__(1024) unsigned char smem_dyn3[];
   const uint32_t base = smem_u32(smem_dyn3);
   if (base & 1023u) { if (threadIdx.x == 0) printf("conv_tc3: dynamic smem base %u is not 1024 B aligned\n", base); __trap(); }
@@ -861,14 +906,15 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       umma2_commit_mc(tfull_bar(acc));
     }
   } else if (HAS_RES && warp == 3 && lane == 0) {
-    // ================= residual producer (CTA-local ring; slab s of a tile -> slot (s % 2) * 2 + s / 2) =================
+    // ================= residual producer (CTA-local ring; group g = s % 2 owns slots [g * GRS, (g + 1) * GRS)) =================
     int it = 0;
     for (int t = pair; t < num_pair_tiles; t += npairs, ++it) {
       const int n0 = (t % p.n_tiles) * BN;
       const int m0 = (int)tile_m0(t);
-      const uint32_t rphase = (uint32_t)it & 1u;
       for (int s = 0; s < NSLAB; ++s) {
-        const int slot = (s & 1) * 2 + (s >> 1);
+        const int cg = it * 2 + (s >> 1);              // this slab's index in its group's sequence
+        const int slot = (s & 1) * GRS + cg % GRS;
+        const uint32_t rphase = (uint32_t)(cg / GRS) & 1u;
         mbar_wait(rempty_bar(slot), rphase ^ 1u);
         mbar_expect_tx(rfull_bar(slot), SLAB_BYTES);
         tma_load_2d(sRes + slot * SLAB_BYTES, &tmR, rfull_bar(slot), n0 + s * SLAB, m0);
@@ -903,8 +949,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t tacc = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int s = g, j = 0; s < NSLAB; s += EG, ++j) {
-        const int slot = g * 2 + j;
-        (void)slot;
+        const int cg = it * 2 + j;
+        const int slot = g * GRS + cg % GRS;
+        const uint32_t rphase = (uint32_t)(cg / GRS) & 1u;
+        (void)slot; (void)rphase;
         uint32_t v[64];
         {
           uint32_t lo[32], hi[32];
@@ -919,7 +967,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
           if (lane == 0) { if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_leader(tempty_bar(acc)); }
         }
-        if (HAS_RES) mbar_wait(rfull_bar(slot), (uint32_t)it & 1u);
+        if (HAS_RES) mbar_wait(rfull_bar(slot), rphase);
         if (!POOL && issuer) bulk_wait_read<0>();      // the store that last read sOutG has drained it
         group_barrier();                               // sOutG reusable (POOL: last slab's column readers done); scale/shift visible
         const uint32_t orow = sOutG + (uint32_t)row * 128u;
@@ -1128,12 +1176,12 @@ int launch2e(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
   return 0;
 }
 
-template <int STAGES, bool HAS_RES, bool POOL>
+template <int STAGES, bool HAS_RES, bool POOL, int RING = 4>
 int launch3(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
-  using S = Smem3<STAGES, HAS_RES>;
+  using S = Smem3<STAGES, HAS_RES, RING>;
   static DeviceOnce once;
   if (once.first()) {
-    VLTK_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<STAGES, HAS_RES, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    VLTK_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<STAGES, HAS_RES, POOL, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   }
   tp.n_tiles = cout_pad / 256;
   const int64_t pair_tiles = (POOL ? tp.M / tp.pool_rows : ceil_div64(ceil_div64(tp.M, BM), 2)) * tp.n_tiles;
@@ -1148,7 +1196,7 @@ int launch3(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
-  VLTK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc3_kernel<STAGES, HAS_RES, POOL>, m.a, m.a2, m.b, m.b2, m.y, m.r, tp));
+  VLTK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc3_kernel<STAGES, HAS_RES, POOL, RING>, m.a, m.a2, m.b, m.b2, m.y, m.r, tp));
   VLTK_LAUNCH_CHECK();
   return 0;
 }
@@ -1178,11 +1226,25 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const TcParams& tp, int c
 
 // cta_group::2 dispatch knobs: environment defaults, overridable at run time (vltk_conv_tc_set_cta_pairs)
 std::atomic<int> g_cta2_min_m{[] { const char* e = getenv("VLTK_CTA2"); return e ? atoi(e) : 32768; }()};
-std::atomic<int> g_cta2_res{[] { const char* e = getenv("VLTK_CTA2_RES"); return (e && e[0] == '1') ? 1 : 0; }()};
+std::atomic<int> g_cta2_res{[] { const char* e = getenv("VLTK_CTA2_RES"); return e ? atoi(e) : 0; }()};
+
+std::atomic<long long*> g_trace_buf{nullptr};
+std::atomic<int> g_trace_cap{0}, g_trace_cta{0};
+
+int conv_tc_set_trace(void* dev_buf, int cap_per_role, int cta) {
+#ifdef VLTK_TC_TRACE
+  g_trace_buf.store((long long*)dev_buf); g_trace_cap.store(cap_per_role); g_trace_cta.store(cta);
+  return 0;
+#else
+  (void)dev_buf; (void)cap_per_role; (void)cta;
+  VLTK_CHECK(false, "conv_tc: this library was built without -DVLTK_TC_TRACE (VLTK_TRACE=1 csrc/build.sh)");
+  return -1;
+#endif
+}
 
 void conv_tc_set_cta_pairs(int min_pixels, int residual_layers) {
   if (min_pixels >= 0) g_cta2_min_m.store(min_pixels);
-  if (residual_layers >= 0) g_cta2_res.store(residual_layers ? 1 : 0);
+  if (residual_layers >= 0) g_cta2_res.store(residual_layers);
 }
 
 size_t conv_tc_pool_partial_bytes(int64_t M, int cout) { return ((size_t)(M / (BM + 1)) + 1) * 2 * cout * sizeof(float); }   // 2 tiles per ROI, rows > BM
@@ -1276,6 +1338,8 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
     t2.OH = p.OH; t2.OW = p.OW; t2.stride = p.stride; t2.pad = p.pad; t2.dil = p.dil; t2.KW = p.KW;
     t2.taps = p.KH * p.KW; t2.cblocks = p.Cin / BK; t2.n_tiles = 0; t2.num_tiles = 0;
     t2.pool_partial = nullptr; t2.pool_rows = 1;
+    t2.trace = g_trace_buf.load(std::memory_order_relaxed); t2.trace_cap = g_trace_cap.load(std::memory_order_relaxed);
+    t2.trace_cta = g_trace_cta.load(std::memory_order_relaxed);
     // (an L2 prefetch of the residual tensor was tried and measured slower: the residual layers are DRAM-bandwidth-
     // bound, not latency-bound — profiles/r01_summary.md §19)
     t2.npass = is_split ? 3 : 1;                       // hi*hi, lo*hi, hi*lo
@@ -1292,7 +1356,7 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
     // stay on v2 unless VLTK_CTA2_RES=1: measured 3 % slower on pairs (K = 512 leaves 8 k-blocks per tile, and the
     // accumulator hand-off then waits for the slower of TWO residual streams; §27).
     const int cta2 = g_cta2_min_m.load(std::memory_order_relaxed);
-    const bool cta2_res = g_cta2_res.load(std::memory_order_relaxed) != 0;
+    const int cta2_res = g_cta2_res.load(std::memory_order_relaxed);   // 0: residual layers on v2; 1: pairs, 4 stages + 4-slab ring; 2: 3 + 6
     const bool pooled = pool && pool->out;
     const bool use3 = cta2 > 0 && bn == 256 && !out_f32 && !is_split && !is_wsplit && M >= cta2 &&
                       (cta2_res || !(p.residual || pooled));
@@ -1315,7 +1379,7 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
       VLTK_CHECK(pool->rows > BM && pool->rows <= 2 * BM && M % pool->rows == 0 && p.Cout % 4 == 0,
                  "conv_tc: pool_rows=%d must be in (%d, %d] and divide M", pool->rows, BM, 2 * BM);
       t2.pool_partial = pool->partial; t2.pool_rows = pool->rows;
-      if (use3 ? launch3<4, true, true>(m3, t2, cout_pad, st) : launch2<256, 3, true, false, true>(m, t2, cout_pad, st)) return -1;
+      if ((use3 && cta2_res == 1) ? launch3<4, true, true>(m3, t2, cout_pad, st) : launch2<256, 3, true, false, true>(m, t2, cout_pad, st)) return -1;
       const int rois = (int)(M / pool->rows);
       const int64_t tot = (int64_t)rois * (p.Cout / 4);
       pool_finish_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(pool->partial, pool->out, rois, pool->rows, p.Cout);
@@ -1323,7 +1387,7 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
       return 0;
     }
     if (p.residual) {
-      if (use3) return launch3<4, true, false>(m3, t2, cout_pad, st);
+      if (use3) return cta2_res == 2 ? launch3<3, true, false, 6>(m3, t2, cout_pad, st) : launch3<4, true, false>(m3, t2, cout_pad, st);
       if (bn == 256) return launch2<256, 3, true, false>(m, t2, cout_pad, st);
       if (bn == 128) return launch2<128, 3, true, false>(m, t2, cout_pad, st);
       return launch2<64, 4, true, false>(m, t2, cout_pad, st);

@@ -57,6 +57,10 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
 // run on conv_tc3_kernel (0 = never); `residual_layers` = 0 keeps residual / pooled layers on v2.  Negative = unchanged.
 void conv_tc_set_cta_pairs(int min_pixels, int residual_layers);
 
+// Diagnosis builds (-DVLTK_TC_TRACE): the next conv_tc2 launches record CTA `cta`'s pipeline events into dev_buf
+// (5 roles x cap_per_role x 2 int64).  dev_buf = nullptr switches it off.  Returns -1 in a library built without tracing.
+int conv_tc_set_trace(void* dev_buf, int cap_per_role, int cta);
+
 // ---- pack.cu: reference-layout weights [cout][cin][taps] (DEVICE f32) -> kernel layouts
 int pack_weight_kn(const float* w, float* w_kn, int cout, int cin, int taps, int ldw, bool round_bf16,
                    cudaStream_t st);

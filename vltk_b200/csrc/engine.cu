@@ -1088,6 +1088,8 @@ int vltk_conv2d_dual_nhwc(const void* x, const float* weight, const void* x2, co
   return rc;
 }
 
+int vltk_conv_tc_set_trace(void* dev_buf, int cap_per_role, int cta) { return conv_tc_set_trace(dev_buf, cap_per_role, cta); }
+
 int vltk_conv_tc_set_cta_pairs(int min_pixels, int residual_layers) {
   conv_tc_set_cta_pairs(min_pixels, residual_layers);
   return 0;
