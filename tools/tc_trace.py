@@ -14,17 +14,23 @@ from vltk_b200 import stages, _lib
 ROLES = ["tma_producer", "mma_issuer", "res_producer", "epilogue_g0", "epilogue_g1"]
 EV = {
     0: {1: "empty slot acquired"},
-    1: {0: "tile start", 1: "accumulator acquired (tempty)", 2: "operands landed (full)", 3: "tile committed"},
+    1: {0: "tile start", 1: "accumulator acquired (tempty)", 2: "operands landed (full)", 3: "tile committed",
+        4: "kernel entry", 5: "set-up done + predecessor complete"},
     2: {1: "ring slot acquired (rempty)"},
     3: {0: "tile start", 1: "accumulator ready (tfull)", 2: "tcgen05.ld done", 3: "residual landed", 4: "staging drained (bulk wait)",
-        5: "barrier 1", 6: "slab computed + written", 7: "barrier 2 + store issued"},
+        5: "barrier 1", 6: "slab computed + written", 7: "barrier 2 + store issued", 8: "all stores complete"},
 }
 EV[4] = EV[3]
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--rois", type=int, default=2400)
+    ap.add_argument("--rois", type=int, default=2400, help="images / ROIs (N of the NHWC input)")
+    ap.add_argument("--h", type=int, default=14)
+    ap.add_argument("--w", type=int, default=14)
+    ap.add_argument("--pad", type=int, default=-1)
+    ap.add_argument("--dil", type=int, default=-1)
+    ap.add_argument("--timeline", type=int, default=0, help="print the first N raw records of every role")
     ap.add_argument("--cin", type=int, default=512)
     ap.add_argument("--cout", type=int, default=2048)
     ap.add_argument("--k", type=int, default=1)
@@ -35,12 +41,12 @@ def main():
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
-    x = torch.randn(a.rois, 14, 14, a.cin, device=dev).bfloat16()
+    x = torch.randn(a.rois, a.h, a.w, a.cin, device=dev).bfloat16()
     wt = torch.randn(a.cout, a.cin, a.k, a.k, device=dev) * (2.0 / (a.cin * a.k * a.k)) ** 0.5
     sc = torch.ones(a.cout, device=dev); sh = torch.zeros(a.cout, device=dev)
-    res = torch.randn(a.rois, 14, 14, a.cout, device=dev).bfloat16() if a.res else None
-    pad = dil = 0 if a.k == 1 else 2
-    dil = max(dil, 1)
+    res = torch.randn(a.rois, a.h, a.w, a.cout, device=dev).bfloat16() if a.res else None
+    pad = a.pad if a.pad >= 0 else (0 if a.k == 1 else 2)
+    dil = a.dil if a.dil >= 0 else (1 if a.k == 1 else 2)
     stages.set_cta_pairs(0, 0)
     buf = torch.zeros(5 * a.cap * 2, dtype=torch.int64, device=dev)
     L = _lib.lib()
@@ -51,6 +57,15 @@ def main():
         L.vltk_conv_tc_set_trace(None, 0, 0)
     t = buf.cpu().reshape(5, a.cap, 2).numpy()
     summary = {}
+    allclk = [int(c) for r in range(5) for _, c in t[r] if c]
+    t0 = min(allclk)
+    print(f"CTA {a.cta}: first record .. last record = {max(allclk) - t0} cycles")
+    if a.timeline:
+        for r, name in enumerate(ROLES):
+            recs = [(int(tag) >> 40, (int(tag) >> 16) & 0xFFFFFF, int(tag) & 0xFFFF, int(clk)) for tag, clk in t[r] if clk]
+            print(f"-- {name}")
+            for ev, it, idx, clk in recs[: a.timeline]:
+                print(f"   +{clk - t0:8d}  tile {it:3d} idx {idx:3d}  {EV[r][ev]}")
     for r, name in enumerate(ROLES):
         rec = [(int(tag) >> 40, (int(tag) >> 16) & 0xFFFFFF, int(tag) & 0xFFFF, int(clk)) for tag, clk in t[r] if clk]
         if not rec:

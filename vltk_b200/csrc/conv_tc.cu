@@ -332,11 +332,29 @@ constexpr int SLAB_BYTES = BM * SLAB * 2;      // 16 KB
 // residual ring depth: 3 slabs (48 KB) next to BN=256 operand stages; 5 slabs (80 KB) with the smaller BN=128 stages.
 template <int BN, bool HAS_RES> struct ResRing { static constexpr int DEPTH = (HAS_RES && BN == 128) ? 5 : 3; };
 
+// n / d and n % d for n < 2^31 by multiply + shift (d fixed per launch): the producer and epilogue roles are single dependent
+// instruction streams, and the pipeline trace showed ~1500 cycles of 64-bit div/mod per tile in the TMA producer — as long
+// as a whole 4-k-block tile of the K <= 256 layers.
+struct FastDiv {
+  unsigned long long mul; uint32_t sh, d;
+  __host__ void init(uint32_t d_) {
+    d = d_ ? d_ : 1;
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;
+    sh = 31 + l;
+    mul = (1ull << sh) / d + 1;
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return (uint32_t)(((unsigned long long)n * mul) >> sh); }
+  __device__ __forceinline__ uint32_t mod(uint32_t n) const { return n - div(n) * d; }
+  __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
+};
+
 struct TcParams2 {
   const float* scale; const float* shift;
+  FastDiv fd_ntiles, fd_ow, fd_oh;             // divisors n_tiles, OW, OH
   int64_t M;
   int Cout, relu;
-  int OH, OW, stride, pad, dil, KW, taps, cblocks;
+  int OH, OW, stride, pad, dil, KH, KW, taps, cblocks;
   int n_tiles, num_tiles;                      // cout tiles, total tiles
   // split-precision GEMM: the K loop runs `npass` times; pass i reads A from map pass_a[i] (0: tmA,
   // 1: tmA2) and W from map pass_b[i] (0: tmB, 1: tmB2), all accumulating into the same TMEM tile.
@@ -368,9 +386,21 @@ struct TcParams2 {
       ++tr_n;                                                                                                      \
     }                                                                                                              \
   } while (0)
+#define TC_TRACE_AT(ev, clk)                                                                                        \
+  do {                                                                                                             \
+    if (tr_on && tr_n < p.trace_cap) {                                                                             \
+      long long* tq = p.trace + ((size_t)tr_role * p.trace_cap + tr_n) * 2;                                        \
+      tq[0] = ((long long)(ev) << 40);                                                                             \
+      tq[1] = (clk);                                                                                               \
+      ++tr_n;                                                                                                      \
+    }                                                                                                              \
+  } while (0)
+#define TC_TRACE_ENTRY() const long long tr_entry = clock64();
 #else
 #define TC_TRACE_DECL(role)
 #define TC_TRACE(ev, it, idx) do {} while (0)
+#define TC_TRACE_AT(ev, clk) do {} while (0)
+#define TC_TRACE_ENTRY()
 #endif
 
 template <int BN, int STAGES, bool HAS_RES, int EG = 1>
@@ -395,6 +425,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2,
                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, TcParams2 p) {
   using S = Smem2<BN, STAGES, HAS_RES, EG>;
+  TC_TRACE_ENTRY()
   static_assert(!(HAS_RES && OUT_F32), "fp32 output has no residual path");
   static_assert(!POOL || !OUT_F32, "the pooled epilogue reduces the bf16-path tile");
   static_assert(EG == 1 || EG == 2, "one or two epilogue warpgroups");
@@ -465,28 +496,31 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int stage = 0; uint32_t phase = 0;
     TC_TRACE_DECL(0)
     int tr_kb = 0; (void)tr_kb;
+    const int KH = p.KH;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-      const int n0 = (t % p.n_tiles) * BN;
-      const int mt = t / p.n_tiles;
-      const int64_t m0 = POOL ? (int64_t)(mt >> 1) * p.pool_rows + (mt & 1) * BM : (int64_t)mt * BM;
-      const int ow0 = (int)(m0 % p.OW);
-      const int64_t q = m0 / p.OW;
-      const int oh0 = (int)(q % p.OH), img0 = (int)(q / p.OH);
+      uint32_t mt, nt, q, ow0, img0, oh0;
+      p.fd_ntiles.divmod((uint32_t)t, mt, nt);
+      const int n0 = (int)nt * BN;
+      const uint32_t m0 = POOL ? (mt >> 1) * (uint32_t)p.pool_rows + (mt & 1) * BM : mt * BM;   // M + 256 < 2^31 (host check)
+      p.fd_ow.divmod(m0, q, ow0);
+      p.fd_oh.divmod(q, img0, oh0);
       for (int ps = 0; ps < p.npass; ++ps) {
         const CUtensorMap* ma = p.pass_a[ps] ? &tmA2 : &tmA;
         const CUtensorMap* mb = p.pass_b[ps] ? &tmB2 : &tmB;
         const int cblocks = p.pass_cblocks[ps];
-        const int bw = ow0 * p.pass_stride[ps] - p.pad, bh = oh0 * p.pass_stride[ps] - p.pad;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int kh = tap / p.KW, kw = tap - kh * p.KW;
-          for (int cb = 0; cb < cblocks; ++cb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            TC_TRACE(1, 0, tr_kb++);
-            mbar_expect_tx(full_bar(stage), S::STAGE_BYTES);
-            tma_load_im2col_4d(sA + stage * A_STAGE_BYTES, ma, full_bar(stage), cb * BK, bw, bh, img0,
-                               (uint16_t)(kw * p.dil), (uint16_t)(kh * p.dil));
-            tma_load_2d(sB + stage * S::B_STAGE_BYTES, mb, full_bar(stage), (tap * cblocks + cb) * BK, n0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        const int bw = (int)ow0 * p.pass_stride[ps] - p.pad, bh = (int)oh0 * p.pass_stride[ps] - p.pad;
+        int kcol = 0;                              // (tap * cblocks + cb) * BK
+        for (int kh = 0; kh < KH; ++kh) {
+          for (int kw = 0; kw < p.KW; ++kw) {
+            for (int cb = 0; cb < cblocks; ++cb, kcol += BK) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              TC_TRACE(1, 0, tr_kb++);
+              mbar_expect_tx(full_bar(stage), S::STAGE_BYTES);
+              tma_load_im2col_4d(sA + stage * A_STAGE_BYTES, ma, full_bar(stage), cb * BK, bw, bh, (int)img0,
+                                 (uint16_t)(kw * p.dil), (uint16_t)(kh * p.dil));
+              tma_load_2d(sB + stage * S::B_STAGE_BYTES, mb, full_bar(stage), kcol, n0);
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
           }
         }
       }
@@ -497,6 +531,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int stage = 0; uint32_t phase = 0;
     int it = 0;
     TC_TRACE_DECL(1)
+    TC_TRACE_AT(4, tr_entry);                  // kernel entry
+    TC_TRACE(5, 0, 0);                         // set-up done, predecessor grid complete (griddepcontrol.wait returned)
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1) & 1u;
@@ -526,8 +562,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     TC_TRACE_DECL(2)
     int tr_c = 0; (void)tr_c;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-      const int n0 = (t % p.n_tiles) * BN;
-      const int mt = t / p.n_tiles;
+      uint32_t umt, unt;
+      p.fd_ntiles.divmod((uint32_t)t, umt, unt);
+      const int n0 = (int)unt * BN, mt = (int)umt;
       const int m0 = POOL ? (mt >> 1) * p.pool_rows + (mt & 1) * BM : mt * BM;
       for (int s = 0; s < NSLAB; ++s) {
         mbar_wait(rempty_bar(slot), phase ^ 1u);
@@ -553,23 +590,48 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #ifdef VLTK_TC_TRACE
     int tr_n = 0; const bool tr_on = p.trace && (int)blockIdx.x == p.trace_cta && issuer; const int tr_role = 3 + g;
 #endif
+    // entry i of my scale/shift cache, for the it_-th tile of this CTA (first cout n0_), holds column ss_col(...); -1: unused
+    constexpr bool SS_PREFETCH = S::GSC <= 128;     // one entry per thread
+    auto ss_col = [&](int n0_, int it_, int i) -> int {
+      const int sf = (g - (it_ * NSLAB) % EG + EG) % EG;
+      const int j = i / SLABC, s = sf + j * EG;
+      return s < NSLAB ? n0_ + s * SLABC + (i - j * SLABC) : -1;
+    };
+    float pf_sc = 1.f, pf_sh = 0.f;
+    if (SS_PREFETCH && et < S::GSC && (int)blockIdx.x < p.num_tiles) {
+      const int c = ss_col((int)p.fd_ntiles.mod(blockIdx.x) * BN, 0, et);
+      if (c >= 0) { pf_sc = p.scale ? __ldg(p.scale + c) : 1.f; pf_sh = p.shift ? __ldg(p.shift + c) : 0.f; }
+    }
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-      const int n0 = (t % p.n_tiles) * BN;
-      const int mt = t / p.n_tiles;
+      uint32_t umt, unt;
+      p.fd_ntiles.divmod((uint32_t)t, umt, unt);
+      const int n0 = (int)unt * BN, mt = (int)umt;
       const int m0 = POOL ? (mt >> 1) * p.pool_rows + (mt & 1) * BM : mt * BM;
       (void)m0;
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1) & 1u;
       const int c0 = it * NSLAB;              // global index of this tile's first slab
       const int s_first = (g - c0 % EG + EG) % EG;
+      // my slabs' BN scale/shift -> my smem cache (this group's previous readers are past their last barrier).  The values
+      // were fetched from global memory one tile ago (ss_col / pf_sc / pf_sh above), so their latency, which the pipeline
+      // trace showed as a ~800-cycle bubble per tile in both epilogue groups, is off the tile's critical path.
+      if constexpr (SS_PREFETCH) {
+        if (et < S::GSC) {
+          if (ss_col(n0, it, et) >= 0) { s_scale[et] = pf_sc; s_shift[et] = pf_sh; }
+          const int tn = t + (int)gridDim.x;
+          const int cn = tn < p.num_tiles ? ss_col((int)p.fd_ntiles.mod((uint32_t)tn) * BN, it + 1, et) : -1;
+          if (cn >= 0) { pf_sc = p.scale ? __ldg(p.scale + cn) : 1.f; pf_sh = p.shift ? __ldg(p.shift + cn) : 0.f; }
+        }
+      }
       if (s_first >= NSLAB) continue;         // (NSLAB < EG) this tile belongs to the other group
-      // my slabs' BN scale/shift -> my smem cache (this group's previous readers are past their last barrier)
-      for (int i = et; i < S::GSC; i += 128) {
-        const int j = i / SLABC, s = s_first + j * EG;
-        if (s < NSLAB) {
-          const int col = n0 + s * SLABC + (i - j * SLABC);
-          s_scale[i] = p.scale ? p.scale[col] : 1.f;
-          s_shift[i] = p.shift ? p.shift[col] : 0.f;
+      if constexpr (!SS_PREFETCH) {
+        for (int i = et; i < S::GSC; i += 128) {
+          const int j = i / SLABC, s = s_first + j * EG;
+          if (s < NSLAB) {
+            const int col = n0 + s * SLABC + (i - j * SLABC);
+            s_scale[i] = p.scale ? p.scale[col] : 1.f;
+            s_shift[i] = p.shift ? p.shift[col] : 0.f;
+          }
         }
       }
       TC_TRACE(0, it, 0);
@@ -639,21 +701,34 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                    make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3)));
           }
         } else {
+          // software-pipelined over the eight 16 B chunks: the residual chunks are all loaded first and chunk q+1's
+          // scale / shift before chunk q's arithmetic and store (two warps per SM sub-partition cannot hide an LDS round
+          // trip per chunk on their own: the trace showed 180-250 cycles per chunk)
+          float4 sc0[2], sc1[2], sh0[2], sh1[2];
+          uint4 rr[HAS_RES ? 8 : 1];
+          if (HAS_RES) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) rr[q] = lds128(rrow + (((uint32_t)q ^ swz) << 4));
+          }
+          auto load_chunk = [&](int q, int b) {
+            sc0[b] = *reinterpret_cast<const float4*>(s_scale + j * SLABC + q * 8);
+            sc1[b] = *reinterpret_cast<const float4*>(s_scale + j * SLABC + q * 8 + 4);
+            sh0[b] = *reinterpret_cast<const float4*>(s_shift + j * SLABC + q * 8);
+            sh1[b] = *reinterpret_cast<const float4*>(s_shift + j * SLABC + q * 8 + 4);
+          };
+          load_chunk(0, 0);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {       // 8 bf16 channels = one 16 B chunk, stored at chunk q ^ (row % 8)
+            const int b = q & 1;
+            if (q + 1 < 8) load_chunk(q + 1, b ^ 1);
             const uint32_t coff = ((uint32_t)q ^ swz) << 4;
-            const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + j * SLABC + q * 8);
-            const float4 sc1 = *reinterpret_cast<const float4*>(s_scale + j * SLABC + q * 8 + 4);
-            const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + j * SLABC + q * 8);
-            const float4 sh1 = *reinterpret_cast<const float4*>(s_shift + j * SLABC + q * 8 + 4);
             float f[8];
-            f[0] = fmaf(__uint_as_float(v[q * 8 + 0]), sc0.x, sh0.x); f[1] = fmaf(__uint_as_float(v[q * 8 + 1]), sc0.y, sh0.y);
-            f[2] = fmaf(__uint_as_float(v[q * 8 + 2]), sc0.z, sh0.z); f[3] = fmaf(__uint_as_float(v[q * 8 + 3]), sc0.w, sh0.w);
-            f[4] = fmaf(__uint_as_float(v[q * 8 + 4]), sc1.x, sh1.x); f[5] = fmaf(__uint_as_float(v[q * 8 + 5]), sc1.y, sh1.y);
-            f[6] = fmaf(__uint_as_float(v[q * 8 + 6]), sc1.z, sh1.z); f[7] = fmaf(__uint_as_float(v[q * 8 + 7]), sc1.w, sh1.w);
+            f[0] = fmaf(__uint_as_float(v[q * 8 + 0]), sc0[b].x, sh0[b].x); f[1] = fmaf(__uint_as_float(v[q * 8 + 1]), sc0[b].y, sh0[b].y);
+            f[2] = fmaf(__uint_as_float(v[q * 8 + 2]), sc0[b].z, sh0[b].z); f[3] = fmaf(__uint_as_float(v[q * 8 + 3]), sc0[b].w, sh0[b].w);
+            f[4] = fmaf(__uint_as_float(v[q * 8 + 4]), sc1[b].x, sh1[b].x); f[5] = fmaf(__uint_as_float(v[q * 8 + 5]), sc1[b].y, sh1[b].y);
+            f[6] = fmaf(__uint_as_float(v[q * 8 + 6]), sc1[b].z, sh1[b].z); f[7] = fmaf(__uint_as_float(v[q * 8 + 7]), sc1[b].w, sh1[b].w);
             if (HAS_RES) {
-              uint4 r = lds128(rrow + coff);
-              const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&r);
+              const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rr[q]);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 float2 rf = __bfloat1622float2(rb[j]);
@@ -715,6 +790,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
     if (!POOL && issuer) bulk_wait_all();     // all output bytes are in global memory
+    TC_TRACE(8, it, 0);
   }
   tc_fence_before();
   __syncthreads();
@@ -824,9 +900,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int num_pair_tiles = p.num_tiles;              // (row-tile pairs) x (cout tiles)
   // first output row of this CTA's half of pair tile t (POOL: one ROI per pair, second half starts at row 128 of the ROI)
-  auto tile_m0 = [&](int t) -> int64_t {
-    const int64_t pt = t / p.n_tiles;
-    return POOL ? pt * p.pool_rows + (int64_t)rank * BM : (pt * 2 + rank) * BM;
+  auto tile_m0 = [&](uint32_t pt) -> uint32_t {       // pt = t / n_tiles; M + 256 < 2^31 (host check)
+    return POOL ? pt * (uint32_t)p.pool_rows + rank * BM : (pt * 2 + rank) * BM;
   };
 
   if (warp == 0 && lane == 0) {
@@ -858,26 +933,30 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     // ================= TMA producer (both CTAs: own A rows, own half of W) =================
     int stage = 0; uint32_t phase = 0;
+    const int KH = p.KH;
     for (int t = pair; t < num_pair_tiles; t += npairs) {
-      const int n0 = (t % p.n_tiles) * BN;
-      const int64_t m0 = tile_m0(t);
-      const int ow0 = (int)(m0 % p.OW);
-      const int64_t q = m0 / p.OW;
-      const int oh0 = (int)(q % p.OH), img0 = (int)(q / p.OH);
+      uint32_t pt, nt, q, ow0, img0, oh0;
+      p.fd_ntiles.divmod((uint32_t)t, pt, nt);
+      const int n0 = (int)nt * BN;
+      const uint32_t m0 = tile_m0(pt);
+      p.fd_ow.divmod(m0, q, ow0);
+      p.fd_oh.divmod(q, img0, oh0);
       for (int ps = 0; ps < p.npass; ++ps) {
         const CUtensorMap* ma = p.pass_a[ps] ? &tmA2 : &tmA;
         const CUtensorMap* mb = p.pass_b[ps] ? &tmB2 : &tmB;
         const int cblocks = p.pass_cblocks[ps];
-        const int bw = ow0 * p.pass_stride[ps] - p.pad, bh = oh0 * p.pass_stride[ps] - p.pad;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int kh = tap / p.KW, kw = tap - kh * p.KW;
-          for (int cb = 0; cb < cblocks; ++cb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            if (leader) mbar_expect_tx(full_bar(stage), 2 * S::STAGE_BYTES);   // both CTAs' bytes land on this barrier
-            tma2_load_im2col_4d(sA + stage * A_STAGE_BYTES, ma, full_bar(stage), cb * BK, bw, bh, img0,
-                                (uint16_t)(kw * p.dil), (uint16_t)(kh * p.dil));
-            tma2_load_2d(sB + stage * B3_STAGE_BYTES, mb, full_bar(stage), (tap * cblocks + cb) * BK, n0 + (int)rank * 128);
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        const int bw = (int)ow0 * p.pass_stride[ps] - p.pad, bh = (int)oh0 * p.pass_stride[ps] - p.pad;
+        int kcol = 0;                                  // (tap * cblocks + cb) * BK
+        for (int kh = 0; kh < KH; ++kh) {
+          for (int kw = 0; kw < p.KW; ++kw) {
+            for (int cb = 0; cb < cblocks; ++cb, kcol += BK) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              if (leader) mbar_expect_tx(full_bar(stage), 2 * S::STAGE_BYTES);   // both CTAs' bytes land on this barrier
+              tma2_load_im2col_4d(sA + stage * A_STAGE_BYTES, ma, full_bar(stage), cb * BK, bw, bh, (int)img0,
+                                  (uint16_t)(kw * p.dil), (uint16_t)(kh * p.dil));
+              tma2_load_2d(sB + stage * B3_STAGE_BYTES, mb, full_bar(stage), kcol, n0 + (int)rank * 128);
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
           }
         }
       }
@@ -909,8 +988,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ================= residual producer (CTA-local ring; group g = s % 2 owns slots [g * GRS, (g + 1) * GRS)) =================
     int it = 0;
     for (int t = pair; t < num_pair_tiles; t += npairs, ++it) {
-      const int n0 = (t % p.n_tiles) * BN;
-      const int m0 = (int)tile_m0(t);
+      uint32_t pt, nt;
+      p.fd_ntiles.divmod((uint32_t)t, pt, nt);
+      const int n0 = (int)nt * BN;
+      const int m0 = (int)tile_m0(pt);
       for (int s = 0; s < NSLAB; ++s) {
         const int cg = it * 2 + (s >> 1);              // this slab's index in its group's sequence
         const int slot = (s & 1) * GRS + cg % GRS;
@@ -931,18 +1012,29 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     float* s_scale = s_scale_all + g * 2 * 128;
     float* s_shift = s_scale + 128;
     auto group_barrier = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
+    // entry `et` of my scale/shift cache holds column ss_col(t) of tile t; fetched one tile ahead (as in v2)
+    auto ss_col = [&](int t_) { return (int)p.fd_ntiles.mod((uint32_t)t_) * BN + (g + (et >> 6) * EG) * SLAB + (et & 63); };
+    float pf_sc = 1.f, pf_sh = 0.f;
+    if (pair < num_pair_tiles) {
+      const int c = ss_col(pair);
+      pf_sc = p.scale ? __ldg(p.scale + c) : 1.f; pf_sh = p.shift ? __ldg(p.shift + c) : 0.f;
+    }
     int it = 0;
     for (int t = pair; t < num_pair_tiles; t += npairs, ++it) {
-      const int n0 = (t % p.n_tiles) * BN;
-      const int m0 = (int)tile_m0(t);
+      uint32_t pt, nt;
+      p.fd_ntiles.divmod((uint32_t)t, pt, nt);
+      const int n0 = (int)nt * BN;
+      const int m0 = (int)tile_m0(pt);
       (void)m0;
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1) & 1u;
-      for (int i = et; i < 128; i += 128) {            // my slabs (s = g, g + 2): 2 x 64 columns
-        const int j = i >> 6, s = g + j * EG;
-        const int col = n0 + s * SLAB + (i & 63);
-        s_scale[i] = p.scale ? p.scale[col] : 1.f;
-        s_shift[i] = p.shift ? p.shift[col] : 0.f;
+      {                                                // my slabs (s = g, g + 2): 2 x 64 columns, one entry per thread
+        s_scale[et] = pf_sc; s_shift[et] = pf_sh;
+        const int tn = t + npairs;
+        if (tn < num_pair_tiles) {
+          const int cn = ss_col(tn);
+          pf_sc = p.scale ? __ldg(p.scale + cn) : 1.f; pf_sh = p.shift ? __ldg(p.shift + cn) : 0.f;
+        }
       }
       mbar_wait(tfull_bar(acc), use);
       tc_fence_after();
@@ -975,21 +1067,31 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         (void)rrow;
         float pv[POOL ? 64 : 1];
         (void)pv;
+        float4 sc0[2], sc1[2], sh0[2], sh1[2];         // software-pipelined over the 16 B chunks, as in v2
+        uint4 rr[HAS_RES ? 8 : 1];
+        if (HAS_RES) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) rr[q] = lds128(rrow + (((uint32_t)q ^ swz) << 4));
+        }
+        auto load_chunk = [&](int q, int b) {
+          sc0[b] = *reinterpret_cast<const float4*>(s_scale + j * SLAB + q * 8);
+          sc1[b] = *reinterpret_cast<const float4*>(s_scale + j * SLAB + q * 8 + 4);
+          sh0[b] = *reinterpret_cast<const float4*>(s_shift + j * SLAB + q * 8);
+          sh1[b] = *reinterpret_cast<const float4*>(s_shift + j * SLAB + q * 8 + 4);
+        };
+        load_chunk(0, 0);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
+          const int b = q & 1;
+          if (q + 1 < 8) load_chunk(q + 1, b ^ 1);
           const uint32_t coff = ((uint32_t)q ^ swz) << 4;
-          const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + j * SLAB + q * 8);
-          const float4 sc1 = *reinterpret_cast<const float4*>(s_scale + j * SLAB + q * 8 + 4);
-          const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + j * SLAB + q * 8);
-          const float4 sh1 = *reinterpret_cast<const float4*>(s_shift + j * SLAB + q * 8 + 4);
           float f[8];
-          f[0] = fmaf(__uint_as_float(v[q * 8 + 0]), sc0.x, sh0.x); f[1] = fmaf(__uint_as_float(v[q * 8 + 1]), sc0.y, sh0.y);
-          f[2] = fmaf(__uint_as_float(v[q * 8 + 2]), sc0.z, sh0.z); f[3] = fmaf(__uint_as_float(v[q * 8 + 3]), sc0.w, sh0.w);
-          f[4] = fmaf(__uint_as_float(v[q * 8 + 4]), sc1.x, sh1.x); f[5] = fmaf(__uint_as_float(v[q * 8 + 5]), sc1.y, sh1.y);
-          f[6] = fmaf(__uint_as_float(v[q * 8 + 6]), sc1.z, sh1.z); f[7] = fmaf(__uint_as_float(v[q * 8 + 7]), sc1.w, sh1.w);
+          f[0] = fmaf(__uint_as_float(v[q * 8 + 0]), sc0[b].x, sh0[b].x); f[1] = fmaf(__uint_as_float(v[q * 8 + 1]), sc0[b].y, sh0[b].y);
+          f[2] = fmaf(__uint_as_float(v[q * 8 + 2]), sc0[b].z, sh0[b].z); f[3] = fmaf(__uint_as_float(v[q * 8 + 3]), sc0[b].w, sh0[b].w);
+          f[4] = fmaf(__uint_as_float(v[q * 8 + 4]), sc1[b].x, sh1[b].x); f[5] = fmaf(__uint_as_float(v[q * 8 + 5]), sc1[b].y, sh1[b].y);
+          f[6] = fmaf(__uint_as_float(v[q * 8 + 6]), sc1[b].z, sh1[b].z); f[7] = fmaf(__uint_as_float(v[q * 8 + 7]), sc1[b].w, sh1[b].w);
           if (HAS_RES) {
-            uint4 r = lds128(rrow + coff);
-            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&r);
+            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rr[q]);
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
               float2 rf = __bfloat1622float2(rb[jj]);
@@ -1017,7 +1119,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         if constexpr (POOL) {
           // same reduction tree as v2's POOL epilogue (bit-identical partial sums)
-          const int mt = (t / p.n_tiles) * 2 + (int)rank;
+          const int mt = (int)pt * 2 + (int)rank;
           const int valid = rank ? p.pool_rows - BM : BM;
           float* comb = reinterpret_cast<float*>(gbase + S::OFF_OUT + (size_t)g * SLAB_BYTES) + (j & 1) * 256;
           float2 ts = make_float2(0.f, 0.f);
@@ -1159,6 +1261,7 @@ int launch2e(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
     VLTK_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, STAGES, HAS_RES, OUT_F32, POOL, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   }
   tp.n_tiles = cout_pad / BN;
+  tp.fd_ntiles.init((uint32_t)tp.n_tiles);
   const int64_t tiles = (POOL ? 2 * (tp.M / tp.pool_rows) : ceil_div64(tp.M, BM)) * tp.n_tiles;
   VLTK_CHECK(tiles < (1ll << 31), "conv_tc: too many tiles");
   tp.num_tiles = (int)tiles;
@@ -1184,6 +1287,7 @@ int launch3(const Maps& m, TcParams2 tp, int cout_pad, cudaStream_t st) {
     VLTK_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<STAGES, HAS_RES, POOL, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   }
   tp.n_tiles = cout_pad / 256;
+  tp.fd_ntiles.init((uint32_t)tp.n_tiles);
   const int64_t pair_tiles = (POOL ? tp.M / tp.pool_rows : ceil_div64(ceil_div64(tp.M, BM), 2)) * tp.n_tiles;
   VLTK_CHECK(pair_tiles < (1ll << 31), "conv_tc: too many tiles");
   tp.num_tiles = (int)pair_tiles;
@@ -1335,9 +1439,11 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
     }
     TcParams2 t2;
     t2.scale = p.scale; t2.shift = p.shift; t2.M = M; t2.Cout = p.Cout; t2.relu = p.relu;
-    t2.OH = p.OH; t2.OW = p.OW; t2.stride = p.stride; t2.pad = p.pad; t2.dil = p.dil; t2.KW = p.KW;
+    t2.OH = p.OH; t2.OW = p.OW; t2.stride = p.stride; t2.pad = p.pad; t2.dil = p.dil; t2.KH = p.KH; t2.KW = p.KW;
     t2.taps = p.KH * p.KW; t2.cblocks = p.Cin / BK; t2.n_tiles = 0; t2.num_tiles = 0;
     t2.pool_partial = nullptr; t2.pool_rows = 1;
+    VLTK_CHECK(M < (1ll << 31) - 512, "conv_tc: M=%lld output pixels exceed the 32-bit tile arithmetic", (long long)M);
+    t2.fd_ow.init((uint32_t)p.OW); t2.fd_oh.init((uint32_t)p.OH);      // fd_ntiles: set by the launcher with n_tiles
     t2.trace = g_trace_buf.load(std::memory_order_relaxed); t2.trace_cap = g_trace_cap.load(std::memory_order_relaxed);
     t2.trace_cta = g_trace_cta.load(std::memory_order_relaxed);
     // (an L2 prefetch of the residual tensor was tried and measured slower: the residual layers are DRAM-bandwidth-
