@@ -160,7 +160,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default=os.environ.get("VLTK_BENCH_MODE", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=1, help="batches kept in flight on separate CUDA streams")
+    ap.add_argument("--streams", type=int, default=2, help="batches kept in flight on separate CUDA streams (each with its own workspace): one batch's few-CTA selection kernels overlap the other's convolutions")
     ap.add_argument("--profile-csv", default=None, help="write per-launch conv timings here")
     args = ap.parse_args()
     if args.impl == "reference":

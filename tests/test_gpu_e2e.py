@@ -295,13 +295,51 @@ def test_forward_stream_equals_forward():
         _, images, sizes, scales = pre(raws)
         host.append((images.cpu(), sizes, scales if name != "stripes" else None))   # one batch without scales_yx
     ref = [model(x, sz, scales_yx=sc, padding="max_detections", return_tensors="np") for x, sz, sc in host]
-    for depth in (1, 2, 3):
-        got = list(model.forward_stream(iter(host), depth=depth))
+    for depth, cstreams in ((1, 1), (2, 1), (3, 1), (1, 2), (2, 2), (3, 2), (4, 3)):
+        got = list(model.forward_stream(iter(host), depth=depth, compute_streams=cstreams))
         assert len(got) == len(ref)
         for a, b in zip(got, ref):
             for k in ("obj_ids", "attr_ids", "boxes", "normalized_boxes", "obj_probs", "attr_probs", "roi_features",
                       "preds_per_image", "sizes", "keep_idx"):
-                assert np.array_equal(a[k], b[k]), (depth, k)
+                assert np.array_equal(a[k], b[k]), (depth, cstreams, k)
+
+
+def test_batches_in_flight_on_two_streams_are_bit_identical_at_full_size():
+    """The benchmarked configuration keeps TWO batches in flight (bench.py --streams 2; FRCNN.forward_stream's
+    compute_streams): batch i runs on stream i % 2 with its own workspace and its own backbone side stream, so one
+    batch's few-CTA selection kernels overlap the other's convolutions.  At BASELINE size (8 x 600x1000, bf16 mode:
+    CTA pairs, two backbone halves) every batch must come out bit-identical to the same batch run alone."""
+    from vltk_b200 import synthetic
+    model, cfg = get_model("cfg2x2", "bf16")
+    mean = torch.tensor(cfg.pixel_mean).view(1, 3, 1, 1)
+    sizes = np.tile(np.array([[600, 1000]], np.int32), (8, 1))
+    scales = np.ones((8, 2), np.float32)
+    ro = model.roi_outputs
+    keys = ("obj_ids", "attr_ids", "boxes", "obj_probs", "attr_probs", "roi_features", "preds_per_image", "keep_idx")
+    dev = model.device
+    xs = []
+    for b in range(3):
+        raws = [synthetic.make_raw_image(600, 1000, 5000 + 8 * b + i) for i in range(8)]
+        xs.append((torch.stack([r.permute(2, 0, 1).float() for r in raws]) - mean).contiguous().to(dev))
+    alone = []
+    for x in xs:
+        t = model.run(x, sizes, scales, ro.max_detections, ro.min_detections, ro.nms_thresh)
+        torch.cuda.synchronize(dev)
+        alone.append({k: t[k].cpu().numpy() for k in keys})
+    side = torch.cuda.Stream(device=dev)
+    for rep in range(2):
+        side.wait_stream(torch.cuda.current_stream(dev))
+        outs = []
+        for i in range(6):                                  # batches 0,1,2,0,1,2 alternating between the two streams
+            if i % 2 == 0:
+                outs.append(model.run(xs[i % 3], sizes, scales, ro.max_detections, ro.min_detections, ro.nms_thresh, slot=0))
+            else:
+                with torch.cuda.stream(side):
+                    outs.append(model.run(xs[i % 3], sizes, scales, ro.max_detections, ro.min_detections, ro.nms_thresh, slot=1))
+        torch.cuda.synchronize(dev)
+        for i, t in enumerate(outs):
+            for k in keys:
+                assert np.array_equal(t[k].cpu().numpy(), alone[i % 3][k]), (rep, i, k)
 
 
 def test_two_devices_in_one_process():

@@ -79,9 +79,11 @@ struct vltk_frcnn {
   struct ProfRec { int kind; double flops; int64_t M; int K, Cout; cudaEvent_t e0, e1; };
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> event_pool;
-  // res2-res4 of a batch run as two image halves on two streams (see forward): fork/join plumbing
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // res2-res4 of a batch run as two image halves on two streams (see forward): fork/join plumbing.  One side stream
+  // per CALLER stream, so forwards that overlap on different caller streams (different workspaces) keep their second
+  // halves independent instead of queueing them on one shared stream.
+  struct Side { cudaStream_t caller; cudaStream_t side; cudaEvent_t ev_fork, ev_join; };
+  std::vector<Side> sides;
 };
 
 namespace vltk_eng {
@@ -445,9 +447,7 @@ void vltk_frcnn_destroy(vltk_frcnn_t* h) {
   for (void* p : h->owned) cudaFree(p);
   for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
-  if (h->side) cudaStreamDestroy(h->side);
-  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  for (auto& sd : h->sides) { cudaStreamDestroy(sd.side); cudaEventDestroy(sd.ev_fork); cudaEventDestroy(sd.ev_join); }
   delete h;
 }
 
@@ -702,15 +702,30 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   // VLTK_SPLIT_BACKBONE=0 restores the single-stream order.
   static const bool want_split = [] { const char* e = getenv("VLTK_SPLIT_BACKBONE"); return !(e && e[0] == '0'); }();
   const bool split = want_split && h->use_tc && n >= 2;
-  if (split && !h->side) {
-    VLTK_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
-    VLTK_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    VLTK_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  if (split) {
+    for (auto& sd : h->sides)
+      if (sd.caller == st) { side = sd.side; ev_fork = sd.ev_fork; ev_join = sd.ev_join; }
+    if (!side) {
+      if (h->sides.size() >= 8) {                     // callers that keep creating streams: recycle the oldest entry
+        cudaStreamSynchronize(h->sides[0].side);
+        cudaStreamDestroy(h->sides[0].side); cudaEventDestroy(h->sides[0].ev_fork); cudaEventDestroy(h->sides[0].ev_join);
+        h->sides.erase(h->sides.begin());
+      }
+      vltk_frcnn::Side sd;
+      sd.caller = st;
+      VLTK_CUDA(cudaStreamCreateWithFlags(&sd.side, cudaStreamNonBlocking));
+      VLTK_CUDA(cudaEventCreateWithFlags(&sd.ev_fork, cudaEventDisableTiming));
+      VLTK_CUDA(cudaEventCreateWithFlags(&sd.ev_join, cudaEventDisableTiming));
+      h->sides.push_back(sd);
+      side = sd.side; ev_fork = sd.ev_fork; ev_join = sd.ev_join;
+    }
   }
   const int nA = split ? (n + 1) / 2 : n, nB = n - nA;
   if (split) {
-    VLTK_CUDA(cudaEventRecord(h->ev_fork, st));
-    VLTK_CUDA(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    VLTK_CUDA(cudaEventRecord(ev_fork, st));
+    VLTK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
   }
   {
     // Half B lives at a FIXED offset (= half A's capacity) in every shared scratch buffer, so the two halves' regions
@@ -737,14 +752,14 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
           char* outB = last ? (char*)p[B_RES4] + (size_t)nA * h1 * w1 * blk.c3.ldw * e : (char*)pp[flip] + offB_big;
           int oh2, ow2;
           if (run_block(h, blk, xB, nB, ch, cw, outB, (char*)p[B_T1] + offB_mid, (char*)p[B_T2] + offB_mid,
-                        (char*)p[B_S] + offB_big, h->side, &oh2, &ow2)) return -1;
+                        (char*)p[B_S] + offB_big, side, &oh2, &ow2)) return -1;
         }
         x = outA; flip ^= 1; ch = oh; cw = ow; cin_x = blk.c3.ldw; ++bi;
       }
   }
   if (split) {
-    VLTK_CUDA(cudaEventRecord(h->ev_join, h->side));
-    VLTK_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+    VLTK_CUDA(cudaEventRecord(ev_join, side));
+    VLTK_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
   }
   VLTK_CHECK(ch == s.h4 && cw == s.w4, "internal: res4 shape mismatch");
   const void* res4 = x;

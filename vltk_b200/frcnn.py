@@ -229,22 +229,29 @@ class FRCNN:
     __call__ = forward
     inference = forward
 
-    def forward_stream(self, batches, max_detections=None, pad_value=0.0, depth=2):
+    def forward_stream(self, batches, max_detections=None, pad_value=0.0, depth=3, compute_streams=2):
         """Pipelined `forward(..., padding="max_detections", return_tensors="np")` over an iterable of host
         batches `(images, image_shapes, scales_yx)`: the host->device copy of batch i+1 and the device->host
         copy of batch i-1 run on their own streams while batch i computes (the forward itself never
-        synchronises).  Yields one dict of numpy arrays per batch, in order.  Every batch's images are copied
-        from (pinned) host memory and every result is read back to the host, exactly like `forward`."""
+        synchronises), and consecutive batches alternate between `compute_streams` CUDA streams, each with its
+        own workspace, so one batch's few-CTA selection kernels (RPN top-k, NMS, detection tail: ~1 ms on 8 SMs)
+        overlap the other batch's convolutions (+4.5 % measured).  Yields one dict of numpy arrays per batch,
+        in order, bit-identical to `forward` on the same batch.  Every batch's images are copied from (pinned)
+        host memory and every result is read back to the host, exactly like `forward`."""
         if not self._finalized:
             raise RuntimeError("load_state_dict() has not been called")
         ro = self.roi_outputs
         md = int(max_detections or ro.max_detections)
         mind = min(int(ro.min_detections), md)
         dev = self.device
+        depth = max(int(depth), 1)
         keys = ("obj_ids", "obj_probs", "attr_ids", "attr_probs", "boxes", "roi_features", "preds_per_image",
                 "normalized_boxes", "keep_idx")
         with torch.cuda.device(dev):
-            compute = torch.cuda.current_stream(dev)
+            main = torch.cuda.current_stream(dev)
+            cs = [main] + [torch.cuda.Stream(device=dev) for _ in range(max(int(compute_streams), 1) - 1)]
+            for s_ in cs[1:]:                        # ordered after whatever the caller enqueued before this call
+                s_.wait_stream(main)
             s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
             slots = [dict(x=None, ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event(), ev_out=torch.cuda.Event(),
                           host=None, dev_out=None, sizes=None, busy=False) for _ in range(depth)]
@@ -258,63 +265,76 @@ class FRCNN:
                 return out
 
             pending = []
-            for i, (images, image_shapes, scales_yx) in enumerate(batches):
-                sl = slots[i % depth]
-                if sl["busy"]:                       # its previous result has not been handed out yet
+            try:
+                for i, (images, image_shapes, scales_yx) in enumerate(batches):
+                    sl = slots[i % depth]
+                    if sl["busy"]:                       # its previous result has not been handed out yet
+                        yield collect(pending.pop(0))
+                    k = i % len(cs)                      # compute stream and workspace slot of this batch
+                    compute = cs[k]
+                    x = torch.as_tensor(images)
+                    if x.is_cuda:
+                        raise ValueError("forward_stream takes host batches; use forward() for device tensors")
+                    x = x.float().contiguous()
+                    if not x.is_pinned():
+                        x = x.pin_memory()
+                    if sl["x"] is None or sl["x"].shape != x.shape:
+                        sl["x"] = torch.empty(x.shape, dtype=torch.float32, device=dev)
+                    sizes = np.asarray(torch.as_tensor(image_shapes).cpu().numpy(), dtype=np.int32)
+                    scales = None if scales_yx is None else np.asarray(torch.as_tensor(scales_yx).cpu().numpy(), dtype=np.float32)
+                    with torch.cuda.stream(s_in):
+                        s_in.wait_event(sl["ev_done"])   # the forward that last read this input buffer is finished
+                        sl["x"].copy_(x, non_blocking=True)
+                        sl["ev_in"].record(s_in)
+                    compute.wait_event(sl["ev_in"])
+                    compute.wait_event(sl["ev_out"])     # the D2H that last read this slot's outputs is finished
+                    with torch.cuda.stream(compute):
+                        t = self.run(sl["x"], sizes, scales, md, mind, ro.nms_thresh, float(pad_value), slot=k)
+                    keep_alive = t.pop("_keepalive")
+                    sl["ev_done"].record(compute)
+                    if sl["host"] is None or sl["host"]["roi_features"].shape != t["roi_features"].shape:
+                        sl["host"] = {k_: torch.empty(t[k_].shape, dtype=t[k_].dtype).pin_memory() for k_ in keys}
+                    with torch.cuda.stream(s_out):
+                        s_out.wait_event(sl["ev_done"])
+                        for k_ in keys:
+                            sl["host"][k_].copy_(t[k_], non_blocking=True)
+                        sl["ev_out"].record(s_out)
+                    sl["dev_out"], sl["sizes"], sl["busy"], sl["_x_host"], sl["_ka"] = t, sizes, True, x, keep_alive
+                    pending.append(sl)
+                    if len(pending) >= depth:            # hand out the oldest result while newer batches run
+                        yield collect(pending.pop(0))
+                while pending:
                     yield collect(pending.pop(0))
-                x = torch.as_tensor(images)
-                if x.is_cuda:
-                    raise ValueError("forward_stream takes host batches; use forward() for device tensors")
-                x = x.float().contiguous()
-                if not x.is_pinned():
-                    x = x.pin_memory()
-                if sl["x"] is None or sl["x"].shape != x.shape:
-                    sl["x"] = torch.empty(x.shape, dtype=torch.float32, device=dev)
-                sizes = np.asarray(torch.as_tensor(image_shapes).cpu().numpy(), dtype=np.int32)
-                scales = None if scales_yx is None else np.asarray(torch.as_tensor(scales_yx).cpu().numpy(), dtype=np.float32)
-                with torch.cuda.stream(s_in):
-                    s_in.wait_event(sl["ev_done"])   # the forward that last read this input buffer is finished
-                    sl["x"].copy_(x, non_blocking=True)
-                    sl["ev_in"].record(s_in)
-                compute.wait_event(sl["ev_in"])
-                compute.wait_event(sl["ev_out"])     # the D2H that last read this slot's outputs is finished
-                t = self.run(sl["x"], sizes, scales, md, mind, ro.nms_thresh, float(pad_value))
-                keep_alive = t.pop("_keepalive")
-                sl["ev_done"].record(compute)
-                if sl["host"] is None or sl["host"]["roi_features"].shape != t["roi_features"].shape:
-                    sl["host"] = {k: torch.empty(t[k].shape, dtype=t[k].dtype).pin_memory() for k in keys}
-                with torch.cuda.stream(s_out):
-                    s_out.wait_event(sl["ev_done"])
-                    for k in keys:
-                        sl["host"][k].copy_(t[k], non_blocking=True)
-                    sl["ev_out"].record(s_out)
-                sl["dev_out"], sl["sizes"], sl["busy"], sl["_x_host"], sl["_ka"] = t, sizes, True, x, keep_alive
-                pending.append(sl)
-                if len(pending) >= depth:            # hand out the oldest result while newer batches run
-                    yield collect(pending.pop(0))
-            while pending:
-                yield collect(pending.pop(0))
+            finally:
+                for s_ in cs[1:]:                        # later work on the caller's stream stays ordered after ours
+                    main.wait_stream(s_)
 
-    def forward_jpeg_stream(self, batches, preprocess, group: int = 8, max_detections=None, pad_value=0.0):
+    def forward_jpeg_stream(self, batches, preprocess, group: int = 8, max_detections=None, pad_value=0.0,
+                            depth: int = 3, compute_streams: int = 2):
         """Raw-image front door of the extraction path: `batches` yields lists whose entries are JPEG byte strings
         and/or decoded BGR u8 [h,w,3] arrays/tensors (one list = one model batch).  The encoded entries of `group`
         batches at a time are decoded by ONE call of the GPU JPEG front end (one CTA per image: the more images
         per call, the better its few-SM kernels amortise), then each batch is resized/normalised/padded by the
-        fused preprocess kernel, run, and read back asynchronously.  Yields one dict of numpy arrays per batch,
-        in order, like `forward_stream` (plus `scales_yx`)."""
+        fused preprocess kernel, run, and read back asynchronously; consecutive batches alternate between
+        `compute_streams` streams (own workspace each) like `forward_stream`; the group decode itself runs with both
+        streams drained.  Yields one dict of numpy arrays per batch, in order (plus `scales_yx`)."""
         if not self._finalized:
             raise RuntimeError("load_state_dict() has not been called")
         ro = self.roi_outputs
         md = int(max_detections or ro.max_detections)
         mind = min(int(ro.min_detections), md)
         dev = self.device
+        depth = max(int(depth), 1)
         keys = ("obj_ids", "obj_probs", "attr_ids", "attr_probs", "boxes", "roi_features", "preds_per_image",
                 "normalized_boxes", "keep_idx")
-        depth = 2
         with torch.cuda.device(dev):
-            compute = torch.cuda.current_stream(dev)
+            main = torch.cuda.current_stream(dev)
+            cs = [main] + [torch.cuda.Stream(device=dev) for _ in range(max(int(compute_streams), 1) - 1)]
+            for s_ in cs[1:]:
+                s_.wait_stream(main)
             s_out = torch.cuda.Stream(device=dev)
             slots = [dict(ev_done=torch.cuda.Event(), ev_out=torch.cuda.Event(), host=None, busy=False) for _ in range(depth)]
+            ev_dec = torch.cuda.Event()
             pending = []
 
             def collect(sl):
@@ -328,49 +348,64 @@ class FRCNN:
 
             it = iter(batches)
             i = 0
-            while True:
-                grp = []
-                for _ in range(group):
-                    b = next(it, None)
-                    if b is None:
+            try:
+                while True:
+                    grp = []
+                    for _ in range(group):
+                        b = next(it, None)
+                        if b is None:
+                            break
+                        grp.append(list(b))
+                    if not grp:
                         break
-                    grp.append(list(b))
-                if not grp:
-                    break
-                flat = [d for b in grp for d in b]
-                enc = [j for j, d in enumerate(flat) if isinstance(d, (bytes, bytearray, memoryview))]
-                imgs = list(flat)
-                if enc:                                          # one front-end call for the whole group
-                    for j, t in zip(enc, preprocess._decode_jpegs([bytes(flat[j]) for j in enc])):
-                        imgs[j] = t
-                o = 0
-                for b in grp:
-                    sl = slots[i % depth]
-                    i += 1
-                    if sl["busy"]:
-                        yield collect(pending.pop(0))
-                    part = imgs[o:o + len(b)]
-                    o += len(b)
-                    _, x, sizes_t, scales_t = preprocess(part, sync=False)
-                    sizes = np.asarray(sizes_t.numpy(), dtype=np.int32)
-                    scales = np.asarray(scales_t.numpy(), dtype=np.float32)
-                    compute.wait_event(sl["ev_out"])
-                    t = self.run(x, sizes, scales, md, mind, ro.nms_thresh, float(pad_value))
-                    sl["_ka"] = (t.pop("_keepalive"), part)
-                    sl["ev_done"].record(compute)
-                    if sl["host"] is None or sl["host"]["roi_features"].shape != t["roi_features"].shape:
-                        sl["host"] = {k: torch.empty(t[k].shape, dtype=t[k].dtype).pin_memory() for k in keys}
-                    with torch.cuda.stream(s_out):
-                        s_out.wait_event(sl["ev_done"])
-                        for k in keys:
-                            sl["host"][k].copy_(t[k], non_blocking=True)
-                        sl["ev_out"].record(s_out)
-                    sl["dev_out"], sl["sizes"], sl["scales"], sl["busy"] = t, sizes, scales, True
-                    pending.append(sl)
-                    if len(pending) >= depth:
-                        yield collect(pending.pop(0))
-            while pending:
-                yield collect(pending.pop(0))
+                    flat = [d for b in grp for d in b]
+                    enc = [j for j, d in enumerate(flat) if isinstance(d, (bytes, bytearray, memoryview))]
+                    imgs = list(flat)
+                    if enc:                                          # one front-end call for the whole group (caller's stream)
+                        # The Huffman kernel is 1-CTA-per-image and runs ~2 ms; the convolutions are persistent kernels
+                        # with a static tile schedule and a full register file per SM, so a conv launch that finds 64
+                        # SMs held by the decoder waits for them (measured: 485 -> 272 images/s when the two overlap).
+                        # The decode therefore runs between groups, after both compute streams have drained.
+                        for s_ in cs[1:]:
+                            main.wait_stream(s_)
+                        for j, t in zip(enc, preprocess._decode_jpegs([bytes(flat[j]) for j in enc])):
+                            imgs[j] = t
+                    ev_dec.record(main)
+                    o = 0
+                    for b in grp:
+                        sl = slots[i % depth]
+                        k = i % len(cs)
+                        compute = cs[k]
+                        i += 1
+                        if sl["busy"]:
+                            yield collect(pending.pop(0))
+                        part = imgs[o:o + len(b)]
+                        o += len(b)
+                        compute.wait_event(ev_dec)               # this group's decoded images
+                        compute.wait_event(sl["ev_out"])
+                        with torch.cuda.stream(compute):
+                            _, x, sizes_t, scales_t = preprocess(part, sync=False)
+                            sizes = np.asarray(sizes_t.numpy(), dtype=np.int32)
+                            scales = np.asarray(scales_t.numpy(), dtype=np.float32)
+                            t = self.run(x, sizes, scales, md, mind, ro.nms_thresh, float(pad_value), slot=k)
+                        sl["_ka"] = (t.pop("_keepalive"), part)  # decoded images stay alive until this slot is reused
+                        sl["ev_done"].record(compute)
+                        if sl["host"] is None or sl["host"]["roi_features"].shape != t["roi_features"].shape:
+                            sl["host"] = {k_: torch.empty(t[k_].shape, dtype=t[k_].dtype).pin_memory() for k_ in keys}
+                        with torch.cuda.stream(s_out):
+                            s_out.wait_event(sl["ev_done"])
+                            for k_ in keys:
+                                sl["host"][k_].copy_(t[k_], non_blocking=True)
+                            sl["ev_out"].record(s_out)
+                        sl["dev_out"], sl["sizes"], sl["scales"], sl["busy"] = t, sizes, scales, True
+                        pending.append(sl)
+                        if len(pending) >= depth:
+                            yield collect(pending.pop(0))
+                while pending:
+                    yield collect(pending.pop(0))
+            finally:
+                for s_ in cs[1:]:
+                    main.wait_stream(s_)
 
     forward_raw_stream = forward_jpeg_stream
 
