@@ -353,7 +353,7 @@ def main():
         achieved = d_fl / (d_ms / 1e3) / 1e12 if d_ms else 0.0
         peak = pk["bf16_tflops_sustained"] if "bf16_tflops_sustained" in pk else pk["bf16_tflops"]
         traffic, traffic_note = None, None
-        ncu_json = os.path.join(ROOT, "profiles", "r01_conv_tc_traffic_v16.json")
+        ncu_json = os.path.join(ROOT, "profiles", "r01_conv_tc_traffic_v19.json")
         if dom == "tcgen05" and os.path.exists(ncu_json):  # dram bytes/launch from the committed ncu --set full capture
             nj = json.load(open(ncu_json))
             traffic = nj["traffic_bytes_per_launch"]

@@ -722,19 +722,22 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int b = q & 1;
             if (q + 1 < 8) load_chunk(q + 1, b ^ 1);
             const uint32_t coff = ((uint32_t)q ^ swz) << 4;
-            float f[8];
-            f[0] = fmaf(__uint_as_float(v[q * 8 + 0]), sc0[b].x, sh0[b].x); f[1] = fmaf(__uint_as_float(v[q * 8 + 1]), sc0[b].y, sh0[b].y);
-            f[2] = fmaf(__uint_as_float(v[q * 8 + 2]), sc0[b].z, sh0[b].z); f[3] = fmaf(__uint_as_float(v[q * 8 + 3]), sc0[b].w, sh0[b].w);
-            f[4] = fmaf(__uint_as_float(v[q * 8 + 4]), sc1[b].x, sh1[b].x); f[5] = fmaf(__uint_as_float(v[q * 8 + 5]), sc1[b].y, sh1[b].y);
-            f[6] = fmaf(__uint_as_float(v[q * 8 + 6]), sc1[b].z, sh1[b].z); f[7] = fmaf(__uint_as_float(v[q * 8 + 7]), sc1[b].w, sh1[b].w);
+            // packed fp32x2 arithmetic (FFMA2 / FADD2, IEEE round-to-nearest per lane: same bits as the scalar form,
+            // half the issue slots — the slab loop is issue-bound, summary §29)
+            float2 g2[4];
+            g2[0] = __ffma2_rn(make_float2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1])), make_float2(sc0[b].x, sc0[b].y), make_float2(sh0[b].x, sh0[b].y));
+            g2[1] = __ffma2_rn(make_float2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3])), make_float2(sc0[b].z, sc0[b].w), make_float2(sh0[b].z, sh0[b].w));
+            g2[2] = __ffma2_rn(make_float2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5])), make_float2(sc1[b].x, sc1[b].y), make_float2(sh1[b].x, sh1[b].y));
+            g2[3] = __ffma2_rn(make_float2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7])), make_float2(sc1[b].z, sc1[b].w), make_float2(sh1[b].z, sh1[b].w));
             if (HAS_RES) {
-              const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rr[q]);
+              const uint32_t rw[4] = {rr[q].x, rr[q].y, rr[q].z, rr[q].w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 rf = __bfloat1622float2(rb[j]);
-                f[2 * j] += rf.x; f[2 * j + 1] += rf.y;
-              }
+              for (int j = 0; j < 4; ++j)     // bf16 pair -> fp32 pair: low half << 16, high half masked
+                g2[j] = __fadd2_rn(g2[j], make_float2(__uint_as_float(rw[j] << 16), __uint_as_float(rw[j] & 0xFFFF0000u)));
             }
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { f[2 * j] = g2[j].x; f[2 * j + 1] = g2[j].y; }
             if (p.relu) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
@@ -1085,19 +1088,20 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int b = q & 1;
           if (q + 1 < 8) load_chunk(q + 1, b ^ 1);
           const uint32_t coff = ((uint32_t)q ^ swz) << 4;
-          float f[8];
-          f[0] = fmaf(__uint_as_float(v[q * 8 + 0]), sc0[b].x, sh0[b].x); f[1] = fmaf(__uint_as_float(v[q * 8 + 1]), sc0[b].y, sh0[b].y);
-          f[2] = fmaf(__uint_as_float(v[q * 8 + 2]), sc0[b].z, sh0[b].z); f[3] = fmaf(__uint_as_float(v[q * 8 + 3]), sc0[b].w, sh0[b].w);
-          f[4] = fmaf(__uint_as_float(v[q * 8 + 4]), sc1[b].x, sh1[b].x); f[5] = fmaf(__uint_as_float(v[q * 8 + 5]), sc1[b].y, sh1[b].y);
-          f[6] = fmaf(__uint_as_float(v[q * 8 + 6]), sc1[b].z, sh1[b].z); f[7] = fmaf(__uint_as_float(v[q * 8 + 7]), sc1[b].w, sh1[b].w);
+          float2 g2[4];                                // packed fp32x2 arithmetic, as in v2
+          g2[0] = __ffma2_rn(make_float2(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1])), make_float2(sc0[b].x, sc0[b].y), make_float2(sh0[b].x, sh0[b].y));
+          g2[1] = __ffma2_rn(make_float2(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3])), make_float2(sc0[b].z, sc0[b].w), make_float2(sh0[b].z, sh0[b].w));
+          g2[2] = __ffma2_rn(make_float2(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5])), make_float2(sc1[b].x, sc1[b].y), make_float2(sh1[b].x, sh1[b].y));
+          g2[3] = __ffma2_rn(make_float2(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7])), make_float2(sc1[b].z, sc1[b].w), make_float2(sh1[b].z, sh1[b].w));
           if (HAS_RES) {
-            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rr[q]);
+            const uint32_t rw[4] = {rr[q].x, rr[q].y, rr[q].z, rr[q].w};
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              float2 rf = __bfloat1622float2(rb[jj]);
-              f[2 * jj] += rf.x; f[2 * jj + 1] += rf.y;
-            }
+            for (int jj = 0; jj < 4; ++jj)
+              g2[jj] = __fadd2_rn(g2[jj], make_float2(__uint_as_float(rw[jj] << 16), __uint_as_float(rw[jj] & 0xFFFF0000u)));
           }
+          float f[8];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) { f[2 * jj] = g2[jj].x; f[2 * jj + 1] = g2[jj].y; }
           if (p.relu) {
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) f[jj] = fmaxf(f[jj], 0.f);
