@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--k", type=int, default=1)
     ap.add_argument("--res", type=int, default=1)
     ap.add_argument("--cta", type=int, default=5)
+    ap.add_argument("--pairs", type=int, default=0, help="1: trace the CTA-pair kernel (conv_tc3_kernel; --cta even = the leader CTA)")
     ap.add_argument("--cap", type=int, default=8192)
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
@@ -47,7 +48,7 @@ def main():
     res = torch.randn(a.rois, a.h, a.w, a.cout, device=dev).bfloat16() if a.res else None
     pad = a.pad if a.pad >= 0 else (0 if a.k == 1 else 2)
     dil = a.dil if a.dil >= 0 else (1 if a.k == 1 else 2)
-    stages.set_cta_pairs(0, 0)
+    stages.set_cta_pairs(1 if a.pairs else 0, 1 if a.pairs else 0)
     buf = torch.zeros(5 * a.cap * 2, dtype=torch.int64, device=dev)
     L = _lib.lib()
     for _ in range(2):   # warm-up launch, then the traced one (the buffer is overwritten)

@@ -937,6 +937,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ================= TMA producer (both CTAs: own A rows, own half of W) =================
     int stage = 0; uint32_t phase = 0;
     const int KH = p.KH;
+    TC_TRACE_DECL(0)
+    int tr_kb = 0; (void)tr_kb;
     for (int t = pair; t < num_pair_tiles; t += npairs) {
       uint32_t pt, nt, q, ow0, img0, oh0;
       p.fd_ntiles.divmod((uint32_t)t, pt, nt);
@@ -954,6 +956,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int kw = 0; kw < p.KW; ++kw) {
             for (int cb = 0; cb < cblocks; ++cb, kcol += BK) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
+              TC_TRACE(1, 0, tr_kb++);
               if (leader) mbar_expect_tx(full_bar(stage), 2 * S::STAGE_BYTES);   // both CTAs' bytes land on this barrier
               tma2_load_im2col_4d(sA + stage * A_STAGE_BYTES, ma, full_bar(stage), cb * BK, bw, bh, (int)img0,
                                   (uint16_t)(kw * p.dil), (uint16_t)(kh * p.dil));
@@ -969,14 +972,19 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     constexpr uint32_t idesc = make_idesc(256, BN);
     int stage = 0; uint32_t phase = 0;
     int it = 0;
+    TC_TRACE_DECL(1)
+    TC_TRACE(5, 0, 0);
     for (int t = pair; t < num_pair_tiles; t += npairs, ++it) {
       const int acc = it & 1;
       const uint32_t use = (uint32_t)(it >> 1) & 1u;
+      TC_TRACE(0, it, 0);
       mbar_wait(tempty_bar(acc), use ^ 1u);            // both CTAs' epilogues have drained this accumulator
+      TC_TRACE(1, it, 0);
       tc_fence_after();
       const uint32_t d = tmem_base + (uint32_t)(acc * BN);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(stage), phase);
+        TC_TRACE(2, it, kb);
         tc_fence_after();
         const uint32_t a = sA + stage * A_STAGE_BYTES, b = sB + stage * B3_STAGE_BYTES;
 #pragma unroll
@@ -986,6 +994,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       umma2_commit_mc(tfull_bar(acc));
+      TC_TRACE(3, it, 0);
     }
   } else if (HAS_RES && warp == 3 && lane == 0) {
     // ================= residual producer (CTA-local ring; group g = s % 2 owns slots [g * GRS, (g + 1) * GRS)) =================
@@ -1015,6 +1024,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     float* s_scale = s_scale_all + g * 2 * 128;
     float* s_shift = s_scale + 128;
     auto group_barrier = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
+#ifdef VLTK_TC_TRACE
+    int tr_n = 0; const bool tr_on = p.trace && (int)blockIdx.x == p.trace_cta && issuer; const int tr_role = 3 + g;
+#endif
     // entry `et` of my scale/shift cache holds column ss_col(t) of tile t; fetched one tile ahead (as in v2)
     auto ss_col = [&](int t_) { return (int)p.fd_ntiles.mod((uint32_t)t_) * BN + (g + (et >> 6) * EG) * SLAB + (et & 63); };
     float pf_sc = 1.f, pf_sh = 0.f;
@@ -1039,7 +1051,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           pf_sc = p.scale ? __ldg(p.scale + cn) : 1.f; pf_sh = p.shift ? __ldg(p.shift + cn) : 0.f;
         }
       }
+      TC_TRACE(0, it, 0);
       mbar_wait(tfull_bar(acc), use);
+      TC_TRACE(1, it, 0);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
@@ -1062,9 +1076,13 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
           if (lane == 0) { if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_leader(tempty_bar(acc)); }
         }
+        TC_TRACE(2, it, s);
         if (HAS_RES) mbar_wait(rfull_bar(slot), rphase);
+        TC_TRACE(3, it, s);
         if (!POOL && issuer) bulk_wait_read<0>();      // the store that last read sOutG has drained it
+        TC_TRACE(4, it, s);
         group_barrier();                               // sOutG reusable (POOL: last slab's column readers done); scale/shift visible
+        TC_TRACE(5, it, s);
         const uint32_t orow = sOutG + (uint32_t)row * 128u;
         const uint32_t rrow = sRes + (uint32_t)slot * SLAB_BYTES + (uint32_t)row * 128u;
         (void)rrow;
@@ -1142,12 +1160,14 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             p.pool_partial[(int64_t)mt * p.Cout + n0 + s * SLAB + et] = tot;
           }
         } else {
+          TC_TRACE(6, it, s);
           fence_proxy_async_smem();
           group_barrier();
           if (issuer) {
             tma_store_2d(&tmY, sOutG, n0 + s * SLAB, m0);
             bulk_commit();
           }
+          TC_TRACE(7, it, s);
         }
       }
     }
