@@ -8,9 +8,12 @@ A step = one pass of the hot path over one batch: BASELINE.json configs[1] — 8
 36 detections per image.  One process per GPU; images shard by rank with no collective in the
 data path (weak scaling: every rank runs its own batches).  Rank 0 prints ONE JSON line.
 
-  value        images/s with the normalised batch already resident in HBM, CUDA-event timed
-  e2e          same metric through FRCNN.forward() with pinned HOST tensors in and HOST arrays out
-  roofline     tcgen05 implicit-GEMM kernel: algorithmic conv FLOPs / its summed CUDA-event time
+  value        images/s with the normalised batch already resident in HBM, CUDA-event timed; --streams batches are kept in
+               flight (default 2: batch i on stream i % 2 with its own workspace, outputs bit-identical to one at a time)
+  e2e          same metric through the public streaming call FRCNN.forward_stream() with pinned HOST tensors in and HOST
+               arrays out (H2D / D2H inside the timed region); the synchronous FRCNN.forward() is timed beside it
+  roofline     tcgen05 implicit-GEMM kernels: algorithmic conv FLOPs / busy time (union of their launches' CUDA-event
+               intervals on their own streams)
   cpu_baseline the oracle port (CPU restatement of the reference) on a 1-image sample
   --impl reference : times that CPU implementation on all host threads instead (1 image/step)
 """
