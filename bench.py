@@ -396,7 +396,7 @@ def main():
             "flops_per_image": fl["total"], "step_tflops": BATCH * fl["total"] / (ms / args.steps / 1e3) / 1e12,
             "clocks": sampler.summary() if sampler else None,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:    # reported baseline: rank 0 at N=1 only (the other N repeat the same CPU number)
             v, nimg, cores = cpu_oracle_images_per_sec(cfg, sd)
             line["cpu_baseline"] = {"value": v, "unit": "images/sec", "cores": cores, "kind": "port",
                                     "sample": f"mean of {nimg} single 600x1000 images after 1 warm-up, oracle/frcnn_oracle.py (torch fp32 CPU, all host threads)"}
