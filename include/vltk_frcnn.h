@@ -25,10 +25,14 @@ extern "C" {
 
 typedef struct vltk_frcnn vltk_frcnn_t;
 
-/* Arithmetic modes of the dense layers (activations NHWC in both). */
+/* Arithmetic modes of the dense layers (activations NHWC in all of them). */
 enum {
   VLTK_MODE_FP32 = 0, /* fp32 storage, fp32 FMA on the CUDA cores: index-exact parity mode      */
-  VLTK_MODE_BF16 = 1  /* bf16 storage, tcgen05 tensor-core implicit GEMM, fp32 accumulate       */
+  VLTK_MODE_BF16 = 1, /* bf16 storage, tcgen05 tensor-core implicit GEMM, fp32 accumulate       */
+  VLTK_MODE_EXACT_TC = 2 /* fp32-FAITHFUL on tcgen05: activations stored as two fp16 planes (x = hi + lo*2^-11),
+                          * weights as three, 3 kind::f16 passes per K chunk, chunk sums promoted to an fp32
+                          * register accumulator (csrc/conv_tcx.cu).  Index-exact parity mode on the tensor
+                          * pipe; requires |activation| <= 65504.                                          */
 };
 
 /* Architecture + selection knobs.  Mirrors the cfg.* keys FRCNN.__init__ reads

@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("VLTK_LIB", "libvltk_frcnn.so"))
 
 MODE_FP32 = 0
 MODE_BF16 = 1
-MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16}
+MODE_EXACT_TC = 2
+MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, "exact_tc": MODE_EXACT_TC}
 
 
 class Config(C.Structure):

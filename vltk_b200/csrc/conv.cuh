@@ -9,7 +9,10 @@
 
 namespace vltk {
 
-enum DType { DT_F32 = 0, DT_BF16 = 1 };
+// DT_H2 ("split fp16", the exact_tc mode): an fp32 value x stored as two fp16 planes, x = hi + lo' * 2^-11 with
+// hi = fp16(x), lo' = fp16((x - hi) * 2^11) (|x - (hi + lo' 2^-11)| <= 2^-24 |x|).  A pixel row of C channels is
+// 2C halfs: [hi(0..C) | lo'(0..C)], so `ld` counts halfs and is 2C for a dense tensor.
+enum DType { DT_F32 = 0, DT_BF16 = 1, DT_H2 = 2 };
 
 struct ConvProblem {
   // activations, NHWC

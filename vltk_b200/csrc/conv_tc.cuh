@@ -53,6 +53,12 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
                    cudaStream_t st, const TcSplit* split = nullptr, const TcPool* pool = nullptr,
                    const TcConcat* concat = nullptr);
 
+// fp32-faithful convolution on the tensor pipe (conv_tcx.cu): split-fp16 activations (DT_H2) x three fp16 weight
+// planes, three kind::f16 passes per K chunk, chunk sums promoted to an fp32 register accumulator.
+//   w3: fp16 [cout_pad][3*K] = rows of (WA | WB | WC), built by pack_weight_h3; p.scale must already carry the
+//   per-row 2^-s of the packing.  out_dtype DT_H2 (optional DT_H2 residual) or DT_F32 (cout_pad % 128 == 0).
+int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMapCache* cache, cudaStream_t st);
+
 // CTA-pair (tcgen05 cta_group::2) dispatch: layers with BN = 256, bf16 output and at least `min_pixels` output pixels
 // run on conv_tc3_kernel (0 = never); `residual_layers` = 0 keeps residual / pooled layers on v2.  Negative = unchanged.
 void conv_tc_set_cta_pairs(int min_pixels, int residual_layers);
@@ -60,6 +66,14 @@ void conv_tc_set_cta_pairs(int min_pixels, int residual_layers);
 // Diagnosis builds (-DVLTK_TC_TRACE): the next conv_tc2 launches record CTA `cta`'s pipeline events into dev_buf
 // (5 roles x cap_per_role x 2 int64).  dev_buf = nullptr switches it off.  Returns -1 in a library built without tracing.
 int conv_tc_set_trace(void* dev_buf, int cap_per_role, int cta);
+
+// ---- descriptor encoders (conv_tc.cu), shared with conv_tcx.cu.  128B-swizzled boxes.
+int tc_num_sms();
+int tc_encode_tiled(CUtensorMap* out, CUtensorMapDataType dt, const void* ptr, uint64_t cols, uint64_t rows,
+                    uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows, bool promote256);
+// NHWC tensor [N,H,W,C] (pixel stride ld_elems elements of esz bytes) gathered as 128-pixel x 64-channel im2col boxes
+int tc_encode_im2col(CUtensorMap* out, CUtensorMapDataType dt, const void* ptr, int N, int H, int W, int C, int ld_elems,
+                     int esz, int KH, int KW, int stride, int pad, int dil);
 
 // ---- pack.cu: reference-layout weights [cout][cin][taps] (DEVICE f32) -> kernel layouts
 int pack_weight_kn(const float* w, float* w_kn, int cout, int cin, int taps, int ldw, bool round_bf16,

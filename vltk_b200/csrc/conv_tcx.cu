@@ -1,0 +1,432 @@
+// fp32-FAITHFUL implicit-GEMM convolution on the tensor cores ("exact_tc" mode):
+//
+//   every fp32 activation x is stored as two fp16 planes   x = hi + lo' * 2^-11   (hi = fp16(x), lo' = fp16((x - hi) * 2^11))
+//   every fp32 weight row (scaled by a per-row power of two 2^s, folded back into the epilogue scale) as three planes
+//       WA = fp16(2^s w) ,  WB = WA * 2^-11 ,  WC = fp16(2^s w - WA)
+//   and the product is   x w 2^s  =  lo' * WB  +  hi * WC  +  hi * WA     (the dropped lo * w_lo term is 2^-24 relative)
+//
+// i.e. THREE tcgen05.mma kind::f16 passes (fp16 x fp16 products are exact in the multiplier) instead of one.  The tensor
+// core's fp32 accumulator TRUNCATES towards zero on every MMA (measured: tools/acc_probe.py, profiles/r02_acc_probe.json —
+// ~0.85 ulp of the running sum per instruction, 240 ulp over a K = 4608 reduction), so a plain three-pass K loop is 50x
+// noisier than an fp32 FMA chain.  Hence TWO-LEVEL ACCUMULATION: the K loop is cut into chunks of `chunk_kb` k-blocks
+// (default 4 = 256 input channels); within a chunk the two small passes run first and the hi*hi pass last, into one of
+// two alternating TMEM accumulators that starts from zero; the epilogue warps drain every finished chunk with
+// tcgen05.ld and add it to a REGISTER-resident fp32 running sum with IEEE round-to-nearest while the tensor core
+// fills the other accumulator.  Truncation then acts on chunk-sized partial sums only (<= 16 MMAs of the big pass).
+//
+// Pipeline roles as in conv_tc2_kernel (TMA producer / MMA issuer / TMEM allocator / epilogue warpgroups); the
+// epilogue writes the two output planes through two 128B-swizzled staging buffers per group and TMA stores, and
+// a residual tensor (two planes) is TMA-loaded INTO those staging buffers and consumed in place.
+//
+// Reference layers: every Conv2d+BN(+ReLU)(+residual) of res2-res5, the RPN convs and the predictor linears
+// (frcnn.py:794-822, 963-979, 1345-1355, 1561-1572, 1726-1740), computed in fp32 by the reference.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "conv_tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace vltk {
+
+namespace {
+
+constexpr int XSLAB = 64;                      // columns per epilogue unit (one 128 B fp16 staging row)
+constexpr int XBUF_BYTES = BM * 128;           // one staging buffer: 128 rows x 128 B
+constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
+
+// kind::f16 instruction descriptor with fp16 A and B (format 0), fp32 accumulate, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct TcxParams {
+  const float* scale; const float* shift;      // per output channel; scale already carries the weight row's 2^-s
+  FastDiv fd_ntiles, fd_ow, fd_oh;
+  int64_t M;
+  int Cout, relu;
+  int stride, pad, dil, KW, num_kb, lg_cblocks;
+  int cin;                                     // channel offset of the lo' plane in x (= Cin)
+  int K;                                       // element offset between the weight planes WA | WB | WC
+  int n_tiles, num_tiles, chunk_kb;
+  int out_plane, res_plane;                    // column offset of the lo' plane in y / residual
+};
+
+template <int BN, int STAGES, int EG>
+struct SmemX {
+  static constexpr int NS_OWN = BN / XSLAB / EG;                 // 64-column units per epilogue group
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
+  static constexpr int OFF_OUT = STAGES * STAGE_BYTES;
+  static constexpr int OFF_SCALE = OFF_OUT + EG * 2 * XBUF_BYTES;
+  static constexpr int OFF_BARS = OFF_SCALE + EG * NS_OWN * XSLAB * 2 * 4;
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + EG;
+  static constexpr int TOTAL = OFF_BARS + NUM_BARS * 8 + 16;
+  static_assert(NS_OWN >= 1 && NS_OWN * EG * XSLAB == BN, "BN must split evenly over the epilogue groups");
+  static_assert(TOTAL <= 232448, "exceeds the 227 KB shared memory of one sm_100 CTA");
+};
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// x -> (hi, lo') ; saturating (|x| > 65504 cannot be represented: documented limit of the mode)
+__device__ __forceinline__ void split_h2(float x, float& hi, float& lo) {
+  const float c = fminf(fmaxf(x, -65504.f), 65504.f);
+  hi = __half2float(__float2half_rn(c));
+  lo = fminf(fmaxf((x - hi) * LO_SCALE, -65504.f), 65504.f);
+}
+
+template <int BN, int STAGES, int EG, bool HAS_RES, bool OUT_F32, bool BIGREG>
+__global__ void __launch_bounds__(128 + 128 * EG, 1)
+conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, TcxParams p) {
+  using S = SmemX<BN, STAGES, EG>;
+  static_assert(!(HAS_RES && OUT_F32), "fp32 output has no residual path");
+  constexpr int NS_OWN = S::NS_OWN;
+  extern __shared__ __align__(1024) unsigned char smem_dynx[];
+  const uint32_t base = smem_u32(smem_dynx);
+  if (base & 1023u) {
+    if (threadIdx.x == 0) printf("conv_tcx: dynamic smem base %u is not 1024 B aligned\n", base);
+    __trap();
+  }
+  unsigned char* gbase = smem_dynx;
+  const uint32_t sA = base, sB = base + S::OFF_B, sOut = base + S::OFF_OUT;
+  float* s_scale_all = reinterpret_cast<float*>(gbase + S::OFF_SCALE);
+  const uint32_t bars = base + S::OFF_BARS;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+  auto res_bar = [&](int g) { return bars + 8u * (2 * STAGES + 4 + g); };
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + S::OFF_BARS + S::NUM_BARS * 8);
+  const uint32_t tmem_slot = bars + S::NUM_BARS * 8;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks = (p.num_kb + p.chunk_kb - 1) / p.chunk_kb;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY);
+    if (HAS_RES) tma_prefetch_desc(&tmR);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * EG); }
+    for (int g = 0; g < EG; ++g) mbar_init(res_bar(g), 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  // Programmatic dependent launch (see conv_tc2_kernel): nothing above touched an activation.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  // The epilogue threads keep a [NS_OWN x 64] fp32 running sum in registers: give them the register file of the
+  // (single-thread) producer / issuer warps.
+  // pass ps of a chunk: 0 = lo' x WB, 1 = hi x WC, 2 = hi x WA   (small terms first, see the header)
+  if (warp < 4) {
+  if constexpr (BIGREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  if (warp == 0 && lane == 0) {
+    // ================= TMA producer =================
+    int stage = 0; uint32_t phase = 0;
+    const int cb_mask = (1 << p.lg_cblocks) - 1;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      uint32_t mt, nt, q, ow0, img0, oh0;
+      p.fd_ntiles.divmod((uint32_t)t, mt, nt);
+      const int n0 = (int)nt * BN;
+      const uint32_t m0 = mt * BM;
+      p.fd_ow.divmod(m0, q, ow0);
+      p.fd_oh.divmod(q, img0, oh0);
+      const int bw = (int)ow0 * p.stride - p.pad, bh = (int)oh0 * p.stride - p.pad;
+      for (int c0 = 0; c0 < p.num_kb; c0 += p.chunk_kb) {
+        const int c1 = min(c0 + p.chunk_kb, p.num_kb);
+        for (int ps = 0; ps < 3; ++ps) {
+          const int a_off = ps == 0 ? p.cin : 0;
+          const int b_off = ps == 0 ? p.K : (ps == 1 ? 2 * p.K : 0);
+          for (int kb = c0; kb < c1; ++kb) {
+            const int tap = kb >> p.lg_cblocks, cb = kb & cb_mask;
+            const int kh = p.KW == 1 ? tap : (tap * 11) >> 5;      // tap / 3 for tap < 9
+            const int kw = tap - kh * p.KW;
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), S::STAGE_BYTES);
+            tma_load_im2col_4d(sA + stage * A_STAGE_BYTES, &tmA, full_bar(stage), a_off + cb * BK, bw, bh, (int)img0,
+                               (uint16_t)(kw * p.dil), (uint16_t)(kh * p.dil));
+            tma_load_2d(sB + stage * S::B_STAGE_BYTES, &tmB, full_bar(stage), b_off + kb * BK, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+    int stage = 0; uint32_t phase = 0;
+    int seq = 0;                                   // chunk sequence number of this CTA (across tiles)
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      for (int c0 = 0; c0 < p.num_kb; c0 += p.chunk_kb, ++seq) {
+        const int nkb = min(p.chunk_kb, p.num_kb - c0) * 3;
+        const int acc = seq & 1;
+        const uint32_t use = (uint32_t)(seq >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), use ^ 1u);      // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a = sA + stage * A_STAGE_BYTES, b = sB + stage * S::B_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16(d, make_smem_desc(a + k * UMMA_K * 2), make_smem_desc(b + k * UMMA_K * 2), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  }
+  } else {
+    // ================= epilogue: chunk promotion + tile finish =================
+    if constexpr (BIGREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int g = (warp - 4) >> 2;                 // epilogue warpgroup
+    const int e = warp & 3;                        // TMEM lane quarter == warp id % 4
+    const int row = e * 32 + lane;
+    const int et = threadIdx.x - 128 - g * 128;
+    const bool issuer = et == 0;
+    const uint32_t swz = (uint32_t)(row & 7);
+    const uint32_t buf0 = sOut + (uint32_t)(g * 2) * XBUF_BYTES + (uint32_t)row * 128u;   // this thread's row in the group's buffers
+    const uint32_t buf1 = buf0 + XBUF_BYTES;
+    const uint32_t gbuf0 = sOut + (uint32_t)(g * 2) * XBUF_BYTES, gbuf1 = gbuf0 + XBUF_BYTES;
+    float* s_scale = s_scale_all + g * 2 * NS_OWN * XSLAB;
+    float* s_shift = s_scale + NS_OWN * XSLAB;
+    auto group_barrier = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
+    uint32_t rphase = 0;
+    int seq = 0;
+    float run[NS_OWN][XSLAB];
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      uint32_t umt, unt;
+      p.fd_ntiles.divmod((uint32_t)t, umt, unt);
+      const int n0 = (int)unt * BN, m0 = (int)umt * BM;
+      // scale / shift of my columns (read in the tile finish, at least one chunk of MMAs from now)
+      for (int i = et; i < NS_OWN * XSLAB; i += 128) {
+        const int col = n0 + (g + (i >> 6) * EG) * XSLAB + (i & 63);
+        s_scale[i] = p.scale ? __ldg(p.scale + col) : 1.f;
+        s_shift[i] = p.shift ? __ldg(p.shift + col) : 0.f;
+      }
+      for (int ci = 0; ci < nchunks; ++ci, ++seq) {
+        const int acc = seq & 1;
+        const uint32_t use = (uint32_t)(seq >> 1) & 1u;
+        if (HAS_RES && ci == nchunks - 1 && issuer) {
+          // residual planes of my first unit -> my staging buffers, hidden behind the last chunk's MMAs
+          bulk_wait_read<0>();                     // the stores that last read the buffers have drained them
+          mbar_expect_tx(res_bar(g), 2 * XBUF_BYTES);
+          tma_load_2d(gbuf0, &tmR, res_bar(g), n0 + g * XSLAB, m0);
+          tma_load_2d(gbuf1, &tmR, res_bar(g), p.res_plane + n0 + g * XSLAB, m0);
+        }
+        mbar_wait(tfull_bar(acc), use);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll
+        for (int j = 0; j < NS_OWN; ++j) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(tacc + (uint32_t)((g + j * EG) * XSLAB), v0);
+          tmem_ld32(tacc + (uint32_t)((g + j * EG) * XSLAB + 32), v1);
+          tmem_ld_wait();
+          if (ci == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { run[j][i] = __uint_as_float(v0[i]); run[j][32 + i] = __uint_as_float(v1[i]); }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              run[j][i] = __fadd_rn(run[j][i], __uint_as_float(v0[i]));
+              run[j][32 + i] = __fadd_rn(run[j][32 + i], __uint_as_float(v1[i]));
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));   // hand the accumulator back to the MMA warp
+      }
+      // ---- tile finish: scale/shift (+ residual) (+ ReLU) -> two fp16 planes (or fp32) -> TMA store
+#pragma unroll
+      for (int j = 0; j < NS_OWN; ++j) {
+        const int col0 = n0 + (g + j * EG) * XSLAB;
+        if (HAS_RES) {
+          if (j > 0 && issuer) {
+            bulk_wait_read<0>();
+            mbar_expect_tx(res_bar(g), 2 * XBUF_BYTES);
+            tma_load_2d(gbuf0, &tmR, res_bar(g), col0, m0);
+            tma_load_2d(gbuf1, &tmR, res_bar(g), p.res_plane + col0, m0);
+          }
+          mbar_wait(res_bar(g), rphase);
+          rphase ^= 1u;
+        } else if (issuer) {
+          bulk_wait_read<0>();
+        }
+        group_barrier();                           // staging reusable; scale/shift visible
+        if constexpr (OUT_F32) {
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {          // 4 fp32 channels = one 16 B chunk
+              const int c = j * XSLAB + hb * 32 + q * 4;
+              const float4 sc = *reinterpret_cast<const float4*>(s_scale + c);
+              const float4 sh = *reinterpret_cast<const float4*>(s_shift + c);
+              float f0 = fmaf(run[j][hb * 32 + q * 4 + 0], sc.x, sh.x), f1 = fmaf(run[j][hb * 32 + q * 4 + 1], sc.y, sh.y);
+              float f2 = fmaf(run[j][hb * 32 + q * 4 + 2], sc.z, sh.z), f3 = fmaf(run[j][hb * 32 + q * 4 + 3], sc.w, sh.w);
+              if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
+              sts128((hb ? buf1 : buf0) + (((uint32_t)q ^ swz) << 4),
+                     make_uint4(__float_as_uint(f0), __float_as_uint(f1), __float_as_uint(f2), __float_as_uint(f3)));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {            // 8 channels = one 16 B fp16 chunk per plane
+            const uint32_t coff = ((uint32_t)q ^ swz) << 4;
+            const int c = j * XSLAB + q * 8;
+            const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + c), sc1 = *reinterpret_cast<const float4*>(s_scale + c + 4);
+            const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + c), sh1 = *reinterpret_cast<const float4*>(s_shift + c + 4);
+            float y[8];
+            y[0] = fmaf(run[j][q * 8 + 0], sc0.x, sh0.x); y[1] = fmaf(run[j][q * 8 + 1], sc0.y, sh0.y);
+            y[2] = fmaf(run[j][q * 8 + 2], sc0.z, sh0.z); y[3] = fmaf(run[j][q * 8 + 3], sc0.w, sh0.w);
+            y[4] = fmaf(run[j][q * 8 + 4], sc1.x, sh1.x); y[5] = fmaf(run[j][q * 8 + 5], sc1.y, sh1.y);
+            y[6] = fmaf(run[j][q * 8 + 6], sc1.z, sh1.z); y[7] = fmaf(run[j][q * 8 + 7], sc1.w, sh1.w);
+            if (HAS_RES) {
+              const uint4 rh = lds128(buf0 + coff), rl = lds128(buf1 + coff);
+              const uint32_t hw[4] = {rh.x, rh.y, rh.z, rh.w}, lw[4] = {rl.x, rl.y, rl.z, rl.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+                const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
+                y[2 * i] = __fadd_rn(y[2 * i], fmaf(fl.x, LO_INV, fh.x));
+                y[2 * i + 1] = __fadd_rn(y[2 * i + 1], fmaf(fl.y, LO_INV, fh.y));
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], 0.f);
+            }
+            float hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) split_h2(y[i], hi[i], lo[i]);
+            sts128(buf0 + coff, make_uint4(pack_half2(hi[0], hi[1]), pack_half2(hi[2], hi[3]), pack_half2(hi[4], hi[5]), pack_half2(hi[6], hi[7])));
+            sts128(buf1 + coff, make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]), pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7])));
+          }
+        }
+        fence_proxy_async_smem();                  // generic-proxy smem writes -> visible to the TMA unit
+        group_barrier();
+        if (issuer) {
+          tma_store_2d(&tmY, gbuf0, col0, m0);
+          tma_store_2d(&tmY, gbuf1, col0 + (OUT_F32 ? 32 : p.out_plane), m0);
+          bulk_commit();
+        }
+      }
+    }
+    if (issuer) bulk_wait_all();                   // all output bytes are in global memory
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<2 * BN>(tmem_base);
+}
+
+template <int BN, int STAGES, int EG, bool HAS_RES, bool OUT_F32, bool BIGREG>
+int launchx(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& my, const CUtensorMap& mr, TcxParams tp,
+            int cout_pad, cudaStream_t st) {
+  using S = SmemX<BN, STAGES, EG>;
+  auto kern = conv_tcx_kernel<BN, STAGES, EG, HAS_RES, OUT_F32, BIGREG>;
+  static DeviceOnce once;
+  if (once.first()) VLTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+  tp.n_tiles = cout_pad / BN;
+  tp.fd_ntiles.init((uint32_t)tp.n_tiles);
+  const int64_t tiles = ceil_div64(tp.M, BM) * tp.n_tiles;
+  VLTK_CHECK(tiles < (1ll << 31), "conv_tcx: too many tiles");
+  tp.num_tiles = (int)tiles;
+  const int grid = (int)std::min<int64_t>(tiles, tc_num_sms());   // persistent: one CTA per SM
+  static const bool use_pdl = [] { const char* e = getenv("VLTK_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128 + 128 * EG); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+  VLTK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, my, mr, tp));
+  VLTK_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMapCache* cache, cudaStream_t st) {
+  const bool out_f32 = p.out_dtype == DT_F32;
+  VLTK_CHECK(p.in_dtype == DT_H2 && (out_f32 || p.out_dtype == DT_H2), "conv_tcx: split-fp16 activations in, split-fp16 or fp32 out");
+  VLTK_CHECK(p.Cin % BK == 0 && ((p.Cin / BK) & (p.Cin / BK - 1)) == 0, "conv_tcx: Cin=%d must be 64 * 2^k", p.Cin);
+  VLTK_CHECK(p.ldx == 2 * p.Cin, "conv_tcx: x must hold the two planes of a pixel back to back (ldx = 2 Cin)");
+  VLTK_CHECK((p.KH == 1 && p.KW == 1) || (p.KH == 3 && p.KW == 3), "conv_tcx: 1x1 and 3x3 kernels only");
+  VLTK_CHECK(!(out_f32 && p.residual), "conv_tcx: fp32 output has no residual path");
+  VLTK_CHECK(cout_pad % 64 == 0 && p.Cout == cout_pad, "conv_tcx: Cout=%d must equal cout_pad=%d (a multiple of 64)", p.Cout, cout_pad);
+  VLTK_CHECK(out_f32 ? (p.ldy % 4 == 0 && p.ldy >= p.Cout) : p.ldy == 2 * p.Cout, "conv_tcx: bad output row stride");
+  VLTK_CHECK(!p.residual || p.ldr == 2 * p.Cout, "conv_tcx: the residual must be a split-fp16 tensor of the output shape");
+  const int64_t M = (int64_t)p.N * p.OH * p.OW;
+  if (M == 0) return 0;
+  VLTK_CHECK(M < (1ll << 31) - 512, "conv_tcx: M=%lld output pixels exceed the 32-bit tile arithmetic", (long long)M);
+  const int K = p.KH * p.KW * p.Cin;
+  static const int smallk = [] { const char* e = getenv("VLTK_TCX_SMALLK"); return e ? atoi(e) : 256; }();
+  static const int chunk = [] { const char* e = getenv("VLTK_TCX_CHUNK"); return e ? std::max(1, atoi(e)) : 4; }();
+  int bn = (cout_pad % 256 == 0) ? 256 : (cout_pad % 128 == 0 ? 128 : 64);
+  if (K <= smallk && cout_pad % 128 == 0) bn = 128;
+  if (out_f32) { VLTK_CHECK(cout_pad % 128 == 0, "conv_tcx: fp32 output needs cout_pad %% 128 == 0"); bn = 128; }
+  if (p.residual && bn == 64) { VLTK_CHECK(false, "conv_tcx: residual layers need Cout %% 128 == 0"); }
+  if (cache->maps.size() > 8192) cache->maps.clear();
+  auto cached = [&](const TensorMapCache::Key& k, CUtensorMap* dst, auto make) -> int {
+    auto it = cache->maps.find(k);
+    if (it == cache->maps.end()) {
+      if (make(dst)) return -1;
+      cache->maps[k] = *dst;
+    } else *dst = it->second;
+    return 0;
+  };
+  CUtensorMap ma, mb, my, mr;
+  if (cached(TensorMapCache::Key(p.x, p.N, p.H, p.W, p.Cin, p.ldx, p.KH, p.stride, p.pad, p.dil, 10), &ma, [&](CUtensorMap* d) {
+        return tc_encode_im2col(d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.x, p.N, p.H, p.W, 2 * p.Cin, p.ldx, 2, p.KH, p.KW, p.stride, p.pad, p.dil);
+      })) return -1;
+  if (cached(TensorMapCache::Key(w3, K, cout_pad, bn, 0, 0, 0, 0, 0, 0, 11), &mb, [&](CUtensorMap* d) {
+        return tc_encode_tiled(d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, w3, (uint64_t)3 * K, (uint64_t)cout_pad, (uint64_t)3 * K * 2, BK, (uint32_t)bn, true);
+      })) return -1;
+  if (cached(TensorMapCache::Key(p.y, (int)M, p.Cout, p.ldy, out_f32 ? 1 : 0, 0, 0, 0, 0, 0, 12), &my, [&](CUtensorMap* d) {
+        return out_f32 ? tc_encode_tiled(d, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.y, (uint64_t)p.Cout, (uint64_t)M, (uint64_t)p.ldy * 4, 32, BM, false)
+                       : tc_encode_tiled(d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.y, (uint64_t)2 * p.Cout, (uint64_t)M, (uint64_t)p.ldy * 2, XSLAB, BM, false);
+      })) return -1;
+  mr = my;
+  if (p.residual &&
+      cached(TensorMapCache::Key(p.residual, (int)M, p.Cout, p.ldr, 0, 0, 0, 0, 0, 0, 13), &mr, [&](CUtensorMap* d) {
+        return tc_encode_tiled(d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.residual, (uint64_t)2 * p.Cout, (uint64_t)M, (uint64_t)p.ldr * 2, XSLAB, BM, false);
+      })) return -1;
+  TcxParams t;
+  memset(&t, 0, sizeof(t));
+  t.scale = p.scale; t.shift = p.shift; t.M = M; t.Cout = p.Cout; t.relu = p.relu;
+  t.stride = p.stride; t.pad = p.pad; t.dil = p.dil; t.KW = p.KW;
+  const int cblocks = p.Cin / BK;
+  t.lg_cblocks = 0;
+  while ((1 << t.lg_cblocks) < cblocks) ++t.lg_cblocks;
+  t.num_kb = p.KH * p.KW * cblocks; t.cin = p.Cin; t.K = K; t.chunk_kb = chunk;
+  t.out_plane = p.Cout; t.res_plane = p.Cout;
+  t.fd_ow.init((uint32_t)p.OW); t.fd_oh.init((uint32_t)p.OH);
+  if (out_f32) return launchx<128, 5, 2, false, true, false>(ma, mb, my, mr, t, cout_pad, st);
+  if (p.residual) {
+    if (bn == 256) return launchx<256, 3, 2, true, false, true>(ma, mb, my, mr, t, cout_pad, st);
+    return launchx<128, 5, 2, true, false, false>(ma, mb, my, mr, t, cout_pad, st);
+  }
+  if (bn == 256) return launchx<256, 3, 2, false, false, true>(ma, mb, my, mr, t, cout_pad, st);
+  if (bn == 128) return launchx<128, 5, 2, false, false, false>(ma, mb, my, mr, t, cout_pad, st);
+  return launchx<64, 6, 1, false, false, false>(ma, mb, my, mr, t, cout_pad, st);
+}
+
+}  // namespace vltk

@@ -1,6 +1,8 @@
 // C ABI + host-side orchestration of the extraction path (include/vltk_frcnn.h).
 // The whole forward is enqueued on one stream with no host synchronisation: dynamic counts
 // (non-empty proposals, NMS survivors, detections) stay on the device.
+#include <cuda_fp16.h>
+#include <math.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -34,6 +36,8 @@ struct LayerW {           // one conv / linear layer, packed for the kernels
   float* w_kn = nullptr;  // SIMT: f32 [K_pad][ldw]
   bf16* w_nk = nullptr;   // tcgen05: bf16 [cout_pad][K]  (bf16 mode, Cin % 64 == 0 only)
   bf16* w_lo = nullptr;   // split-precision layers: w = w_nk (hi) + w_lo
+  void* w_h3 = nullptr;   // exact_tc: fp16 [cout_pad][3K] rows of (WA | WB | WC), see conv_tcx.cu
+  float* scale_x = nullptr;  // exact_tc: scale[o] * 2^-s[o] (the row scaling of w_h3 folded back), cout_pad entries
   int cout_pad = 0;
   float* scale = nullptr; // [ldw] or nullptr
   float* shift = nullptr; // [ldw]
@@ -48,7 +52,7 @@ struct Block {
   bf16* scf_w = nullptr;    // bf16(scale_sc * W_sc)  [cout][cin]
 };
 
-struct Tap { const void* p = nullptr; int64_t n = 0; DType dt = DT_F32; };
+struct Tap { const void* p = nullptr; int64_t n = 0; DType dt = DT_F32; int c = 0; };   // c: channels per row (DT_H2)
 
 }  // namespace
 }  // namespace vltk
@@ -60,6 +64,8 @@ struct vltk_frcnn {
   int device = 0;
   bool finalized = false;
   bool use_tc = false;
+  bool use_tcx = false;    // exact_tc mode: conv_tcx.cu on split-fp16 activations
+  bool pack_x = true;      // pack_layer builds exact_tc planes (switched off for the predictor linears, packed separately)
   DType act = DT_F32;
   std::map<std::string, std::vector<float>> host;
   std::vector<void*> owned;  // device allocations
@@ -112,6 +118,61 @@ const std::vector<float>* find(vltk_frcnn* h, const std::string& k, int64_t nume
   return &it->second;
 }
 
+// exact_tc weight planes (conv_tcx.cu): row o of wk ([cout][K], kernel K order) -> fp16 (WA | WB | WC) with a per-row
+// power-of-two scale 2^s chosen so that max|w| 2^s lies in [2^12, 2^13) (every plane then sits in fp16's normal
+// range): WA = fp16(2^s w), WB = WA 2^-11, WC = fp16(2^s w - WA).  scale_x[o] = base_scale[o] 2^-s undoes the scaling
+// in the epilogue (exact: powers of two).  Rows past `cout` are zero with scale 1.
+void build_h3(const float* wk, int cout, int K, int cout_pad, const float* base_scale, std::vector<__half>& pl, std::vector<float>& sx) {
+  pl.assign((size_t)cout_pad * 3 * K, __float2half_rn(0.f));
+  sx.assign(cout_pad, 1.f);
+  for (int o = 0; o < cout; ++o) {
+    const float* w = wk + (size_t)o * K;
+    float mx = 0.f;
+    for (int k = 0; k < K; ++k) mx = std::max(mx, fabsf(w[k]));
+    int s = 0;
+    if (mx > 0.f && std::isfinite(mx)) {
+      int e;
+      frexpf(mx, &e);                 // mx = m 2^e, m in [0.5, 1)
+      s = std::min(std::max(13 - e, -60), 60);
+    }
+    const float up = ldexpf(1.f, s), dn = ldexpf(1.f, -s);
+    __half* row = pl.data() + (size_t)o * 3 * K;
+    for (int k = 0; k < K; ++k) {
+      const float v = w[k] * up;
+      const __half a = __float2half_rn(v);
+      const float af = __half2float(a);
+      row[k] = a;
+      row[K + k] = __float2half_rn(af * (1.f / 2048.f));
+      row[2 * K + k] = __float2half_rn(v - af);
+    }
+    sx[o] = (base_scale ? base_scale[o] : 1.f) * dn;
+  }
+}
+
+int pack_h3(vltk_frcnn* h, LayerW& L, const std::vector<float>& wk, int cout, int K, int cout_pad, const float* base_scale) {
+  L.cout_pad = cout_pad;
+  std::vector<__half> pl;
+  std::vector<float> sx;
+  build_h3(wk.data(), cout, K, cout_pad, base_scale, pl, sx);
+  if (dev_alloc(h, &L.w_h3, pl.size() * 2)) return -1;
+  VLTK_CUDA(cudaMemcpy(L.w_h3, pl.data(), pl.size() * 2, cudaMemcpyHostToDevice));
+  if (upload(h, sx, &L.scale_x)) return -1;
+  return 0;
+}
+
+// exact_tc linear (fp32 out): W[cout][k_full] uses columns [0, k_used); rows padded to a multiple of 128
+int pack_h3_linear(vltk_frcnn* h, LayerW& L, const std::vector<float>& w, int cout, int k_full, int k_used,
+                   const std::vector<float>& bias) {
+  std::vector<float> wk((size_t)cout * k_used);
+  for (int o = 0; o < cout; ++o)
+    for (int k = 0; k < k_used; ++k) wk[(size_t)o * k_used + k] = w[(size_t)o * k_full + k];
+  if (pack_h3(h, L, wk, cout, k_used, round_up(cout, 128), nullptr)) return -1;
+  std::vector<float> sh(L.cout_pad, 0.f);
+  for (int o = 0; o < cout; ++o) sh[o] = bias[o];
+  if (upload(h, sh, &L.shift)) return -1;
+  return 0;
+}
+
 // Packs a reference-layout weight [cout][cin][k][k] into the kernel layouts.
 //   round_bf16: weights are rounded to bf16 values (bf16 mode), so the SIMT cross-check and the
 //   tensor-core kernel see identical operands.
@@ -161,6 +222,14 @@ int pack_layer(vltk_frcnn* h, LayerW& L, const std::string& name, int cin, int c
     for (int o = 0; o < cout; ++o) sh[o] = (*b)[o];
   }
   if (bn || bias) { if (upload(h, sh, &L.shift)) return -1; }
+  if (h->use_tcx && h->pack_x && cin % 64 == 0) {
+    const int K = k * k * cin;
+    std::vector<float> wk((size_t)cout * K);
+    for (int o = 0; o < cout; ++o)
+      for (int c = 0; c < cin; ++c)
+        for (int t = 0; t < k * k; ++t) wk[(size_t)o * K + (size_t)t * cin + c] = (*w)[((size_t)o * cin + c) * k * k + t];
+    if (pack_h3(h, L, wk, cout, K, round_up(cout, 64), bn ? sc.data() : nullptr)) return -1;
+  }
   return 0;
 }
 
@@ -239,7 +308,7 @@ struct Bump {  // workspace carve-up, 256-byte aligned
   }
 };
 
-size_t esz(DType d) { return d == DT_F32 ? 4 : 2; }
+size_t esz(DType d) { return d == DT_BF16 ? 2 : 4; }   // per channel element (DT_H2: two fp16 planes)
 
 struct Shapes {
   int N, H, W, Hs, Ws, Hp, Wp, h2, w2, h3, w3, h4, w4, R, P, K;
@@ -266,6 +335,8 @@ int run_conv(vltk_frcnn* h, const LayerW& L, const void* x, DType xdt, int N, in
   ConvProblem p;
   memset(&p, 0, sizeof(p));
   p.x = x; p.ldx = L.cin_pad; p.y = y; p.ldy = ldy; p.residual = residual; p.ldr = ldr;
+  if (xdt == DT_H2) p.ldx = 2 * L.cin;                 // two planes per pixel row (conv.cuh)
+  if (ydt == DT_H2) { p.ldy = 2 * ldy; p.ldr = 2 * ldr; }
   p.N = N; p.H = H; p.W = W; p.Cin = L.cin_pad;
   p.KH = p.KW = L.k; p.stride = L.stride; p.pad = L.pad; p.dil = L.dil;
   p.OH = (H + 2 * L.pad - (L.dil * (L.k - 1) + 1)) / L.stride + 1;
@@ -276,6 +347,7 @@ int run_conv(vltk_frcnn* h, const LayerW& L, const void* x, DType xdt, int N, in
   if (ow_out) *ow_out = p.OW;
   h->launches++;
   const bool tc = h->use_tc && L.w_nk && xdt == DT_BF16 && ydt == DT_BF16;
+  const bool tcx = h->use_tcx && L.w_h3 && xdt == DT_H2;
   vltk_frcnn::ProfRec rec;
   if (h->profiling) {
     auto get_event = [&]() {
@@ -284,7 +356,7 @@ int run_conv(vltk_frcnn* h, const LayerW& L, const void* x, DType xdt, int N, in
       else cudaEventCreate(&e);
       return e;
     };
-    rec.kind = tc ? 0 : 1;
+    rec.kind = (tc || tcx) ? 0 : 1;
     rec.M = (int64_t)N * p.OH * p.OW; rec.K = L.k * L.k * L.cin; rec.Cout = L.cout;
     if (cc) rec.K += cc->Cin2;                           // K-concatenated second GEMM (projection shortcut)
     rec.flops = 2.0 * (double)rec.M * rec.K * rec.Cout;  // algorithmic: unpadded cin/cout
@@ -292,7 +364,15 @@ int run_conv(vltk_frcnn* h, const LayerW& L, const void* x, DType xdt, int N, in
     cudaEventRecord(rec.e0, st);
   }
   if ((pool || cc) && !tc) { set_error("internal: fused mean-pool / concat need the tensor-core path"); return -2; }
-  int rc = tc ? conv_tc_launch(p, L.w_nk, L.cout_pad, &h->tmaps, st, nullptr, pool, cc) : conv_simt_launch(p, L.w_kn, L.ldw, st);
+  int rc;
+  if (tcx) {
+    VLTK_CHECK(ydt == DT_H2, "internal: run_conv on split-fp16 input writes split-fp16");
+    p.scale = L.scale_x;
+    rc = conv_tcx_launch(p, L.w_h3, L.cout_pad, &h->tmaps, st);
+  } else {
+    VLTK_CHECK(xdt != DT_H2 && ydt != DT_H2, "internal: layer %dx%d k%d has no exact_tc weights", L.cin, L.cout, L.k);
+    rc = tc ? conv_tc_launch(p, L.w_nk, L.cout_pad, &h->tmaps, st, nullptr, pool, cc) : conv_simt_launch(p, L.w_kn, L.ldw, st);
+  }
   if (h->profiling) {
     cudaEventRecord(rec.e1, st);
     h->prof.push_back(rec);
@@ -401,8 +481,8 @@ __global__ void widen_bf16_kernel(const bf16* __restrict__ x, float* __restrict_
   if (i < n) y[i] = __bfloat162float(x[i]);
 }
 
-void tap(vltk_frcnn* h, const char* name, const void* p, int64_t n, DType dt) {
-  Tap t; t.p = p; t.n = n; t.dt = dt;
+void tap(vltk_frcnn* h, const char* name, const void* p, int64_t n, DType dt, int c = 0) {
+  Tap t; t.p = p; t.n = n; t.dt = dt; t.c = c;
   h->taps[name] = t;
 }
 
@@ -426,7 +506,7 @@ int vltk_frcnn_create(const vltk_frcnn_config* cfg, int device, vltk_frcnn_t** o
   VLTK_CHECK(device >= 0 && device < ndev, "create: device %d out of range", device);
   VLTK_CHECK(cfg->rpn_pre_nms_topk >= 1 && cfg->rpn_pre_nms_topk <= 8192, "rpn_pre_nms_topk must be in 1..8192");
   VLTK_CHECK(cfg->rpn_post_nms_topk >= 1 && cfg->rpn_post_nms_topk <= 512, "rpn_post_nms_topk must be in 1..512");
-  VLTK_CHECK(cfg->mode == VLTK_MODE_FP32 || cfg->mode == VLTK_MODE_BF16, "unknown mode %d", cfg->mode);
+  VLTK_CHECK(cfg->mode == VLTK_MODE_FP32 || cfg->mode == VLTK_MODE_BF16 || cfg->mode == VLTK_MODE_EXACT_TC, "unknown mode %d", cfg->mode);
   VLTK_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
   VLTK_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -434,7 +514,8 @@ int vltk_frcnn_create(const vltk_frcnn_config* cfg, int device, vltk_frcnn_t** o
   vltk_frcnn* h = new vltk_frcnn();
   h->cfg = *cfg;
   h->device = device;
-  h->act = cfg->mode == VLTK_MODE_BF16 ? DT_BF16 : DT_F32;
+  h->act = cfg->mode == VLTK_MODE_BF16 ? DT_BF16 : (cfg->mode == VLTK_MODE_EXACT_TC ? DT_H2 : DT_F32);
+  h->use_tcx = cfg->mode == VLTK_MODE_EXACT_TC;
   const char* notc = getenv("VLTK_NO_TC");
   h->use_tc = cfg->mode == VLTK_MODE_BF16 && !(notc && notc[0] == '1');
   *out = h;
@@ -515,12 +596,13 @@ int vltk_frcnn_finalize(vltk_frcnn_t* h) {
     for (int o = 0; o < 4 * A; ++o) sh[o] = (*bd)[o];
     for (int o = 0; o < A; ++o) sh[4 * A + o] = (*bo)[o];
     if (upload(h, kn, &L.w_kn) || upload(h, sh, &L.shift)) return -1;
-    if (tc && hid % 64 == 0) {   // tensor pipe: exact bf16 activations x (w_hi + w_lo), fp32 out, rows padded to 64
+    if ((tc || h->use_tcx) && hid % 64 == 0) {   // tensor pipe, fp32 out: bf16 mode exact bf16 activations x (w_hi + w_lo), rows padded to 64; exact_tc three fp16 planes, rows padded to 128
       std::vector<float> wrow((size_t)5 * A * hid), brow(5 * A);
       for (int o = 0; o < 4 * A; ++o) { brow[o] = (*bd)[o]; for (int k = 0; k < hid; ++k) wrow[(size_t)o * hid + k] = (*wd)[(size_t)o * hid + k]; }
       for (int o = 0; o < A; ++o) { brow[4 * A + o] = (*bo)[o]; for (int k = 0; k < hid; ++k) wrow[(size_t)(4 * A + o) * hid + k] = (*wo)[(size_t)o * hid + k]; }
       float* simt_shift = L.shift;
-      if (pack_split_linear(h, L, wrow, 5 * A, hid, hid, brow)) return -1;   // sets w_nk / w_lo / cout_pad and a padded shift
+      if (h->use_tcx ? pack_h3_linear(h, L, wrow, 5 * A, hid, hid, brow)
+                     : pack_split_linear(h, L, wrow, 5 * A, hid, hid, brow)) return -1;   // sets the planes / cout_pad and a padded shift
       h->rpn_head_shift_simt = simt_shift;
     }
   }
@@ -531,6 +613,7 @@ int vltk_frcnn_finalize(vltk_frcnn_t* h) {
   }
   // predictor (frcnn.py:1726-1740): always fp32 — its argmaxes decide ids
   const int NC = c.num_classes, NA = c.num_attrs, E = D / 8, HA = D / 4;
+  h->pack_x = false;
   if (pack_layer(h, h->cls_score, "roi_heads.box_predictor.cls_score", D, NC + 1, 1, 1, 0, 1, 0, false, true, false, false)) return -1;
   if (pack_layer(h, h->bbox_pred, "roi_heads.box_predictor.bbox_pred", D, NC * 4, 1, 1, 0, 1, 0, false, true, false, false)) return -1;
   if (pack_layer(h, h->attr_score, "roi_heads.box_predictor.attr_score", HA, NA + 1, 1, 1, 0, 1, 0, false, true, false, false)) return -1;
@@ -553,6 +636,16 @@ int vltk_frcnn_finalize(vltk_frcnn_t* h) {
       }
     if (upload(h, kn, &L.w_kn) || upload(h, sh, &L.shift) || upload(h, tab, &h->attr_table)) return -1;
     if (tc && pack_split_linear(h, L, *w, HA, D + E, D, *b)) return -1;
+    if (h->use_tcx && pack_h3_linear(h, L, *w, HA, D + E, D, *b)) return -1;
+  }
+  if (h->use_tcx) {   // cls_score / attr_score on the tensor pipe (fp32-faithful); bbox_pred stays on the CUDA cores
+    const auto* wc = find(h, "roi_heads.box_predictor.cls_score.weight", (int64_t)(NC + 1) * D);
+    const auto* bc = find(h, "roi_heads.box_predictor.cls_score.bias", NC + 1);
+    const auto* wa = find(h, "roi_heads.box_predictor.attr_score.weight", (int64_t)(NA + 1) * HA);
+    const auto* ba = find(h, "roi_heads.box_predictor.attr_score.bias", NA + 1);
+    if (!wc || !bc || !wa || !ba) return -2;
+    if (pack_h3_linear(h, h->cls_score, *wc, NC + 1, D, D, *bc)) return -1;
+    if (pack_h3_linear(h, h->attr_score, *wa, NA + 1, HA, HA, *ba)) return -1;
   }
   if (tc) {
     const auto* wc = find(h, "roi_heads.box_predictor.cls_score.weight", (int64_t)(NC + 1) * D);
@@ -612,8 +705,10 @@ static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void*
   p[B_ARGMAX] = b.take((size_t)NR * 4);
   p[B_TG] = b.take((size_t)NR * (D / 4) * 4); p[B_AH] = b.take((size_t)NR * (D / 4) * 4);
   p[B_ATTR] = b.take((size_t)NR * ld(h->attr_score) * 4);
-  p[B_FHI] = b.take((size_t)NR * D * 2); p[B_FLO] = b.take((size_t)NR * D * 2);
-  p[B_AHHI] = b.take((size_t)NR * (D / 4) * 2); p[B_AHLO] = b.take((size_t)NR * (D / 4) * 2);
+  // predictor inputs: bf16 hi / lo planes (bf16 mode) or one split-fp16 tensor in B_FHI / B_AHHI (exact_tc)
+  const size_t pe = h->use_tcx ? 4 : 2;
+  p[B_FHI] = b.take((size_t)NR * D * pe); p[B_FLO] = b.take((size_t)NR * D * 2);
+  p[B_AHHI] = b.take((size_t)NR * (D / 4) * pe); p[B_AHLO] = b.take((size_t)NR * (D / 4) * 2);
   p[B_STEMA] = b.take(h->stem_tc.w_nk ? (size_t)N * s.Hs * s.Ws * 192 * 2 : 0);
   p[B_PARTIAL] = b.take(h->use_tc ? conv_tc_pool_partial_bytes((int64_t)NR * PP, D) : 0);
   p[B_NMSDONE] = b.take((size_t)N * 4);
@@ -686,9 +781,11 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
     h->launches++;
     if (conv_tc_launch(q, L.w_nk, L.cout_pad, &h->tmaps, st)) return -1;
     if (h->profiling) { cudaEventRecord(rec.e1, st); h->prof.push_back(rec); }
-  } else if (run_conv(h, h->stem, p[B_IN4], DT_F32, n, height, width, p[B_STEM], d, h->stem.ldw, nullptr, 0, 1, st)) return -1;
+  } else if (run_conv(h, h->stem, p[B_IN4], DT_F32, n, height, width, p[B_STEM], d == DT_H2 ? DT_F32 : d, h->stem.ldw, nullptr, 0, 1, st)) return -1;
   { StageTimer t(h, K_MAXPOOL, ((double)n * s.Hs * s.Ws + (double)n * s.Hp * s.Wp) * c.stem_out_channels * esz(d), st);
-    if (maxpool3x3s2_ceil(p[B_STEM], p[B_POOL], d, n, s.Hs, s.Ws, c.stem_out_channels, s.Hp, s.Wp, st)) return -1; }
+    // exact_tc: the 3-channel stem runs in fp32 on the CUDA cores (0.14 % of the FLOPs); the pool splits its output
+    if (d == DT_H2 ? maxpool3x3s2_ceil_f32_to_h2((const float*)p[B_STEM], p[B_POOL], n, s.Hs, s.Ws, c.stem_out_channels, s.Hp, s.Wp, st)
+                   : maxpool3x3s2_ceil(p[B_STEM], p[B_POOL], d, n, s.Hs, s.Ws, c.stem_out_channels, s.Hp, s.Wp, st)) return -1; }
   h->launches++;
   const void* x = p[B_POOL];
   int ch = s.Hp, cw = s.Wp;
@@ -701,7 +798,7 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   // output row is computed from its own input rows only, so the result is bit-identical to the unsplit order.
   // VLTK_SPLIT_BACKBONE=0 restores the single-stream order.
   static const bool want_split = [] { const char* e = getenv("VLTK_SPLIT_BACKBONE"); return !(e && e[0] == '0'); }();
-  const bool split = want_split && h->use_tc && n >= 2;
+  const bool split = want_split && (h->use_tc || h->use_tcx) && n >= 2;
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   if (split) {
@@ -764,7 +861,7 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   VLTK_CHECK(ch == s.h4 && cw == s.w4, "internal: res4 shape mismatch");
   const void* res4 = x;
   const int C4 = c.res2_out_channels * 4, A = c.num_anchors;
-  tap(h, "res4", res4, (int64_t)n * s.h4 * s.w4 * C4, d);
+  tap(h, "res4", res4, (int64_t)n * s.h4 * s.w4 * C4, d, C4);
 
   // ---- RPN head + proposal selection (frcnn.py:1561-1572, 264-390)
   if (run_conv(h, h->rpn_conv, res4, d, n, s.h4, s.w4, p[B_RPNH], d, h->rpn_conv.ldw, nullptr, 0, 1, st)) return -1;
@@ -787,6 +884,24 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
     }
     h->launches++;
     if (conv_tc_launch(q, L.w_nk, L.cout_pad, &h->tmaps, st, &sp)) return -1;
+    if (h->profiling) { cudaEventRecord(rec.e1, st); h->prof.push_back(rec); }
+  } else if (h->use_tcx && h->rpn_head.w_h3 && d == DT_H2) {
+    // 1x1 head on the tensor pipe, fp32-faithful, fp32 rows of cout_pad (= 128) columns
+    const LayerW& L = h->rpn_head;
+    const int64_t Mh = (int64_t)n * s.h4 * s.w4;
+    ldh = L.cout_pad;
+    ConvProblem q;
+    memset(&q, 0, sizeof(q));
+    q.x = p[B_RPNH]; q.ldx = 2 * L.cin_pad; q.y = p[B_HEAD]; q.ldy = ldh; q.N = (int)Mh; q.H = q.W = q.OH = q.OW = 1;
+    q.Cin = L.cin_pad; q.Cout = L.cout_pad; q.KH = q.KW = 1; q.stride = 1; q.dil = 1; q.scale = L.scale_x; q.shift = L.shift; q.relu = 0;
+    q.in_dtype = DT_H2; q.out_dtype = DT_F32;
+    vltk_frcnn::ProfRec rec;
+    if (h->profiling) {
+      rec.kind = 0; rec.M = Mh; rec.K = L.cin; rec.Cout = L.cout; rec.flops = 2.0 * (double)Mh * L.cin * L.cout;
+      cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1); cudaEventRecord(rec.e0, st);
+    }
+    h->launches++;
+    if (conv_tcx_launch(q, L.w_h3, L.cout_pad, &h->tmaps, st)) return -1;
     if (h->profiling) { cudaEventRecord(rec.e1, st); h->prof.push_back(rec); }
   } else {
     LayerW L = h->rpn_head;
@@ -823,8 +938,10 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   // ---- ROI head: RoIPool -> res5 -> mean (frcnn.py:1387-1403)
   const int NR = n * s.R, PP = s.P * s.P, D = c.res2_out_channels * 8;
   { StageTimer t(h, K_ROIPOOL, ((double)n * s.h4 * s.w4 * C4 + (double)n * s.R * s.P * s.P * C4) * esz(d), st);
-    if (roi_pool(res4, d, n, s.h4, s.w4, C4, (const float*)p[B_PROP], (const int*)p[B_COUNT], s.R, s.P,
-                 1.0f / (float)c.anchor_stride, p[B_POOLED], st)) return -1; }
+    if (d == DT_H2 ? roi_pool_h2(res4, n, s.h4, s.w4, C4, (const float*)p[B_PROP], (const int*)p[B_COUNT], s.R, s.P,
+                                 1.0f / (float)c.anchor_stride, p[B_POOLED], st)
+                   : roi_pool(res4, d, n, s.h4, s.w4, C4, (const float*)p[B_PROP], (const int*)p[B_COUNT], s.R, s.P,
+                              1.0f / (float)c.anchor_stride, p[B_POOLED], st)) return -1; }
   h->launches++;
   x = p[B_POOLED];
   void* r5[2] = {p[B_R5A], p[B_R5B]};
@@ -848,7 +965,7 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   }
   if (!fuse_mean) {
     StageTimer t(h, K_MEAN, (double)NR * PP * D * esz(d) + (double)NR * D * 4, st);
-    if (mean_rows(x, (float*)p[B_FEATS], d, NR, PP, D, st)) return -1;
+    if (d == DT_H2 ? mean_rows_h2(x, (float*)p[B_FEATS], NR, PP, D, st) : mean_rows(x, (float*)p[B_FEATS], d, NR, PP, D, st)) return -1;
   }
   h->launches++;
   tap(h, "feats", p[B_FEATS], (int64_t)NR * D, DT_F32);
@@ -856,10 +973,39 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   // ---- predictor (frcnn.py:1726-1740): fp32 on the CUDA cores, or fp32-faithful split-bf16 (hi*hi +
   //      lo*hi + hi*lo, fp32 accumulate and fp32 logits) on the tensor pipe
   const bool ptc = h->use_tc && h->cls_score.w_lo;
-  const int ldc = ptc ? h->cls_score.cout_pad : h->cls_score.ldw;
+  const bool ptx = h->use_tcx && h->cls_score.w_h3 && h->fc_attr.w_h3 && h->attr_score.w_h3;
+  const int ldc = (ptc || ptx) ? h->cls_score.cout_pad : h->cls_score.ldw;
   const int ldb = ptc ? h->bbox_pred.cout_pad : h->bbox_pred.ldw;
-  const int lda = ptc ? h->attr_score.cout_pad : h->attr_score.ldw;
-  if (ptc) {
+  const int lda = (ptc || ptx) ? h->attr_score.cout_pad : h->attr_score.ldw;
+  if (ptx) {
+    // exact_tc: fp32-faithful GEMMs on split-fp16 inputs (conv_tcx.cu); bbox_pred in fp32 on the CUDA cores
+    auto h2_gemm = [&](const LayerW& L, const void* xh2, int K, void* y, int relu) -> int {
+      ConvProblem q;
+      memset(&q, 0, sizeof(q));
+      q.x = xh2; q.ldx = 2 * K; q.y = y; q.ldy = L.cout_pad; q.N = NR; q.H = q.W = q.OH = q.OW = 1; q.Cin = K;
+      q.Cout = L.cout_pad; q.KH = q.KW = 1; q.stride = 1; q.dil = 1; q.scale = L.scale_x; q.shift = L.shift; q.relu = relu;
+      q.in_dtype = DT_H2; q.out_dtype = DT_F32;
+      h->launches++;
+      vltk_frcnn::ProfRec rec;
+      if (h->profiling) {
+        rec.kind = 0; rec.M = NR; rec.K = K; rec.Cout = L.cout; rec.flops = 2.0 * NR * (double)K * L.cout;
+        cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1); cudaEventRecord(rec.e0, st);
+      }
+      int rc = conv_tcx_launch(q, L.w_h3, L.cout_pad, &h->tmaps, st);
+      if (h->profiling) { cudaEventRecord(rec.e1, st); h->prof.push_back(rec); }
+      return rc;
+    };
+    { StageTimer t(h, K_GLUE, (double)NR * D * 8.0, st);
+      if (split_f32_h2((const float*)p[B_FEATS], nullptr, 0, p[B_FHI], NR, D, st)) return -1; }
+    if (h2_gemm(h->cls_score, p[B_FHI], D, p[B_CLS], 0)) return -1;
+    if (run_conv(h, h->bbox_pred, p[B_FEATS], DT_F32, NR, 1, 1, p[B_BBOX], DT_F32, ldb, nullptr, 0, 0, st)) return -1;
+    if (row_argmax((const float*)p[B_CLS], ldc, NR, c.num_classes + 1, (int*)p[B_ARGMAX], st)) return -1;
+    if (gather_rows(h->attr_table, D / 4, (const int*)p[B_ARGMAX], NR, D / 4, (float*)p[B_TG], D / 4, st)) return -1;
+    if (h2_gemm(h->fc_attr, p[B_FHI], D, p[B_AH], 0)) return -1;      // W[:, :D] x + b
+    if (split_f32_h2((const float*)p[B_AH], (const float*)p[B_TG], 1, p[B_AHHI], NR, D / 4, st)) return -1;   // + T[argmax], ReLU, split
+    if (h2_gemm(h->attr_score, p[B_AHHI], D / 4, p[B_ATTR], 0)) return -1;
+    h->launches += 4;
+  } else if (ptc) {
     auto split_gemm = [&](const LayerW& L, const void* xhi, const void* xlo, int K, void* y, int relu) -> int {
       ConvProblem q;
       memset(&q, 0, sizeof(q));
@@ -946,7 +1092,8 @@ int64_t vltk_frcnn_debug_read(vltk_frcnn_t* h, const char* name, float* dst, int
   } else {
     float* tmp = nullptr;
     VLTK_CUDA(cudaMalloc(&tmp, (size_t)t.n * 4));
-    widen_bf16_kernel<<<(unsigned)ceil_div64(t.n, 256), 256>>>((const bf16*)t.p, tmp, t.n);
+    if (t.dt == DT_H2) widen_h2(t.p, tmp, t.n / t.c, t.c, 0);
+    else widen_bf16_kernel<<<(unsigned)ceil_div64(t.n, 256), 256>>>((const bf16*)t.p, tmp, t.n);
     cudaError_t e = cudaMemcpy(dst, tmp, (size_t)t.n * 4, cudaMemcpyDeviceToHost);
     cudaFree(tmp);
     VLTK_CUDA(e);
@@ -1013,6 +1160,45 @@ int vltk_conv2d_nhwc(const void* x, const float* weight, const float* scale, con
   p.Cout = cout; p.scale = scale; p.shift = shift; p.relu = relu; p.in_dtype = d; p.out_dtype = d;
   const int K = kh * kw * cin, K_pad = round_up(K, 16);
   int rc = 0;
+  if (mode == VLTK_MODE_EXACT_TC) {
+    // fp32 NHWC tensors in and out; split / widened around the split-fp16 tensor-core kernel.  use_tc = 2: fp32 rows out
+    // straight from the kernel's fp32 epilogue (the predictor / RPN-head form; cout % 128 == 0, no residual).
+    VLTK_CHECK(cin % 64 == 0 && cout % 64 == 0, "conv2d(exact_tc): cin and cout must be multiples of 64");
+    const bool f32out = use_tc == 2;
+    const int64_t Min = (int64_t)n * hh * ww, Mout = (int64_t)n * p.OH * p.OW;
+    std::vector<float> hw((size_t)cout * K), wk((size_t)cout * K), hs(cout, 1.f);
+    VLTK_CUDA(cudaStreamSynchronize(st));
+    VLTK_CUDA(cudaMemcpy(hw.data(), weight, hw.size() * 4, cudaMemcpyDeviceToHost));
+    if (scale) VLTK_CUDA(cudaMemcpy(hs.data(), scale, (size_t)cout * 4, cudaMemcpyDeviceToHost));
+    for (int o = 0; o < cout; ++o)
+      for (int c = 0; c < cin; ++c)
+        for (int t = 0; t < kh * kw; ++t) wk[(size_t)o * K + (size_t)t * cin + c] = hw[((size_t)o * cin + c) * kh * kw + t];
+    std::vector<__half> pl;
+    std::vector<float> sx;
+    build_h3(wk.data(), cout, K, cout, hs.data(), pl, sx);
+    void *w3 = nullptr, *xh = nullptr, *yh = nullptr, *rh = nullptr;
+    float* dsx = nullptr;
+    VLTK_CUDA(scratch.get(&w3, pl.size() * 2));
+    VLTK_CUDA(scratch.get(&dsx, sx.size() * 4));
+    VLTK_CUDA(scratch.get(&xh, (size_t)Min * cin * 4));
+    VLTK_CUDA(scratch.get(&yh, (size_t)Mout * cout * 4));
+    VLTK_CUDA(cudaMemcpyAsync(w3, pl.data(), pl.size() * 2, cudaMemcpyHostToDevice, st));
+    VLTK_CUDA(cudaMemcpyAsync(dsx, sx.data(), sx.size() * 4, cudaMemcpyHostToDevice, st));
+    rc = split_f32_h2((const float*)x, nullptr, 0, xh, Min, cin, st);
+    if (!rc && residual) {
+      VLTK_CUDA(scratch.get(&rh, (size_t)Mout * cout * 4));
+      rc = split_f32_h2((const float*)residual, nullptr, 0, rh, Mout, cout, st);
+    }
+    p.x = xh; p.ldx = 2 * cin; p.in_dtype = DT_H2; p.scale = dsx;
+    if (f32out) { p.out_dtype = DT_F32; p.ldy = cout; p.residual = nullptr; }
+    else { p.y = yh; p.ldy = 2 * cout; p.out_dtype = DT_H2; p.residual = rh; p.ldr = 2 * cout; }
+    TensorMapCache cache;
+    if (!rc) rc = conv_tcx_launch(p, w3, cout, &cache, st);
+    if (!rc && !f32out) rc = widen_h2(yh, (float*)y, Mout, cout, st);
+    cudaStreamSynchronize(st);
+    if (!rc) VLTK_LAUNCH_CHECK();
+    return rc;
+  }
   if (use_tc) {
     VLTK_CHECK(d == DT_BF16 && cin % 64 == 0, "conv2d: tensor-core path needs bf16 and cin %% 64 == 0");
     const int cout_pad = round_up(cout, 64);

@@ -20,6 +20,15 @@ int preprocess_image(const uint8_t* raw, int rh, int rw, int nh, int nw, int Hm,
                      const float* mean, const float* stdv, float pad_value, float* out_nchw,
                      void* out_nhwc4, DType dt, cudaStream_t st);
 
+// ---- h2ops.cu: the same stages on split-fp16 activations (DT_H2, exact_tc mode) -----------------
+int maxpool3x3s2_ceil_f32_to_h2(const float* x, void* y, int N, int H, int W, int C, int OH, int OW, cudaStream_t st);
+int roi_pool_h2(const void* feat, int N, int H, int W, int C, const float* rois, const int* count, int R, int P,
+                float scale, void* out, cudaStream_t st);
+int mean_rows_h2(const void* x, float* y, int R, int P, int C, cudaStream_t st);
+// out[r] = split(relu?(x[r] + add?[r])) as [rows][hi(C) | lo'(C)]
+int split_f32_h2(const float* x, const float* add, int relu, void* out, int64_t rows, int C, cudaStream_t st);
+int widen_h2(const void* x, float* y, int64_t rows, int C, cudaStream_t st);
+
 // ---- rpn.cu -------------------------------------------------------------------------------
 struct RpnSelectArgs {
   const float* head;      // [N, HW, ldh] f32 RPN head output, one row per res4 pixel:

@@ -23,9 +23,11 @@ def conv2d_nhwc(x, weight, scale=None, shift=None, residual=None, stride=1, pad=
                 mode="fp32", tensor_cores=False):
     """x [N,H,W,Cin] (f32 or bf16 per `mode`), weight [Cout,Cin,k,k] f32 (reference layout);
     returns y [N,OH,OW,Cout] = act(conv(x,w)*scale + shift + residual)
-    (reference: Conv2d+BN+ReLU, frcnn.py:794-822; bottleneck add, :963-979)."""
+    (reference: Conv2d+BN+ReLU, frcnn.py:794-822; bottleneck add, :963-979).
+    mode="exact_tc": the fp32-faithful tensor-core kernel (csrc/conv_tcx.cu); tensor_cores=2 takes its fp32-output
+    epilogue (cout % 128 == 0, no residual) instead of the split-fp16 one."""
     L = _lib.lib()
-    dt = torch.float32 if mode == "fp32" else torch.bfloat16
+    dt = torch.bfloat16 if mode == "bf16" else torch.float32     # exact_tc: fp32 tensors, split / widened inside
     assert x.is_cuda and x.dtype == dt and x.is_contiguous()
     n, h, w, cin = x.shape
     cout, cin2, kh, kw = weight.shape
