@@ -154,6 +154,35 @@ def clip_boxes_(boxes: torch.Tensor, hw) -> torch.Tensor:
     return boxes
 
 
+# The restatements below (nms_np, roi_pool_np) are the CHECKER: slow Python/numpy loops, bit-exact with the compiled
+# torchvision ops (tests/test_host_logic.py).  When this file is TIMED as the CPU baseline (bench.py --impl reference,
+# cpu_baseline) the two ops are taken from torchvision itself, exactly as the reference calls them
+# (frcnn.py:30-31, 132, 383, 1179), so the baseline is not slowed down by the restatement.
+_THIRD_PARTY_OPS = False
+
+
+def use_torchvision_ops(flag: bool):
+    """True: nms / RoIPool run through torchvision.ops like the reference does (timing); False: the restatements."""
+    global _THIRD_PARTY_OPS
+    _THIRD_PARTY_OPS = bool(flag)
+
+
+def nms_keep(boxes: torch.Tensor, scores: torch.Tensor, thresh: float, max_keep: Optional[int] = None) -> torch.Tensor:
+    """Kept indices (int64 tensor, score order) of greedy NMS, cut to max_keep."""
+    if _THIRD_PARTY_OPS:
+        import torchvision
+        keep = torchvision.ops.nms(boxes.float(), scores.float(), float(thresh))
+        return keep if max_keep is None else keep[:max_keep]
+    return torch.from_numpy(nms_np(boxes.numpy(), scores.numpy(), thresh, max_keep))
+
+
+def roi_pool(feat: torch.Tensor, rois: torch.Tensor, out: int, scale: float) -> torch.Tensor:
+    if _THIRD_PARTY_OPS:
+        import torchvision
+        return torchvision.ops.RoIPool((out, out), scale)(feat, rois)
+    return roi_pool_np(feat, rois, out, scale)
+
+
 def nms_np(boxes: np.ndarray, scores: np.ndarray, thresh: float, max_keep: Optional[int] = None):
     """Greedy NMS as published for torchvision.ops.nms (CPU kernel): stable
     score-descending order; j suppressed iff IoU(i,j) > thresh; area=(x2-x1)*(y2-y1);
@@ -281,9 +310,8 @@ def rpn_select(cfg, logits_nchw, deltas_nchw, cell, image_shapes, return_debug=F
         ok = alive & ((boxes[:, 2] - boxes[:, 0]) > cfg.rpn_min_size) & \
              ((boxes[:, 3] - boxes[:, 1]) > cfg.rpn_min_size)
         pos = torch.nonzero(ok).squeeze(1)
-        keep = nms_np(boxes[pos].numpy(), sc[pos].numpy(), cfg.rpn_nms_thresh,
-                      cfg.rpn_post_nms_topk)
-        kept_pos = pos[torch.from_numpy(keep)]  # positions inside the sorted top-k list
+        keep = nms_keep(boxes[pos], sc[pos], cfg.rpn_nms_thresh, cfg.rpn_post_nms_topk)
+        kept_pos = pos[keep]  # positions inside the sorted top-k list
         out.append((boxes[kept_pos], sc[kept_pos]))
         dbg.append({"topk_idx": idx, "topk_boxes": boxes, "topk_scores": sc, "kept_pos": kept_pos})
     return (out, dbg) if return_debug else out
@@ -315,10 +343,9 @@ def roi_outputs(cfg, obj_logits, attr_logits, box_deltas, proposals: Sequence[to
         clip_boxes_(boxes, image_shapes[i])
         keep = None
         for thr in cfg.nms_thresh_test:
-            keep = nms_np(boxes.numpy(), max_scores.numpy(), thr)[: cfg.max_detections]
+            keep = nms_keep(boxes, max_scores, thr)[: cfg.max_detections]
             if cfg.min_detections <= len(keep) <= cfg.max_detections:
                 break
-        keep = torch.from_numpy(keep)
         kb = boxes[keep].clone()
         if scales_yx is not None:
             kb[:, 0::2] *= scales_yx[i][1]
@@ -355,7 +382,7 @@ def forward(sd: Dict[str, torch.Tensor], cfg, images: torch.Tensor, image_shapes
     boxes = [p[0] for p in props]
     rois = torch.cat([torch.cat((torch.full((len(b), 1), float(i)), b), 1)
                       for i, b in enumerate(boxes)], 0)
-    pooled = roi_pool_np(res4, rois, cfg.pooler_resolution, 1.0 / cfg.anchor_stride)
+    pooled = roi_pool(res4, rois, cfg.pooler_resolution, 1.0 / cfg.anchor_stride)
     feats = res5_head(sd, pooled, chunk=res5_chunk)
     obj_logits, attr_logits, box_deltas = box_predictor(sd, feats)
     out = roi_outputs(cfg, obj_logits, attr_logits, box_deltas, boxes, feats, image_shapes,

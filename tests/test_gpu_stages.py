@@ -83,6 +83,57 @@ def test_conv_tcgen05_matches_simt_and_reference(dev, case):
     assert ((y_tc - ref).abs() <= ulp * (ref.abs() + 1e-2)).all()
 
 
+EXACT_TC_CASES = [c for c in CONV_CASES if c[3] % 64 == 0 and c[4] % 64 == 0] + [
+    (40, 14, 14, 512, 512, 3, 1, 2, 2, False, True),     # res5 conv2: K = 4608 = 18 promotion chunks, many tiles per CTA
+    (60, 14, 14, 2048, 512, 1, 1, 0, 1, False, True),    # res5.1 conv1: K = 2048
+    (2, 38, 63, 256, 1024, 1, 1, 0, 1, True, True),      # res4 conv3 + identity shortcut, BN = 128 path
+    (1, 7, 9, 512, 128, 1, 1, 0, 1, False, False),       # 63 rows: one partial tile
+]
+
+
+@pytest.mark.parametrize("case", EXACT_TC_CASES)
+def test_conv_exact_tc_is_fp32_faithful(dev, case):
+    """csrc/conv_tcx.cu (split-fp16 operands, 3 tcgen05 passes per K chunk, chunk sums promoted to fp32 registers)
+    against an fp64 convolution of the SAME fp32 inputs.  The bound is the one an fp32 FMA chain is held to, in units
+    of the reduction's magnitude: |err| <= 8 * 2^-24 * (sum |x||w|) * scale + 2^-22 |y|  (the CUDA-core fp32 kernel
+    measures 3.6 - 6.4 of those ulps on these shapes, this kernel 0.6 - 3.5: profiles/r02_exact_probe_bringup.json).
+    Also pins the fp32-output epilogue (RPN head / predictor form) where the shape allows it."""
+    from vltk_b200 import stages
+    n, h, w, cin, cout, k, s, p, d, use_res, relu = case
+    x, wt, sc, sh, res = _conv_inputs(case, dev, torch.float32)
+    y = stages.conv2d_nhwc(x, wt, sc, sh, res, s, p, d, relu, mode="exact_tc").double().cpu()
+    xd, wd = x.permute(0, 3, 1, 2).double().cpu(), wt.double().cpu()
+    scd, shd = sc.double().cpu().view(1, -1, 1, 1), sh.double().cpu().view(1, -1, 1, 1)
+    pre = (F.conv2d(xd, wd, None, s, p, d) * scd + shd).permute(0, 2, 3, 1)
+    mag = (F.conv2d(xd.abs(), wd.abs(), None, s, p, d) * scd.abs()).permute(0, 2, 3, 1)
+    if res is not None:
+        pre = pre + res.double().cpu()
+        mag = mag + res.double().cpu().abs()        # the residual is stored split too (2^-24 relative)
+    ref = F.relu(pre) if relu else pre
+    tol = 8 * 2.0 ** -24 * mag + 2.0 ** -22 * ref.abs() + 1e-30
+    assert ((y - ref).abs() <= tol).all(), float(((y - ref).abs() / tol).max())
+    if cout % 128 == 0 and not use_res:
+        y32 = stages.conv2d_nhwc(x, wt, sc, sh, None, s, p, d, relu, mode="exact_tc", tensor_cores=2).double().cpu()
+        assert ((y32 - ref).abs() <= tol).all()
+        # same accumulation, two epilogues: the split-fp16 store may only add its 2^-24 representation error
+        assert ((y32 - y).abs() <= 2.0 ** -23 * ref.abs() + 1e-30).all()
+
+
+def test_conv_exact_tc_is_deterministic_and_position_independent(dev):
+    """Every output row depends on its own input rows only, with a fixed chunk order: a tensor and the same tensor
+    embedded at another batch offset give bit-identical rows (what makes images independent of their batch
+    neighbours in exact_tc mode)."""
+    from vltk_b200 import stages
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(6, 14, 14, 256, generator=g).to(dev)
+    wt = (torch.randn(512, 256, 3, 3, generator=g) * (2.0 / 2304) ** 0.5).to(dev)
+    a = stages.conv2d_nhwc(x, wt, None, None, None, 1, 2, 2, True, mode="exact_tc")
+    b = stages.conv2d_nhwc(x, wt, None, None, None, 1, 2, 2, True, mode="exact_tc")
+    assert torch.equal(a, b)
+    part = stages.conv2d_nhwc(x[2:5].contiguous(), wt, None, None, None, 1, 2, 2, True, mode="exact_tc")
+    assert torch.equal(part, a[2:5])
+
+
 @pytest.mark.parametrize("pairs", [0, 1])
 def test_residual_ring_two_epilogue_groups_is_deterministic_under_hbm_load(dev, pairs):
     """(run on the single-CTA kernel, pairs=0, and on the CTA-pair kernel, whose ring is group-private, pairs=1)

@@ -149,3 +149,23 @@ def test_oracle_ignorey_rules():
     assert out[2].tolist() == [0., 60., 5., 50.]
     assert out[3].tolist() == [0., 70., 5., 95.]
     assert out[4].tolist() == [0., 5., 5., 40.]
+
+
+def test_oracle_timing_path_with_torchvision_ops_equals_the_restatement():
+    """bench.py times the oracle with nms / RoIPool taken from torchvision itself (what the reference calls,
+    frcnn.py:132, 383, 1179) instead of the slow restatements: both paths must give identical outputs."""
+    from oracle import cases
+    cfg, wseed, raws = cases.case_inputs("tiny")
+    sd = synthetic.make_state_dict(FRCNNConfig(), wseed)
+    images, sizes, scales = O.preprocess(cfg, raws)
+    a = O.forward(sd, cfg, images, sizes, scales)
+    O.use_torchvision_ops(True)
+    try:
+        b = O.forward(sd, cfg, images, sizes, scales, res5_chunk=1 << 30)
+    finally:
+        O.use_torchvision_ops(False)
+    for k in ("keep", "obj_ids", "attr_ids"):
+        assert all(torch.equal(x, y) for x, y in zip(a[k], b[k])), k
+    for k in ("boxes", "roi_features", "obj_probs"):
+        for x, y in zip(a[k], b[k]):
+            np.testing.assert_allclose(x.numpy(), y.numpy(), rtol=1e-5, atol=1e-5)

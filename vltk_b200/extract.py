@@ -31,13 +31,11 @@ def _rows(ids: Sequence[str], dense: Dict[str, np.ndarray], sizes, scales_yx):
     """Dense model outputs -> column arrays, reference columns first."""
     n = len(ids)
     boxes = np.asarray(dense["boxes"], np.float32)
-    # adapter epilogue: round(boxes / wh_scale) (adapters/frcnn.py:57, utils/adapters.py:205-216);
-    # boxes are already multiplied by scales_yx, dividing returns resized-image pixels
-    sc = np.asarray(scales_yx, np.float32).reshape(n, 2)
-    box = boxes.copy()
-    box[:, :, 0::2] /= sc[:, None, 1:2]
-    box[:, :, 1::2] /= sc[:, None, 0:1]
-    box = np.round(box)
+    # adapter epilogue (adapters/frcnn.py:50-57, utils/adapters.py:205-216): the reference calls the model WITHOUT
+    # scales_yx (boxes in resized-image pixels) and writes round(boxes * 1/wh_scale) with wh_scale = resized/raw
+    # (processing/image.py:128-135), i.e. RAW-image pixels.  `boxes` here was already multiplied by
+    # scales_yx = raw/resized by the model (frcnn.py:1280-1283), so it is in that frame: only the rounding is left.
+    box = np.round(boxes)
     cols = {
         "imgid": np.asarray([str(i) for i in ids], dtype=object),
         "attr_ids": np.asarray(dense["attr_ids"]).astype(np.float32),
