@@ -162,6 +162,18 @@ int vltk_conv2d_dual_nhwc(const void* x, const float* weight, const void* x2, co
  * produce bit-identical outputs.  Always returns 0. */
 int vltk_conv_tc_set_cta_pairs(int min_pixels, int residual_layers);
 
+/* One PART of the model through the engine's own layers, weights and arithmetic mode, on caller-provided DEVICE fp32
+ * tensors (converted to / from the mode's activation type inside): the teacher-forced stage tests feed the oracle's
+ * stage input and compare the stage output.
+ *   part 0   BasicStem (frcnn.py:872-879): x = images NCHW [n,3,hh,ww] -> y = pooled NHWC [n,Hp,Wp,64]
+ *   part 2-4 res2 / res3 / res4 (frcnn.py:963-979, 1076-1090): x NHWC [n,hh,ww,cin] -> y NHWC [n,oh,ow,cout];
+ *            only blocks [block_begin, block_end) of the stage run (block_end < 0: to the end)
+ *   part 5   RPNHead (frcnn.py:1561-1572): x = res4 NHWC [n,hh,ww,1024] -> y = fp32 rows [n*hh*ww, ld]:
+ *            columns [0,4A) anchor deltas (a*4+coord), [4A,5A) objectness
+ * out_dims receives {oh, ow, channels (ld for part 5)}; y_cap = capacity of y in floats.  Synchronises. */
+int vltk_frcnn_run_part(vltk_frcnn_t* h, int part, int block_begin, int block_end, const float* x, int n, int hh, int ww,
+                        float* y, int64_t y_cap, int32_t* out_dims, void* stream);
+
 /* Pipeline trace of the single-CTA tcgen05 kernel (diagnosis only; tools/tc_trace.py).  In a library built with
  * VLTK_TRACE=1 csrc/build.sh, the following conv launches make CTA `cta` append (tag, clock64) records per role
  * (0 TMA producer, 1 MMA issuer, 2 residual producer, 3/4 the two epilogue groups) to dev_buf, a DEVICE array of

@@ -115,6 +115,73 @@ def box_predictor(sd, feats):
     return scores, attr, deltas
 
 
+# ------------------------------------------------- bf16-operand emulation ("bf16op")
+# What the bf16 tensor-core mode computes, restated on the CPU: operands rounded to bf16, fp32 accumulation, the
+# frozen BN as y = acc * scale + shift with the engine's folded constants, the sum rounded to bf16 on store.  The only
+# differences left between this and the GPU are the fp32 summation order and the occasional bf16 rounding flip it
+# causes, so teacher-forced stage tests can hold the bf16 kernels to a few bf16 ulps instead of a statistical bound.
+def rb(t: torch.Tensor) -> torch.Tensor:
+    """round-to-nearest-even to bf16, kept in fp32"""
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def bn_fold(sd, n):
+    """frozen BN (eps 1e-5, frcnn.py:163-173) as y = x * scale + shift, fp32 like the engine's pack_layer"""
+    scale = sd[n + ".weight"] * (1.0 / torch.sqrt(sd[n + ".running_var"] + BN_EPS))
+    return scale, sd[n + ".bias"] - sd[n + ".running_mean"] * scale
+
+
+def conv_bn_bf16(sd, prefix, x, stride=1, pad=0, dil=1, relu=False, residual=None):
+    """Conv2d + frozen BN (+ residual) (+ ReLU) the way conv_tc computes it; x (and residual) hold bf16 values."""
+    acc = F.conv2d(x, rb(sd[prefix + ".weight"]), None, stride, pad, dil)
+    scale, shift = bn_fold(sd, prefix + ".norm")
+    y = torch.addcmul(shift.view(1, -1, 1, 1), acc, scale.view(1, -1, 1, 1))
+    if residual is not None:
+        y = y + residual
+    return rb(F.relu_(y) if relu else y)
+
+
+def bottleneck_bf16(sd, prefix, x, stride, dil):
+    """BottleneckBlock.forward (frcnn.py:963-979) in the bf16 mode's arithmetic.  Projection blocks run conv3 and the
+    shortcut as ONE K-concatenated GEMM with both BN scales folded into the bf16 weights (csrc/conv_tc.cuh TcConcat)."""
+    t1 = conv_bn_bf16(sd, prefix + ".conv1", x, stride=stride, relu=True)
+    t2 = conv_bn_bf16(sd, prefix + ".conv2", t1, pad=dil, dil=dil, relu=True)
+    if (prefix + ".shortcut.weight") in sd:
+        s3, b3 = bn_fold(sd, prefix + ".conv3.norm")
+        ss, bs = bn_fold(sd, prefix + ".shortcut.norm")
+        w3 = rb(s3.view(-1, 1, 1, 1) * sd[prefix + ".conv3.weight"])
+        ws = rb(ss.view(-1, 1, 1, 1) * sd[prefix + ".shortcut.weight"])
+        y = F.conv2d(t2, w3) + F.conv2d(x, ws, None, stride) + (b3 + bs).view(1, -1, 1, 1)
+        return rb(F.relu_(y))
+    return conv_bn_bf16(sd, prefix + ".conv3", t2, relu=True, residual=x)
+
+
+def stem_bf16(sd, images):
+    """BasicStem (frcnn.py:872-879): the bf16 mode rounds the fp32 pixels to bf16 in its im2col rows."""
+    x = conv_bn_bf16(sd, "backbone.stem.conv1", rb(images), stride=2, pad=3, relu=True)
+    return F.max_pool2d(x, kernel_size=3, stride=2, padding=0, ceil_mode=True)
+
+
+def stage_bf16(sd, name, x, blocks=None):
+    """one residual stage (`res2` | `res3` | `res4`), or its blocks [blocks[0], blocks[1]), on a bf16-valued NCHW tensor"""
+    p = "backbone." + name
+    first_stride = 1 if name == "res2" else 2
+    b0, b1 = blocks or (0, _count_blocks(sd, p))
+    for b in range(b0, b1):
+        x = bottleneck_bf16(sd, f"{p}.{b}", x, first_stride if b == 0 else 1, 1)
+    return x
+
+
+def rpn_head_bf16(sd, res4):
+    """RPNHead (frcnn.py:1561-1572) in the bf16 mode: 3x3 conv on bf16 operands, hidden map stored in bf16; the 1x1
+    head keeps fp32 weights (bf16 hi + lo planes on the tensor pipe) and fp32 outputs."""
+    p = "proposal_generator.rpn_head."
+    t = rb(F.relu(F.conv2d(res4, rb(sd[p + "conv.weight"]), sd[p + "conv.bias"], 1, 1)))
+    logits = F.conv2d(t, sd[p + "objectness_logits.weight"], sd[p + "objectness_logits.bias"])
+    deltas = F.conv2d(t, sd[p + "anchor_deltas.weight"], sd[p + "anchor_deltas.bias"])
+    return logits, deltas
+
+
 # --------------------------------------------------------------------- box algebra
 def grid_anchors(cell: torch.Tensor, h: int, w: int, stride: int) -> torch.Tensor:
     """[h*w*A, 4]; index (y*w + x)*A + a, offset 0 (frcnn.py:176-197, 1463-1477)."""

@@ -92,6 +92,8 @@ SYMBOLS = {
                                      C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "vltk_roi_outputs": (C.c_int, [C.c_void_p] * 8 + [C.c_int] * 5
                          + [C.POINTER(C.c_float), C.POINTER(Knobs), C.POINTER(Out), C.c_void_p]),
+    "vltk_frcnn_run_part": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                      C.c_void_p, C.c_void_p]),
     "vltk_frcnn_debug_read": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
     "vltk_frcnn_launch_count": (C.c_int64, [C.c_void_p]),
     "vltk_frcnn_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),

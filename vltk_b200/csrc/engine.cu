@@ -718,6 +718,101 @@ static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void*
   return b.off + 256;
 }
 
+// BasicStem (frcnn.py:872-879): conv7x7 s2 p3 + BN + ReLU + 3x3 s2 ceil-mode max-pool, images NCHW f32 -> pooled NHWC in
+// the engine's activation type.  Buffers: b_in4 [N,H,W,4] f32, b_stema im2col rows (bf16 mode), b_stem, b_pool.
+static int run_stem(vltk_frcnn* h, const float* images, int n, int height, int width, const Shapes& s, void* b_in4,
+                    void* b_stema, void* b_stem, void* b_pool, cudaStream_t st) {
+  const vltk_frcnn_config& c = h->cfg;
+  const DType d = h->act;
+  const bool stem_on_tc = h->use_tc && h->stem_tc.w_nk;
+  static const bool im2col_direct = [] { const char* e = getenv("VLTK_STEM_NHWC4"); return !(e && e[0] == '1'); }();
+  if (!(stem_on_tc && im2col_direct)) {
+    StageTimer t(h, K_LAYOUT, (double)n * height * width * (12 + 16), st);
+    if (nchw3_to_nhwc4(images, b_in4, DT_F32, n, height, width, st)) return -1;
+    h->launches++;
+  }
+  if (stem_on_tc) {
+    const int64_t Ms = (int64_t)n * s.Hs * s.Ws;
+    { StageTimer t(h, K_LAYOUT, (double)n * height * width * 12.0 + (double)Ms * 384.0, st);
+      if (im2col_direct ? stem_im2col_nchw(images, b_stema, n, height, width, s.Hs, s.Ws, st)
+                        : stem_im2col((const float*)b_in4, b_stema, n, height, width, s.Hs, s.Ws, st)) return -1; }
+    h->launches++;
+    ConvProblem q;
+    memset(&q, 0, sizeof(q));
+    const LayerW& L = h->stem_tc;
+    q.x = b_stema; q.ldx = 192; q.y = b_stem; q.ldy = L.cout; q.N = (int)Ms; q.H = q.W = q.OH = q.OW = 1;
+    q.Cin = 192; q.Cout = L.cout; q.KH = q.KW = 1; q.stride = 1; q.dil = 1; q.scale = L.scale; q.shift = L.shift;
+    q.relu = 1; q.in_dtype = DT_BF16; q.out_dtype = DT_BF16;
+    vltk_frcnn::ProfRec rec;
+    if (h->profiling) {
+      rec.kind = 0; rec.M = Ms; rec.K = 147; rec.Cout = L.cout; rec.flops = 2.0 * (double)Ms * 147 * L.cout;
+      cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1); cudaEventRecord(rec.e0, st);
+    }
+    h->launches++;
+    if (conv_tc_launch(q, L.w_nk, L.cout_pad, &h->tmaps, st)) return -1;
+    if (h->profiling) { cudaEventRecord(rec.e1, st); h->prof.push_back(rec); }
+  } else if (run_conv(h, h->stem, b_in4, DT_F32, n, height, width, b_stem, d == DT_H2 ? DT_F32 : d, h->stem.ldw, nullptr, 0, 1, st)) return -1;
+  { StageTimer t(h, K_MAXPOOL, ((double)n * s.Hs * s.Ws + (double)n * s.Hp * s.Wp) * c.stem_out_channels * esz(d), st);
+    // exact_tc: the 3-channel stem runs in fp32 on the CUDA cores (0.14 % of the FLOPs); the pool splits its output
+    if (d == DT_H2 ? maxpool3x3s2_ceil_f32_to_h2((const float*)b_stem, b_pool, n, s.Hs, s.Ws, c.stem_out_channels, s.Hp, s.Wp, st)
+                   : maxpool3x3s2_ceil(b_stem, b_pool, d, n, s.Hs, s.Ws, c.stem_out_channels, s.Hp, s.Wp, st)) return -1; }
+  h->launches++;
+  return 0;
+}
+
+// RPNHead (frcnn.py:1561-1572): relu(conv3x3 + b) then the fused 1x1 head -> fp32 rows of *ldh_out columns:
+// [0,4A) anchor deltas, [4A,5A) objectness.
+static int run_rpn_head(vltk_frcnn* h, const void* res4, int n, int h4, int w4, void* b_hidden, void* b_head, int* ldh_out,
+                        cudaStream_t st) {
+  const DType d = h->act;
+  if (run_conv(h, h->rpn_conv, res4, d, n, h4, w4, b_hidden, d, h->rpn_conv.ldw, nullptr, 0, 1, st)) return -1;
+  int ldh = h->rpn_head.ldw;
+  if (h->use_tc && h->rpn_head.w_lo && d == DT_BF16) {
+    // 1x1 head on the tensor pipe, fp32-faithful: the RPN conv output IS bf16, so x*(w_hi + w_lo) in one fp32 TMEM tile
+    const LayerW& L = h->rpn_head;
+    const int64_t Mh = (int64_t)n * h4 * w4;
+    ldh = L.cout_pad;
+    ConvProblem q;
+    memset(&q, 0, sizeof(q));
+    q.x = b_hidden; q.ldx = L.cin_pad; q.y = b_head; q.ldy = ldh; q.N = (int)Mh; q.H = q.W = q.OH = q.OW = 1;
+    q.Cin = L.cin_pad; q.Cout = L.cout_pad; q.KH = q.KW = 1; q.stride = 1; q.dil = 1; q.shift = L.shift; q.relu = 0;
+    q.in_dtype = DT_BF16; q.out_dtype = DT_F32;
+    TcSplit sp; sp.x_lo = nullptr; sp.w_lo = L.w_lo;
+    vltk_frcnn::ProfRec rec;
+    if (h->profiling) {
+      rec.kind = 0; rec.M = Mh; rec.K = L.cin; rec.Cout = L.cout; rec.flops = 2.0 * (double)Mh * L.cin * L.cout;
+      cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1); cudaEventRecord(rec.e0, st);
+    }
+    h->launches++;
+    if (conv_tc_launch(q, L.w_nk, L.cout_pad, &h->tmaps, st, &sp)) return -1;
+    if (h->profiling) { cudaEventRecord(rec.e1, st); h->prof.push_back(rec); }
+  } else if (h->use_tcx && h->rpn_head.w_h3 && d == DT_H2) {
+    // 1x1 head on the tensor pipe, fp32-faithful, fp32 rows of cout_pad (= 128) columns
+    const LayerW& L = h->rpn_head;
+    const int64_t Mh = (int64_t)n * h4 * w4;
+    ldh = L.cout_pad;
+    ConvProblem q;
+    memset(&q, 0, sizeof(q));
+    q.x = b_hidden; q.ldx = 2 * L.cin_pad; q.y = b_head; q.ldy = ldh; q.N = (int)Mh; q.H = q.W = q.OH = q.OW = 1;
+    q.Cin = L.cin_pad; q.Cout = L.cout_pad; q.KH = q.KW = 1; q.stride = 1; q.dil = 1; q.scale = L.scale_x; q.shift = L.shift; q.relu = 0;
+    q.in_dtype = DT_H2; q.out_dtype = DT_F32;
+    vltk_frcnn::ProfRec rec;
+    if (h->profiling) {
+      rec.kind = 0; rec.M = Mh; rec.K = L.cin; rec.Cout = L.cout; rec.flops = 2.0 * (double)Mh * L.cin * L.cout;
+      cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1); cudaEventRecord(rec.e0, st);
+    }
+    h->launches++;
+    if (conv_tcx_launch(q, L.w_h3, L.cout_pad, &h->tmaps, st)) return -1;
+    if (h->profiling) { cudaEventRecord(rec.e1, st); h->prof.push_back(rec); }
+  } else {
+    LayerW L = h->rpn_head;
+    if (h->rpn_head_shift_simt) L.shift = h->rpn_head_shift_simt;
+    if (run_conv(h, L, b_hidden, d, n, h4, w4, b_head, DT_F32, L.ldw, nullptr, 0, 0, st)) return -1;
+  }
+  *ldh_out = ldh;
+  return 0;
+}
+
 size_t vltk_frcnn_workspace_bytes(vltk_frcnn_t* h, int n, int height, int width) {
   if (!h || !h->finalized || n < 0) return 0;
   void* p[B_NUM];
@@ -754,39 +849,7 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   }
 
   // ---- backbone (frcnn.py:1076-1090)
-  const bool stem_on_tc = h->use_tc && h->stem_tc.w_nk;
-  static const bool im2col_direct = [] { const char* e = getenv("VLTK_STEM_NHWC4"); return !(e && e[0] == '1'); }();
-  if (!(stem_on_tc && im2col_direct)) {
-    StageTimer t(h, K_LAYOUT, (double)n * height * width * (12 + 16), st);
-    if (nchw3_to_nhwc4(images, p[B_IN4], DT_F32, n, height, width, st)) return -1;
-    h->launches++;
-  }
-  if (stem_on_tc) {
-    const int64_t Ms = (int64_t)n * s.Hs * s.Ws;
-    { StageTimer t(h, K_LAYOUT, (double)n * height * width * 12.0 + (double)Ms * 384.0, st);
-      if (im2col_direct ? stem_im2col_nchw(images, p[B_STEMA], n, height, width, s.Hs, s.Ws, st)
-                        : stem_im2col((const float*)p[B_IN4], p[B_STEMA], n, height, width, s.Hs, s.Ws, st)) return -1; }
-    h->launches++;
-    ConvProblem q;
-    memset(&q, 0, sizeof(q));
-    const LayerW& L = h->stem_tc;
-    q.x = p[B_STEMA]; q.ldx = 192; q.y = p[B_STEM]; q.ldy = L.cout; q.N = (int)Ms; q.H = q.W = q.OH = q.OW = 1;
-    q.Cin = 192; q.Cout = L.cout; q.KH = q.KW = 1; q.stride = 1; q.dil = 1; q.scale = L.scale; q.shift = L.shift;
-    q.relu = 1; q.in_dtype = DT_BF16; q.out_dtype = DT_BF16;
-    vltk_frcnn::ProfRec rec;
-    if (h->profiling) {
-      rec.kind = 0; rec.M = Ms; rec.K = 147; rec.Cout = L.cout; rec.flops = 2.0 * (double)Ms * 147 * L.cout;
-      cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1); cudaEventRecord(rec.e0, st);
-    }
-    h->launches++;
-    if (conv_tc_launch(q, L.w_nk, L.cout_pad, &h->tmaps, st)) return -1;
-    if (h->profiling) { cudaEventRecord(rec.e1, st); h->prof.push_back(rec); }
-  } else if (run_conv(h, h->stem, p[B_IN4], DT_F32, n, height, width, p[B_STEM], d == DT_H2 ? DT_F32 : d, h->stem.ldw, nullptr, 0, 1, st)) return -1;
-  { StageTimer t(h, K_MAXPOOL, ((double)n * s.Hs * s.Ws + (double)n * s.Hp * s.Wp) * c.stem_out_channels * esz(d), st);
-    // exact_tc: the 3-channel stem runs in fp32 on the CUDA cores (0.14 % of the FLOPs); the pool splits its output
-    if (d == DT_H2 ? maxpool3x3s2_ceil_f32_to_h2((const float*)p[B_STEM], p[B_POOL], n, s.Hs, s.Ws, c.stem_out_channels, s.Hp, s.Wp, st)
-                   : maxpool3x3s2_ceil(p[B_STEM], p[B_POOL], d, n, s.Hs, s.Ws, c.stem_out_channels, s.Hp, s.Wp, st)) return -1; }
-  h->launches++;
+  if (run_stem(h, images, n, height, width, s, p[B_IN4], p[B_STEMA], p[B_STEM], p[B_POOL], st)) return -1;
   const void* x = p[B_POOL];
   int ch = s.Hp, cw = s.Wp;
   void* pp[2] = {p[B_A], p[B_B]};
@@ -864,50 +927,8 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   tap(h, "res4", res4, (int64_t)n * s.h4 * s.w4 * C4, d, C4);
 
   // ---- RPN head + proposal selection (frcnn.py:1561-1572, 264-390)
-  if (run_conv(h, h->rpn_conv, res4, d, n, s.h4, s.w4, p[B_RPNH], d, h->rpn_conv.ldw, nullptr, 0, 1, st)) return -1;
-  int ldh = h->rpn_head.ldw;
-  if (h->use_tc && h->rpn_head.w_lo && d == DT_BF16) {
-    // 1x1 head on the tensor pipe, fp32-faithful: the RPN conv output IS bf16, so x*(w_hi + w_lo) in one fp32 TMEM tile
-    const LayerW& L = h->rpn_head;
-    const int64_t Mh = (int64_t)n * s.h4 * s.w4;
-    ldh = L.cout_pad;
-    ConvProblem q;
-    memset(&q, 0, sizeof(q));
-    q.x = p[B_RPNH]; q.ldx = L.cin_pad; q.y = p[B_HEAD]; q.ldy = ldh; q.N = (int)Mh; q.H = q.W = q.OH = q.OW = 1;
-    q.Cin = L.cin_pad; q.Cout = L.cout_pad; q.KH = q.KW = 1; q.stride = 1; q.dil = 1; q.shift = L.shift; q.relu = 0;
-    q.in_dtype = DT_BF16; q.out_dtype = DT_F32;
-    TcSplit sp; sp.x_lo = nullptr; sp.w_lo = L.w_lo;
-    vltk_frcnn::ProfRec rec;
-    if (h->profiling) {
-      rec.kind = 0; rec.M = Mh; rec.K = L.cin; rec.Cout = L.cout; rec.flops = 2.0 * (double)Mh * L.cin * L.cout;
-      cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1); cudaEventRecord(rec.e0, st);
-    }
-    h->launches++;
-    if (conv_tc_launch(q, L.w_nk, L.cout_pad, &h->tmaps, st, &sp)) return -1;
-    if (h->profiling) { cudaEventRecord(rec.e1, st); h->prof.push_back(rec); }
-  } else if (h->use_tcx && h->rpn_head.w_h3 && d == DT_H2) {
-    // 1x1 head on the tensor pipe, fp32-faithful, fp32 rows of cout_pad (= 128) columns
-    const LayerW& L = h->rpn_head;
-    const int64_t Mh = (int64_t)n * s.h4 * s.w4;
-    ldh = L.cout_pad;
-    ConvProblem q;
-    memset(&q, 0, sizeof(q));
-    q.x = p[B_RPNH]; q.ldx = 2 * L.cin_pad; q.y = p[B_HEAD]; q.ldy = ldh; q.N = (int)Mh; q.H = q.W = q.OH = q.OW = 1;
-    q.Cin = L.cin_pad; q.Cout = L.cout_pad; q.KH = q.KW = 1; q.stride = 1; q.dil = 1; q.scale = L.scale_x; q.shift = L.shift; q.relu = 0;
-    q.in_dtype = DT_H2; q.out_dtype = DT_F32;
-    vltk_frcnn::ProfRec rec;
-    if (h->profiling) {
-      rec.kind = 0; rec.M = Mh; rec.K = L.cin; rec.Cout = L.cout; rec.flops = 2.0 * (double)Mh * L.cin * L.cout;
-      cudaEventCreate(&rec.e0); cudaEventCreate(&rec.e1); cudaEventRecord(rec.e0, st);
-    }
-    h->launches++;
-    if (conv_tcx_launch(q, L.w_h3, L.cout_pad, &h->tmaps, st)) return -1;
-    if (h->profiling) { cudaEventRecord(rec.e1, st); h->prof.push_back(rec); }
-  } else {
-    LayerW L = h->rpn_head;
-    if (h->rpn_head_shift_simt) L.shift = h->rpn_head_shift_simt;
-    if (run_conv(h, L, p[B_RPNH], d, n, s.h4, s.w4, p[B_HEAD], DT_F32, L.ldw, nullptr, 0, 0, st)) return -1;
-  }
+  int ldh = 0;
+  if (run_rpn_head(h, res4, n, s.h4, s.w4, p[B_RPNH], p[B_HEAD], &ldh, st)) return -1;
   tap(h, "rpn_head", p[B_HEAD], (int64_t)n * s.h4 * s.w4 * ldh, DT_F32);
   RpnSelectArgs ra;
   memset(&ra, 0, sizeof(ra));
@@ -1286,6 +1307,81 @@ int vltk_conv2d_dual_nhwc(const void* x, const float* weight, const void* x2, co
   TensorMapCache cache;
   if (!rc) rc = conv_tc_launch(p, w1, cout, &cache, st, nullptr, nullptr, &cc);
   cudaStreamSynchronize(st);
+  return rc;
+}
+
+// One part of the engine on caller-provided fp32 tensors, through the engine's own layers, weights and activation type
+// (teacher-forced stage tests: feed the oracle's stage input, compare the stage output).
+int vltk_frcnn_run_part(vltk_frcnn_t* h, int part, int block_begin, int block_end, const float* x, int n, int hh, int ww,
+                        float* y, int64_t y_cap, int32_t* out_dims, void* stream) {
+  VLTK_CHECK(h && h->finalized && x && y && out_dims, "run_part: bad argument");
+  VLTK_CHECK(part == 0 || (part >= 2 && part <= 5), "run_part: part must be 0 (stem), 2-4 (res2-res4) or 5 (rpn head)");
+  VLTK_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  Scratch scratch(st);
+  const DType d = h->act;
+  const size_t e = esz(d);
+  auto to_act = [&](const float* src, int64_t rows, int C, void** dst) -> int {
+    if (d == DT_F32) { *dst = (void*)src; return 0; }
+    VLTK_CUDA(scratch.get(dst, (size_t)rows * C * e));
+    return d == DT_BF16 ? cast_f32(src, *dst, DT_BF16, rows * C, st) : split_f32_h2(src, nullptr, 0, *dst, rows, C, st);
+  };
+  auto from_act = [&](const void* src, int64_t rows, int C) -> int {
+    VLTK_CHECK(rows * C <= y_cap, "run_part: output has %lld elements, capacity %lld", (long long)(rows * C), (long long)y_cap);
+    if (d == DT_F32) { VLTK_CUDA(cudaMemcpyAsync(y, src, (size_t)rows * C * 4, cudaMemcpyDeviceToDevice, st)); return 0; }
+    if (d == DT_H2) return widen_h2(src, y, rows, C, st);
+    widen_bf16_kernel<<<(unsigned)ceil_div64(rows * C, 256), 256, 0, st>>>((const bf16*)src, y, rows * C);
+    VLTK_LAUNCH_CHECK();
+    return 0;
+  };
+  const vltk_frcnn_config& c = h->cfg;
+  int rc = 0;
+  if (part == 0) {            // x: images NCHW f32 [n,3,hh,ww] -> pooled stem output NHWC
+    const Shapes s = make_shapes(c, n, hh, ww);
+    void *in4 = nullptr, *stema = nullptr, *stem = nullptr, *pool = nullptr;
+    VLTK_CUDA(scratch.get(&in4, (size_t)n * hh * ww * 16));
+    VLTK_CUDA(scratch.get(&stema, (size_t)n * s.Hs * s.Ws * 192 * 2));
+    VLTK_CUDA(scratch.get(&stem, (size_t)n * s.Hs * s.Ws * c.stem_out_channels * 4));
+    VLTK_CUDA(scratch.get(&pool, (size_t)n * s.Hp * s.Wp * c.stem_out_channels * 4));
+    rc = run_stem(h, x, n, hh, ww, s, in4, stema, stem, pool, st);
+    if (!rc) rc = from_act(pool, (int64_t)n * s.Hp * s.Wp, c.stem_out_channels);
+    out_dims[0] = s.Hp; out_dims[1] = s.Wp; out_dims[2] = c.stem_out_channels;
+  } else if (part <= 4) {     // x: NHWC f32 [n,hh,ww,cin] -> stage output NHWC
+    const std::vector<Block>& full = h->stages[part - 2];
+    const int b0 = std::max(block_begin, 0), b1 = block_end < 0 ? (int)full.size() : std::min(block_end, (int)full.size());
+    VLTK_CHECK(b0 < b1, "run_part: empty block range [%d, %d) of a %d-block stage", b0, b1, (int)full.size());
+    const std::vector<Block> stage(full.begin() + b0, full.begin() + b1);   // (LayerW holds device pointers only)
+    const int cin = stage[0].c1.cin, cout = stage[0].c3.cout, mid = stage[0].c1.cout, stride = stage[0].c1.stride;
+    const int h1 = (hh - 1) / stride + 1, w1 = (ww - 1) / stride + 1;
+    void *xa = nullptr, *pa = nullptr, *pb = nullptr, *t1 = nullptr, *t2 = nullptr, *sb = nullptr;
+    if (to_act(x, (int64_t)n * hh * ww, cin, &xa)) return -1;
+    const size_t big = (size_t)n * h1 * w1 * cout * e, midb = (size_t)n * h1 * w1 * mid * e;
+    VLTK_CUDA(scratch.get(&pa, big)); VLTK_CUDA(scratch.get(&pb, big)); VLTK_CUDA(scratch.get(&sb, big));
+    VLTK_CUDA(scratch.get(&t1, midb)); VLTK_CUDA(scratch.get(&t2, midb));
+    const void* cur = xa;
+    void* pp[2] = {pa, pb};
+    int ch = hh, cw = ww, flip = 0;
+    for (const Block& blk : stage) {
+      int oh = 0, ow = 0;
+      if (run_block(h, blk, cur, n, ch, cw, pp[flip], t1, t2, sb, st, &oh, &ow)) return -1;
+      cur = pp[flip]; flip ^= 1; ch = oh; cw = ow;
+    }
+    rc = from_act(cur, (int64_t)n * ch * cw, cout);
+    out_dims[0] = ch; out_dims[1] = cw; out_dims[2] = cout;
+  } else {                    // x: res4 NHWC f32 [n,hh,ww,C4] -> fp32 head rows [n*hh*ww, ldh]
+    const int C4 = h->rpn_conv.cin;
+    void *xa = nullptr, *hid = nullptr, *head = nullptr;
+    if (to_act(x, (int64_t)n * hh * ww, C4, &xa)) return -1;
+    VLTK_CUDA(scratch.get(&hid, (size_t)n * hh * ww * c.rpn_hidden * e));
+    VLTK_CUDA(scratch.get(&head, (size_t)n * hh * ww * std::max(h->rpn_head.ldw, h->rpn_head.cout_pad) * 4));
+    int ldh = 0;
+    rc = run_rpn_head(h, xa, n, hh, ww, hid, head, &ldh, st);
+    VLTK_CHECK((int64_t)n * hh * ww * ldh <= y_cap, "run_part: head output exceeds the capacity");
+    if (!rc) VLTK_CUDA(cudaMemcpyAsync(y, head, (size_t)n * hh * ww * ldh * 4, cudaMemcpyDeviceToDevice, st));
+    out_dims[0] = hh; out_dims[1] = ww; out_dims[2] = ldh;
+  }
+  cudaStreamSynchronize(st);
+  if (!rc) VLTK_LAUNCH_CHECK();
   return rc;
 }
 

@@ -424,6 +424,23 @@ class FRCNN:
                 continue
             raise _lib.LibraryError(msg)
 
+    def run_part(self, part: int, x: torch.Tensor, blocks=(0, -1)) -> torch.Tensor:
+        """One part of the model on a DEVICE fp32 tensor through this engine's layers and arithmetic mode (tests only;
+        include/vltk_frcnn.h vltk_frcnn_run_part): part 0 stem (x = images NCHW) -> pooled NHWC; 2-4 res2-res4
+        (NHWC -> NHWC; only blocks [blocks[0], blocks[1]) of the stage); 5 RPN head (res4 NHWC -> fp32 rows [n, h, w, ld], columns [0,60) deltas, [60,75) logits)."""
+        x = x.to(self.device).float().contiguous()
+        n = x.shape[0]
+        hh, ww = (x.shape[2], x.shape[3]) if part == 0 else (x.shape[1], x.shape[2])
+        cap = int(n) * hh * ww * 2048
+        y = torch.empty(cap, dtype=torch.float32, device=self.device)
+        dims = (C.c_int32 * 3)()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.vltk_frcnn_run_part(self._h, int(part), int(blocks[0]), int(blocks[1]), x.data_ptr(), n, hh, ww, y.data_ptr(), cap,
+                                                     C.cast(dims, C.c_void_p), torch.cuda.current_stream(self.device).cuda_stream),
+                       "vltk_frcnn_run_part")
+        oh, ow, ch = int(dims[0]), int(dims[1]), int(dims[2])
+        return y[: n * oh * ow * ch].view(n, oh, ow, ch).clone()
+
     def launch_count(self) -> int:
         return int(self._lib.vltk_frcnn_launch_count(self._h))
 
