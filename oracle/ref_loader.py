@@ -74,3 +74,22 @@ def load_preprocess():
         tc.img_tensorize = getattr(compat, "img_tensorize", None)
         sys.modules["vltk.legacy.transformers_compat"] = tc
     return importlib.import_module("vltk.legacy.processing").Preprocess
+
+
+def load_adapter():
+    """The reference's `Adapter` base class (vltk/abc/adapter.py) — the loader of extracted-feature Arrow files
+    (`Adapter.load` -> `_load_one_arrow` -> `datasets.Dataset(arrow_table)`, adapter.py:381-462).  Shims, all for
+    imports the loading path never executes: `jsonlines` (vltk/utils/base.py:17, absent here) is stubbed and
+    `datasets.ArrowWriter` (top-level name in the pinned datasets==1.9.0) is aliased to datasets.arrow_writer's."""
+    load_reference()
+    import datasets
+    if not hasattr(datasets, "ArrowWriter"):
+        from datasets.arrow_writer import ArrowWriter
+        datasets.ArrowWriter = ArrowWriter
+    sys.modules.setdefault("jsonlines", types.ModuleType("jsonlines"))
+    for name in ("vltk.abc", "vltk.utils"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = [os.path.join(REF_ROOT, *name.split("."))]
+            sys.modules[name] = m
+    return importlib.import_module("vltk.abc.adapter").Adapter

@@ -19,7 +19,7 @@ SIZES = [(150, 200), (240, 160), (192, 256), (170, 230), (200, 150)]
 def engine():
     from vltk_b200.frcnn import FRCNN
     cfg = cases.case_config("mixed")
-    model = FRCNN.from_pretrained(state_dict=weights(0), config=cfg, mode="fp32")
+    model = FRCNN.from_pretrained(state_dict=weights(0), config=cfg, mode="exact_tc")
     return model, cfg
 
 

@@ -169,3 +169,58 @@ def test_oracle_timing_path_with_torchvision_ops_equals_the_restatement():
     for k in ("boxes", "roi_features", "obj_probs"):
         for x, y in zip(a[k], b[k]):
             np.testing.assert_allclose(x.numpy(), y.numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_our_arrow_files_load_through_the_reference_adapter(tmp_path):
+    """The consumer side of the drop-in: a `{split}.arrow` written by vltk_b200.extract must load through the
+    reference's OWN loader — Adapter.load -> _load_one_arrow -> datasets.Dataset(arrow_table) (abc/adapter.py:381-462)
+    — and give back features / box / object_ids / attr_ids per image id via Adapter.get (adapter.py:186-196).
+    Authoring container only (needs /root/reference); the reference's own fixture goes through the same code for
+    comparison of the column types."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present")
+    pytest.importorskip("datasets")
+    from vltk_b200.extract import _rows, write_arrow
+    Adapter = ref_loader.load_adapter()
+
+    class FRCNNFeatures(Adapter):
+        _is_feature = True
+
+        def forward(*a, **k):
+            raise NotImplementedError
+
+        def schema(*a, **k):
+            return {}
+
+        def _meta_names():
+            return []
+
+    rng = np.random.default_rng(0)
+    n, md, d = 5, 36, 2048
+    dense = dict(boxes=rng.random((n, md, 4), np.float32) * 300, normalized_boxes=rng.random((n, md, 4), np.float32),
+                 obj_ids=rng.integers(0, 1600, (n, md)), obj_probs=rng.random((n, md), np.float32),
+                 attr_ids=rng.integers(0, 400, (n, md)), attr_probs=rng.random((n, md), np.float32),
+                 roi_features=rng.random((n, md, d), np.float32), preds_per_image=np.full(n, md))
+    ids = [f"{1000 + i}" for i in range(n)]
+    cols = _rows(ids, dense, np.tile([[600, 800]], (n, 1)))
+    path = str(tmp_path / "train.arrow")
+    write_arrow(path, cols, {"dataset": "synthetic", "model_config": {}, "processor_args": {"size": [800, 1333]}})
+    ours = FRCNNFeatures.load(path)
+    assert ours.img_to_row_map == {k: i for i, k in enumerate(ids)}
+    # a plain-string value comes back as raw bytes, exactly like `dataset` in the reference's own file (adapter.py:400-404)
+    assert ours.meta_dataset in ("synthetic", b"synthetic") and ours.meta_processor_args == {"size": [800, 1333]}
+    for i, k in enumerate(ids):
+        row = ours.get(k)
+        assert row["imgid"] == k
+        np.testing.assert_array_equal(np.asarray(row["features"], np.float32), dense["roi_features"][i])
+        np.testing.assert_array_equal(np.asarray(row["box"], np.float32), np.round(dense["boxes"][i]))
+        assert row["object_ids"] == dense["obj_ids"][i].astype(np.float32).tolist()
+        assert row["attr_ids"] == dense["attr_ids"][i].astype(np.float32).tolist()
+    # the reference's own extracted-features file through the same loader: same feature types for its columns
+    theirs = FRCNNFeatures.load(os.path.join(ref_loader.REF_ROOT, "tests", "visualgenome", "frcnn", "train.arrow"))
+    for k in ("imgid", "attr_ids", "object_ids", "features", "box"):
+        assert ours.features[k] == theirs.features[k], (k, ours.features[k], theirs.features[k])
+        assert ours.data.schema.field(k).type == theirs.data.schema.field(k).type      # same Arrow storage type
+    r0 = theirs.get(theirs.imgids[0])
+    assert np.asarray(r0["features"], np.float32).shape == (36, 2048) and np.asarray(r0["box"], np.float32).shape == (36, 4)

@@ -44,10 +44,10 @@ class FRCNN:
                          "mean": [102.9801, 115.9465, 122.7717], "std": [1.0, 1.0, 1.0]}
     _state_dict = None
     _config = None
-    _mode = "bf16"
+    _mode = "exact_tc"
 
     @classmethod
-    def configure(cls, state_dict, config: FRCNNConfig = None, mode: str = "bf16"):
+    def configure(cls, state_dict, config: FRCNNConfig = None, mode: str = "exact_tc"):
         cls._state_dict, cls._config, cls._mode = state_dict, config or FRCNNConfig(), mode
 
     @staticmethod

@@ -75,6 +75,7 @@ struct vltk_frcnn {
   std::vector<Block> res5;
   LayerW rpn_conv, rpn_head, cls_score, bbox_pred, fc_attr, attr_score;
   float* rpn_head_shift_simt = nullptr;   // ldw-sized bias of the CUDA-core RPN head (the tensor-pipe copy is padded to 64)
+  float* bbox_w_f32 = nullptr;  // exact_tc: bbox_pred.weight [4 NC][D] in fp32 (winner-only evaluation in roi_stats_kernel)
   float* attr_table = nullptr;  // [C+1][512] = emb @ fc_attr.W[:, D:]^T  (bias stays in fc_attr.shift)
   float* cell = nullptr;        // [A,4]
   std::map<std::string, Tap> taps;
@@ -646,6 +647,10 @@ int vltk_frcnn_finalize(vltk_frcnn_t* h) {
     if (!wc || !bc || !wa || !ba) return -2;
     if (pack_h3_linear(h, h->cls_score, *wc, NC + 1, D, D, *bc)) return -1;
     if (pack_h3_linear(h, h->attr_score, *wa, NA + 1, HA, HA, *ba)) return -1;
+    // bbox_pred is only ever needed for each ROI's winning class (frcnn.py:116-131): keep W [4 NC][D] in fp32 for roi_stats_kernel
+    const auto* wb = find(h, "roi_heads.box_predictor.bbox_pred.weight", (int64_t)NC * 4 * D);
+    if (!wb) return -2;
+    if (upload(h, *wb, &h->bbox_w_f32)) return -1;
   }
   if (tc) {
     const auto* wc = find(h, "roi_heads.box_predictor.cls_score.weight", (int64_t)(NC + 1) * D);
@@ -1019,7 +1024,7 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
     { StageTimer t(h, K_GLUE, (double)NR * D * 8.0, st);
       if (split_f32_h2((const float*)p[B_FEATS], nullptr, 0, p[B_FHI], NR, D, st)) return -1; }
     if (h2_gemm(h->cls_score, p[B_FHI], D, p[B_CLS], 0)) return -1;
-    if (run_conv(h, h->bbox_pred, p[B_FEATS], DT_F32, NR, 1, 1, p[B_BBOX], DT_F32, ldb, nullptr, 0, 0, st)) return -1;
+    // bbox_pred: only the winning class's 4 rows are ever used (frcnn.py:116-131) -> evaluated inside roi_stats_kernel (fp32)
     if (row_argmax((const float*)p[B_CLS], ldc, NR, c.num_classes + 1, (int*)p[B_ARGMAX], st)) return -1;
     if (gather_rows(h->attr_table, D / 4, (const int*)p[B_ARGMAX], NR, D / 4, (float*)p[B_TG], D / 4, st)) return -1;
     if (h2_gemm(h->fc_attr, p[B_FHI], D, p[B_AH], 0)) return -1;      // W[:, :D] x + b
@@ -1065,15 +1070,16 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
     h->launches += 2;
   }
   tap(h, "cls_logits", p[B_CLS], (int64_t)NR * ldc, DT_F32);
-  if (!ptc) tap(h, "bbox_deltas", p[B_BBOX], (int64_t)NR * ldb, DT_F32);
+  if (!ptc && !ptx) tap(h, "bbox_deltas", p[B_BBOX], (int64_t)NR * ldb, DT_F32);
   tap(h, "attr_logits", p[B_ATTR], (int64_t)NR * lda, DT_F32);
 
   // ---- detection tail (frcnn.py:1262-1294)
   TailArgs ta;
   memset(&ta, 0, sizeof(ta));
   ta.N = n; ta.R = s.R; ta.cls_logits = (const float*)p[B_CLS]; ta.ldc = ldc;
-  ta.bbox_deltas = ptc ? nullptr : (const float*)p[B_BBOX]; ta.ldb = ldb;
+  ta.bbox_deltas = (ptc || ptx) ? nullptr : (const float*)p[B_BBOX]; ta.ldb = ldb;
   if (ptc) { ta.bbox_w_hi = h->bbox_pred.w_nk; ta.bbox_w_lo = h->bbox_pred.w_lo; ta.bbox_bias = h->bbox_pred.shift; }
+  if (ptx) { ta.bbox_w_f32 = h->bbox_w_f32; ta.bbox_bias = h->bbox_pred.shift; }
   ta.attr_logits = (const float*)p[B_ATTR]; ta.lda = lda;
   ta.feats = (const float*)p[B_FEATS]; ta.D = D; ta.proposals = (const float*)p[B_PROP];
   ta.count = (const int*)p[B_COUNT]; ta.sizes_hw = (const int*)p[B_SIZES];

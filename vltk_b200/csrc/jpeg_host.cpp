@@ -98,12 +98,13 @@ int exif_orientation(const uint8_t* p, int len) {
     return le ? (uint32_t)(t[o] | (t[o + 1] << 8) | (t[o + 2] << 16) | ((uint32_t)t[o + 3] << 24))
               : (uint32_t)(((uint32_t)t[o] << 24) | (t[o + 1] << 16) | (t[o + 2] << 8) | t[o + 3]);
   };
+  if (n < 8) return 0;
   const uint32_t ifd = u32(4);
-  if (ifd + 2 > (uint32_t)n) return 0;
+  if (ifd > (uint32_t)n - 2) return 0;                  // (no `ifd + 2`: it wraps for offsets >= 0xFFFFFFFE)
   const int cnt = u16((int)ifd);
   for (int i = 0; i < cnt; ++i) {
-    const uint32_t e = ifd + 2 + 12u * i;
-    if (e + 12 > (uint32_t)n) return 0;
+    const uint64_t e = (uint64_t)ifd + 2 + 12ull * i;
+    if (e + 12 > (uint64_t)n) return 0;
     if (u16((int)e) == 0x0112) return u16((int)e + 8);
   }
   return 0;
@@ -191,6 +192,7 @@ int parse(const uint8_t* d, size_t len, Parsed* P) {
     } else if (m == 0xDA) {                              // SOS
       if (!have_sof) { set_error("jpeg: SOS before SOF"); return -2; }
       if (I.progressive) { P->scan_offset = pos - 2; break; }   // the scans are walked by decode_progressive()
+      if (n < 1) { set_error("jpeg: empty SOS segment"); return -2; }
       const int ns = s[0];
       if (ns != I.ncomp || n < 1 + 2 * ns + 3) {
         set_error("jpeg: only one interleaved scan covering all components is supported (scan has %d of %d)", ns, I.ncomp);
@@ -345,6 +347,7 @@ int decode_progressive(const uint8_t* d, size_t len, Parsed& P, int16_t* coef) {
     if (m == 0xDD) { if (n >= 2) restart_interval = rd16(s); pos += L; continue; }
     if (m != 0xDA) { pos += L; continue; }
     // ---- one scan
+    if (n < 1) { set_error("jpeg: empty SOS segment"); return -2; }
     const int ns = s[0];
     if (ns < 1 || ns > I.ncomp || n < 1 + 2 * ns + 3) { set_error("jpeg: bad SOS"); return -2; }
     int comp[3], td[3], ta[3];

@@ -96,6 +96,7 @@ struct TailArgs {
   // bbox_pred evaluated ONLY for each ROI's winning class (4 of its 6400 rows; frcnn.py:1244-1250 computes all,
   // 116-131 keeps one): deltas = W[4c..4c+3, :] . feats + b with W = hi + lo bf16 planes [rows][D] (fp32-faithful)
   const bf16* bbox_w_hi; const bf16* bbox_w_lo; const float* bbox_bias;
+  const float* bbox_w_f32;     // exact_tc: W as fp32 [rows][D] instead of the two bf16 planes
   const float* attr_logits;    // [N*R, lda]  (num_attrs+1 valid)
   int lda;
   const float* feats;          // [N*R, D]

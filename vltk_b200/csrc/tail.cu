@@ -57,6 +57,7 @@ roi_stats_kernel(TailArgs a, float* __restrict__ stats) {
   }
   mx = warp_max(mx);
   warp_argmax(best, bi);
+  if (bi == 0x7fffffff) bi = 0;            // all-NaN / -inf row (the reference asserts isfinite, frcnn.py:148): stay in bounds
   float s = 0.f;
   for (int i = lane; i <= NC; i += 32) s += expf(l[i] - mx);
   s = warp_sum(s);
@@ -69,6 +70,7 @@ roi_stats_kernel(TailArgs a, float* __restrict__ stats) {
     if (v > ab) { ab = v; ai = i; }
   }
   warp_argmax(ab, ai);
+  if (ai == 0x7fffffff) ai = 0;
   float as = 0.f;
   for (int i = lane; i < NA; i += 32) as += expf(al[i] - ab);
   as = warp_sum(as);
@@ -83,8 +85,13 @@ roi_stats_kernel(TailArgs a, float* __restrict__ stats) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int64_t o = (int64_t)(4 * bi + j) * a.D + k;
-        const float4 wh = load4(a.bbox_w_hi + o), wl = load4(a.bbox_w_lo + o);
-        acc[j] += x.x * (wh.x + wl.x) + x.y * (wh.y + wl.y) + x.z * (wh.z + wl.z) + x.w * (wh.w + wl.w);
+        if (a.bbox_w_f32) {                  // exact_tc: the fp32 weights themselves
+          const float4 w = *reinterpret_cast<const float4*>(a.bbox_w_f32 + o);
+          acc[j] += x.x * w.x + x.y * w.y + x.z * w.z + x.w * w.w;
+        } else {
+          const float4 wh = load4(a.bbox_w_hi + o), wl = load4(a.bbox_w_lo + o);
+          acc[j] += x.x * (wh.x + wl.x) + x.y * (wh.y + wl.y) + x.z * (wh.z + wl.z) + x.w * (wh.w + wl.w);
+        }
       }
     }
     d = make_float4(warp_sum(acc[0]) + a.bbox_bias[4 * bi], warp_sum(acc[1]) + a.bbox_bias[4 * bi + 1],
@@ -246,7 +253,7 @@ __global__ void row_argmax_kernel(const float* __restrict__ x, int ld, int rows,
     if (v > best) { best = v; bi = i; }
   }
   warp_argmax(best, bi);
-  if (lane == 0) out[row] = bi;
+  if (lane == 0) out[row] = bi == 0x7fffffff ? 0 : bi;   // never an out-of-range table index (non-finite row)
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ table, int ld, const int* __restrict__ idx,

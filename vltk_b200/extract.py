@@ -27,46 +27,76 @@ def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_items, world))
 
 
-def _rows(ids: Sequence[str], dense: Dict[str, np.ndarray], sizes, scales_yx):
-    """Dense model outputs -> column arrays, reference columns first."""
-    n = len(ids)
-    boxes = np.asarray(dense["boxes"], np.float32)
+def _rows_t(dense: Dict[str, object], sizes) -> Dict[str, torch.Tensor]:
+    """Dense model outputs (numpy arrays or torch tensors, host or device) -> column tensors on the same device,
+    reference columns first (everything but `imgid`)."""
+    t = {k: torch.as_tensor(v) for k, v in dense.items() if k not in ("sizes", "scales_yx", "keep_idx")}
+    dev = t["roi_features"].device
+    boxes = t["boxes"].float()
+    n = boxes.shape[0]
     # adapter epilogue (adapters/frcnn.py:50-57, utils/adapters.py:205-216): the reference calls the model WITHOUT
     # scales_yx (boxes in resized-image pixels) and writes round(boxes * 1/wh_scale) with wh_scale = resized/raw
     # (processing/image.py:128-135), i.e. RAW-image pixels.  `boxes` here was already multiplied by
     # scales_yx = raw/resized by the model (frcnn.py:1280-1283), so it is in that frame: only the rounding is left.
-    box = np.round(boxes)
-    cols = {
-        "imgid": np.asarray([str(i) for i in ids], dtype=object),
-        "attr_ids": np.asarray(dense["attr_ids"]).astype(np.float32),
-        "object_ids": np.asarray(dense["obj_ids"]).astype(np.float32),
-        "features": np.asarray(dense["roi_features"], np.float32),
-        "box": box.astype(np.float32),
+    return {
+        "attr_ids": t["attr_ids"].float(),
+        "object_ids": t["obj_ids"].float(),
+        "features": t["roi_features"].float(),
+        "box": torch.round(boxes),
         "boxes": boxes,
-        "normalized_boxes": np.asarray(dense["normalized_boxes"], np.float32),
-        "obj_probs": np.asarray(dense["obj_probs"], np.float32),
-        "attr_probs": np.asarray(dense["attr_probs"], np.float32),
-        "preds_per_image": np.asarray(dense["preds_per_image"]).astype(np.int32),
-        "sizes": np.asarray(sizes).astype(np.int32).reshape(n, 2),
+        "normalized_boxes": t["normalized_boxes"].float(),
+        "obj_probs": t["obj_probs"].float(),
+        "attr_probs": t["attr_probs"].float(),
+        "preds_per_image": t["preds_per_image"].to(torch.int32),
+        "sizes": torch.as_tensor(np.asarray(sizes)).to(torch.int32).reshape(n, 2).to(dev),
     }
+
+
+def _rows(ids: Sequence[str], dense: Dict[str, np.ndarray], sizes, scales_yx=None):
+    """Dense model outputs -> numpy column arrays, `imgid` first then the reference columns."""
+    cols = {"imgid": np.asarray([str(i) for i in ids], dtype=object)}
+    cols.update({k: v.cpu().numpy() for k, v in _rows_t(dense, sizes).items()})
     return cols
 
 
-def _fixed(arr: np.ndarray):
-    """[n, a, b] / [n, a] float/int arrays -> nested fixed-size-list Arrow arrays."""
+def _nested(arr: np.ndarray):
+    """[n, a] / [n, a, b] arrays -> list<T> / list<list<T>> Arrow arrays (int32 offsets over ONE flat, zero-copy
+    values buffer): the storage the reference's files use for Sequence(float32) and Array2D columns
+    (tests/visualgenome/frcnn/train.arrow; vltk/features.py:13-16, 81-95)."""
     import pyarrow as pa
-    flat = pa.array(np.ascontiguousarray(arr).reshape(-1))
-    out = flat
-    for dim in reversed(arr.shape[1:]):
-        out = pa.FixedSizeListArray.from_arrays(out, int(dim))
+    arr = np.ascontiguousarray(arr)
+    out = pa.array(arr.reshape(-1))
+    rows = int(np.prod(arr.shape[:-1]))
+    for k in range(arr.ndim - 1, 0, -1):
+        width = int(arr.shape[k])
+        out = pa.ListArray.from_arrays(pa.array(np.arange(rows + 1, dtype=np.int32) * width), out)
+        rows //= int(arr.shape[k - 1]) if k > 1 else 1
+        if k > 1:
+            rows = int(np.prod(arr.shape[:k - 1]))
     return out
 
 
-def write_arrow(path: str, cols: Dict[str, np.ndarray], meta: Dict[str, object]):
-    """Arrow IPC stream, one record batch per 128 rows like the reference's flush cadence
-    (extraction.py:26, 206-219); metadata values are json strings (utils/base.py:71-88)."""
+def _hf_features(cols: Dict[str, np.ndarray]) -> dict:
+    """The `huggingface` schema-metadata entry `datasets` writes and the reference's loader relies on to rebuild
+    typed features (abc/adapter.py:381-409 -> datasets.Dataset(arrow_table)): Value / Sequence / Array2D per column,
+    in the notation of the reference's own fixture."""
+    def val(dt):
+        return {"dtype": str(np.dtype(dt)), "id": None, "_type": "Value"}
+    feats = {}
+    for k, v in cols.items():
+        if k == "imgid":
+            feats[k] = {"dtype": "string", "id": None, "_type": "Value"}
+        elif v.ndim == 1:
+            feats[k] = val(v.dtype)
+        elif v.ndim == 2:
+            feats[k] = {"feature": val(v.dtype), "length": -1, "id": None, "_type": "Sequence"}
+        else:
+            feats[k] = {"shape": [int(v.shape[1]), int(v.shape[2])], "dtype": str(v.dtype), "id": None, "_type": "Array2D"}
+    return {"info": {"features": feats}}
+
+
+def _to_table(cols: Dict[str, np.ndarray]):
     import pyarrow as pa
-    n = len(cols["imgid"])
     arrays, names = [], []
     for k, v in cols.items():
         names.append(k)
@@ -75,11 +105,24 @@ def write_arrow(path: str, cols: Dict[str, np.ndarray], meta: Dict[str, object])
         elif v.ndim == 1:
             arrays.append(pa.array(v))
         else:
-            arrays.append(_fixed(v))
-    table = pa.Table.from_arrays(arrays, names=names)
+            arrays.append(_nested(v))
+    return pa.Table.from_arrays(arrays, names=names)
+
+
+def _schema_metadata(meta: Dict[str, object], cols, img_to_row_map) -> dict:
     md = {k: (v if isinstance(v, str) else json.dumps(v)) for k, v in meta.items()}
-    md["img_to_row_map"] = json.dumps({str(i): r for r, i in enumerate(cols["imgid"])})
-    table = table.replace_schema_metadata(md)
+    md["img_to_row_map"] = json.dumps(img_to_row_map)
+    md["huggingface"] = json.dumps(_hf_features(cols))
+    return md
+
+
+def write_arrow(path: str, cols: Dict[str, np.ndarray], meta: Dict[str, object]):
+    """Arrow IPC stream, one record batch per 128 rows like the reference's flush cadence
+    (extraction.py:26, 206-219); metadata values are json strings (utils/base.py:71-88)."""
+    import pyarrow as pa
+    n = len(cols["imgid"])
+    table = _to_table(cols)
+    table = table.replace_schema_metadata(_schema_metadata(meta, cols, {str(i): r for r, i in enumerate(cols["imgid"])}))
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
     with pa.OSFile(path, "wb") as sink:
         with pa.ipc.new_stream(sink, table.schema) as w:
@@ -107,10 +150,11 @@ class _AsyncArrowWriter:
     def __init__(self, path: str, ids_in_order: Sequence[str], meta: Dict[str, object]):
         import queue
         import threading
-        self.path, self.meta = path, dict(meta)
-        self.meta["img_to_row_map"] = {str(i): r for r, i in enumerate(ids_in_order)}
+        self.path, self.meta_user = path, dict(meta)
+        self.img_to_row_map = {str(i): r for r, i in enumerate(ids_in_order)}
         self.q = queue.Queue(maxsize=4)
         self.err = None
+        self.aborted = False
         self.rows = 0
         self.t = threading.Thread(target=self._run, daemon=True)
         self.t.start()
@@ -118,26 +162,17 @@ class _AsyncArrowWriter:
     def _run(self):
         import pyarrow as pa
         sink = writer = None
+        tmp = self.path + ".partial"
         try:
             while True:
                 cols = self.q.get()
                 if cols is None:
                     break
-                arrays, names = [], []
-                for k, v in cols.items():
-                    names.append(k)
-                    if k == "imgid":
-                        arrays.append(pa.array([str(x) for x in v], type=pa.string()))
-                    elif v.ndim == 1:
-                        arrays.append(pa.array(v))
-                    else:
-                        arrays.append(_fixed(v))
-                table = pa.Table.from_arrays(arrays, names=names)
+                table = _to_table(cols)
                 if writer is None:
-                    md = {k: (v if isinstance(v, str) else json.dumps(v)) for k, v in self.meta.items()}
-                    schema = table.schema.with_metadata(md)
+                    schema = table.schema.with_metadata(_schema_metadata(self.meta_user, cols, self.img_to_row_map))
                     os.makedirs(os.path.dirname(os.path.abspath(self.path)), exist_ok=True)
-                    sink = pa.OSFile(self.path, "wb")
+                    sink = pa.OSFile(tmp, "wb")
                     writer = pa.ipc.new_stream(sink, schema)
                 for b in table.to_batches(max_chunksize=128):
                     writer.write_batch(b)
@@ -151,13 +186,20 @@ class _AsyncArrowWriter:
                 writer.close()
             if sink is not None:
                 sink.close()
+            # a file only appears under its final name when every announced row was written: a failed shard leaves no
+            # truncated file whose img_to_row_map promises rows that are not there
+            if self.err is None and not self.aborted and writer is not None and self.rows == len(self.img_to_row_map):
+                os.replace(tmp, self.path)
+            elif os.path.exists(tmp):
+                os.remove(tmp)
 
     def put(self, cols):
         if self.err:
             raise self.err
         self.q.put(cols)
 
-    def close(self):
+    def close(self, abort: bool = False):
+        self.aborted = self.aborted or abort
         self.q.put(None)
         self.t.join()
         if self.err:
@@ -225,11 +267,9 @@ def extract(image_source: Callable[[int], np.ndarray], image_ids: Sequence[str],
     meta.setdefault("processor_args", {})
     direct = (not single_file) or world == 1
     path = os.path.join(out_dir, f"{split}.arrow" if world == 1 else f"{split}.rank{rank}.arrow")
-    writer = _AsyncArrowWriter(path, [image_ids[i] for i in mine], meta) if (direct and mine) else None
-    plan: List[tuple] = []          # (window number, positions inside the window) per batch, in feed order
-    chunks: List[Dict[str, np.ndarray]] = []
     cfg = getattr(preprocess, "cfg", None)
     bucket = bucket and cfg is not None
+    plan: List[tuple] = []          # (window number, first shard row, rows, positions inside the window) per batch, in feed order
 
     def feed():
         for wn, w0 in enumerate(range(0, len(mine), window)):
@@ -241,70 +281,115 @@ def extract(image_source: Callable[[int], np.ndarray], image_ids: Sequence[str],
                 yield [raws[j] for j in pos]
 
     kw = {} if max_detections is None else {"max_detections": max_detections}
-    pending: Dict[int, list] = {}
-    try:
+    gather = None
+    if not direct:
+        gather = _WindowGather(image_ids, out_dir, split, rank, world, window, meta)
+        if gather.on_device and hasattr(model, "forward_raw_stream"):
+            kw["on_device"] = True          # dense outputs stay in HBM: packed there and handed to NCCL
+
+    def windows():
+        """This rank's finished windows, in order: (first shard row, {column: tensor}) restored to shard order."""
+        pending: Dict[int, list] = {}
         for dense in _stream(model, preprocess, feed(), max(1, window // batch_size), **kw):
             wn, w0, wlen, pos = plan.pop(0)
-            ids = [image_ids[mine[w0 + j]] for j in pos]
-            rows = _rows(ids, dense, dense["sizes"], dense["scales_yx"])
-            slot = pending.setdefault(wn, [None, 0, wlen, []])
-            slot[3].append((pos, rows))
-            slot[1] += len(pos)
+            slot = pending.setdefault(wn, [0, []])
+            slot[1].append((pos, _rows_t(dense, dense["sizes"])))
+            slot[0] += len(pos)
             if progress:
                 progress(len(pos))
-            if slot[1] == wlen:                      # window complete: back to shard order
-                parts = pending.pop(wn)[3]
-                keys = list(parts[0][1].keys())
-                where = np.concatenate([np.asarray(p, np.int64) for p, _ in parts])
-                inv = np.argsort(where, kind="stable")
-                cols = {k: np.concatenate([r[k] for _, r in parts], 0)[inv] for k in keys}
-                if writer is not None:
-                    writer.put(cols)
-                else:
-                    chunks.append(cols)
-    finally:
-        if writer is not None:
-            writer.close()
+            if slot[0] == wlen:                      # window complete: back to shard order
+                parts = pending.pop(wn)[1]
+                where = torch.as_tensor(np.concatenate([np.asarray(p, np.int64) for p, _ in parts]))
+                inv = torch.argsort(where, stable=True)
+                yield w0, {k: torch.cat([r[k] for _, r in parts], 0)[inv.to(parts[0][1][k].device)] for k in parts[0][1]}
+
     if direct:
+        if not mine:
+            return None                              # a rank that owns no images writes no file
+        writer = _AsyncArrowWriter(path, [image_ids[i] for i in mine], meta)
+        ok = False
+        try:
+            for w0, cols_t in windows():
+                n = next(iter(cols_t.values())).shape[0]
+                cols = {"imgid": np.asarray([str(image_ids[mine[w0 + j]]) for j in range(n)], dtype=object)}
+                cols.update({k: v.cpu().numpy() for k, v in cols_t.items()})
+                writer.put(cols)
+            ok = True
+        finally:
+            writer.close(abort=not ok)               # a failed shard leaves no file behind
         return path
-    keys = list(chunks[0].keys()) if chunks else []
-    cols = {k: np.concatenate([c[k] for c in chunks], 0) for k in keys}
-    return _gather_and_write(cols, keys, mine, len(image_ids), out_dir, split, rank, world, meta)
+    return gather.run(windows())
 
 
-def _gather_and_write(cols, keys, mine, n_total, out_dir, split, rank, world, meta):
-    """The one collective of the path: fixed-size per-image tensors -> writer rank 0."""
-    import torch.distributed as dist
-    assert dist.is_initialized(), "single_file=True needs torch.distributed"
-    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-    per_rank = -(-n_total // world)  # pad every rank to the same row count
-    gathered = {}
-    for k in keys:
-        if k == "imgid":
-            continue
-        a = torch.from_numpy(np.ascontiguousarray(cols[k])) if len(mine) else None
-        shape = (per_rank,) + tuple(a.shape[1:]) if a is not None else None
-        # shapes are identical on every rank except for the row count; broadcast them from rank 0
-        meta_t = [shape, str(a.dtype) if a is not None else None]
-        lst = [None] * world
-        dist.all_gather_object(lst, meta_t)
-        shape, dt = next((s, d) for s, d in lst if s is not None)
-        buf = torch.zeros(shape, dtype=getattr(torch, dt.split(".")[-1]), device=dev)
-        if a is not None:
-            buf[: a.shape[0]] = a.to(dev)
-        out = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
-        dist.gather(buf, out, dst=0)
-        if rank == 0:
-            gathered[k] = [o.cpu().numpy() for o in out]
-    ids_all = [None] * world
-    dist.all_gather_object(ids_all, [str(x) for x in cols.get("imgid", [])])
-    if rank != 0:
-        return None
-    # interleave back to global index order: global i lives at rank i % world, row i // world
-    order = [(i % world, i // world) for i in range(n_total)]
-    final = {"imgid": np.asarray([ids_all[r][j] for r, j in order], dtype=object)}
-    for k, parts in gathered.items():
-        final[k] = np.stack([parts[r][j] for r, j in order], 0)
-    path = os.path.join(out_dir, f"{split}.arrow")
-    write_arrow(path, final, meta)
-    return path
+class _WindowGather:
+    """single_file=True: the ONE collective of the path.  Every rank packs each finished window of its shard (all
+    fixed-size columns of a row back to back, ~297 KB per image) into one byte tensor on its device and rank 0 receives
+    the world's windows with ONE torch.distributed.gather per window (NCCL over NVLink between GPUs; gloo in the CPU
+    tests) — no per-column collectives, no host round trip on the sending ranks.  Global image i lives at rank i % world,
+    shard row i // world, so a gathered window [world, window, row] transposed to [window, world, row] IS global index
+    order; rank 0 copies it to the host once and the background writer appends it to `{split}.arrow`.
+    Every rank takes part in every window's gather (ranks whose shard has no rows there send zeros), so shards of
+    unequal length — including empty ones — cannot deadlock."""
+
+    def __init__(self, image_ids, out_dir, split, rank, world, window, meta):
+        import torch.distributed as dist
+        assert dist.is_initialized(), "single_file=True needs torch.distributed"
+        self.dist, self.ids, self.rank, self.world, self.window = dist, list(image_ids), rank, world, window
+        self.on_device = dist.get_backend() == "nccl"
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if self.on_device else torch.device("cpu")
+        self.n_total = len(self.ids)
+        per_rank = -(-self.n_total // world)
+        self.n_windows = -(-per_rank // window)
+        self.path = os.path.join(out_dir, f"{split}.arrow")
+        self.writer = _AsyncArrowWriter(self.path, self.ids, meta) if (rank == 0 and self.n_total) else None
+        self.spec = None                # [(column, torch dtype name, trailing shape)], agreed once
+        self.row_bytes = 0
+
+    def _agree_on_spec(self, cols_t):
+        mine = None if cols_t is None else [(k, str(v.dtype).split(".")[-1], tuple(int(d) for d in v.shape[1:])) for k, v in cols_t.items()]
+        box = [mine if self.rank == 0 else None]
+        self.dist.broadcast_object_list(box, src=0)   # rank 0 owns image 0, so it always has a first window
+        self.spec = box[0]
+        self.row_bytes = sum(int(np.prod(sh, dtype=np.int64)) * torch.empty((), dtype=getattr(torch, dt)).element_size() for _, dt, sh in self.spec)
+
+    def _pack(self, cols_t):
+        n = next(iter(cols_t.values())).shape[0]
+        parts = [cols_t[k].to(self.dev).contiguous().reshape(n, -1).view(torch.uint8) for k, _, _ in self.spec]
+        return torch.cat(parts, 1)
+
+    def _unpack(self, host: np.ndarray):
+        out, off = {}, 0
+        for k, dt, sh in self.spec:
+            npdt = np.dtype(dt)
+            nb = int(np.prod(sh, dtype=np.int64)) * npdt.itemsize
+            out[k] = np.ascontiguousarray(host[:, off:off + nb]).view(npdt).reshape((host.shape[0],) + tuple(sh))
+            off += nb
+        return out
+
+    def run(self, windows):
+        ok = False
+        try:
+            it = iter(windows)
+            for w in range(self.n_windows):
+                nxt = next(it, None)                  # None: this rank's shard has no rows in window w
+                cols_t = None if nxt is None else nxt[1]
+                if self.spec is None:
+                    self._agree_on_spec(cols_t)
+                buf = torch.zeros((self.window, self.row_bytes), dtype=torch.uint8, device=self.dev)
+                if cols_t is not None:
+                    pk = self._pack(cols_t)
+                    buf[: pk.shape[0]] = pk
+                out = [torch.empty_like(buf) for _ in range(self.world)] if self.rank == 0 else None
+                self.dist.gather(buf, out, dst=0)
+                if self.rank == 0:
+                    lo = w * self.window * self.world
+                    hi = min(lo + self.window * self.world, self.n_total)
+                    g = torch.stack(out).permute(1, 0, 2).reshape(self.window * self.world, self.row_bytes)[: hi - lo]
+                    cols = {"imgid": np.asarray([str(x) for x in self.ids[lo:hi]], dtype=object)}
+                    cols.update(self._unpack(g.cpu().numpy()))
+                    self.writer.put(cols)
+            ok = True
+        finally:
+            if self.writer is not None:
+                self.writer.close(abort=not ok)
+        return self.path if (self.rank == 0 and self.n_total) else None

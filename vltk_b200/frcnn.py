@@ -31,7 +31,7 @@ class ROIOutputs:
 
 
 class FRCNN:
-    def __init__(self, cfg: Optional[FRCNNConfig] = None, mode: str = "bf16", device: int = 0):
+    def __init__(self, cfg: Optional[FRCNNConfig] = None, mode: str = "exact_tc", device: int = 0):
         self.config = cfg or FRCNNConfig()
         self.mode = mode
         self.device_index = int(device)
@@ -73,7 +73,7 @@ class FRCNN:
         if config is None and model_args:
             config = model_args[0]
         state_dict = kwargs.pop("state_dict", None)
-        mode = kwargs.pop("mode", "bf16")
+        mode = kwargs.pop("mode", "exact_tc")
         device = kwargs.pop("device", 0)
         if state_dict is None:
             if pretrained_model_name_or_path is None:
@@ -165,6 +165,12 @@ class FRCNN:
         """kwargs (frcnn.py:1924-1929): max_detections, return_tensors in {"np","pt",None},
         padding in {None,"max_detections"}, pad_value, location in {"cuda","cpu"}.
 
+        Differences from the live reference, on purpose: (i) the `max_detections` kwarg overrides
+        `roi_outputs.max_detections` for this call, as in v1.0.0 and as the docstring of the reference promises — the
+        live reference ignores it (its handling is commented out, frcnn.py:1975-1994); (ii) padding="max_detections"
+        returns v1.0.0's dense layout, which the live reference also dropped.  Index-exact agreement with the
+        reference needs mode="exact_tc" (or "fp32"); mode="bf16" is the fast mode (stage-level bf16 bounds only).
+
         padding=None returns the live reference's ragged lists of per-image tensors;
         padding="max_detections" returns the v1.0.0 dense layout [N,max_det,...] plus `sizes`
         and `normalized_boxes`.
@@ -185,7 +191,7 @@ class FRCNN:
         assert return_tensors in (None, "np", "pt"), return_tensors
         ro = self.roi_outputs
         max_det = int(kwargs.get("max_detections", None) or ro.max_detections)
-        min_det = min(int(ro.min_detections), max_det)
+        min_det = int(ro.min_detections)   # not clamped: with min > max no threshold satisfies the window and the LAST one is kept, like do_nms (frcnn.py:1273-1278)
 
         with torch.cuda.device(self.device):
             x = torch.as_tensor(images)
@@ -242,7 +248,7 @@ class FRCNN:
             raise RuntimeError("load_state_dict() has not been called")
         ro = self.roi_outputs
         md = int(max_detections or ro.max_detections)
-        mind = min(int(ro.min_detections), md)
+        mind = int(ro.min_detections)
         dev = self.device
         depth = max(int(depth), 1)
         keys = ("obj_ids", "obj_probs", "attr_ids", "attr_probs", "boxes", "roi_features", "preds_per_image",
@@ -310,19 +316,21 @@ class FRCNN:
                     main.wait_stream(s_)
 
     def forward_jpeg_stream(self, batches, preprocess, group: int = 8, max_detections=None, pad_value=0.0,
-                            depth: int = 3, compute_streams: int = 2):
+                            depth: int = 3, compute_streams: int = 2, on_device: bool = False):
         """Raw-image front door of the extraction path: `batches` yields lists whose entries are JPEG byte strings
         and/or decoded BGR u8 [h,w,3] arrays/tensors (one list = one model batch).  The encoded entries of `group`
         batches at a time are decoded by ONE call of the GPU JPEG front end (one CTA per image: the more images
         per call, the better its few-SM kernels amortise), then each batch is resized/normalised/padded by the
         fused preprocess kernel, run, and read back asynchronously; consecutive batches alternate between
         `compute_streams` streams (own workspace each) like `forward_stream`; the group decode itself runs with both
-        streams drained.  Yields one dict of numpy arrays per batch, in order (plus `scales_yx`)."""
+        streams drained.  Yields one dict of numpy arrays per batch, in order (plus `scales_yx`).
+        on_device=True skips the device->host copy and yields the dense DEVICE tensors instead (the single-file
+        extraction packs them on the device and hands them to NCCL without a host round trip)."""
         if not self._finalized:
             raise RuntimeError("load_state_dict() has not been called")
         ro = self.roi_outputs
         md = int(max_detections or ro.max_detections)
-        mind = min(int(ro.min_detections), md)
+        mind = int(ro.min_detections)
         dev = self.device
         depth = max(int(depth), 1)
         keys = ("obj_ids", "obj_probs", "attr_ids", "attr_probs", "boxes", "roi_features", "preds_per_image",
@@ -338,9 +346,13 @@ class FRCNN:
             pending = []
 
             def collect(sl):
-                sl["ev_out"].synchronize()
-                out = OrderedDict((k, sl["host"][k].numpy().copy()) for k in keys)
-                out["preds_per_image"] = out["preds_per_image"].astype(np.int64)
+                if on_device:                            # fresh tensors per forward (run() allocates its outputs): no copy needed
+                    sl["ev_done"].synchronize()
+                    out = OrderedDict((k, sl["dev_out"][k]) for k in keys)
+                else:
+                    sl["ev_out"].synchronize()
+                    out = OrderedDict((k, sl["host"][k].numpy().copy()) for k in keys)
+                    out["preds_per_image"] = out["preds_per_image"].astype(np.int64)
                 out["sizes"] = sl["sizes"].astype(np.int64)
                 out["scales_yx"] = sl["scales"]
                 sl["busy"] = False
@@ -390,13 +402,14 @@ class FRCNN:
                             t = self.run(x, sizes, scales, md, mind, ro.nms_thresh, float(pad_value), slot=k)
                         sl["_ka"] = (t.pop("_keepalive"), part)  # decoded images stay alive until this slot is reused
                         sl["ev_done"].record(compute)
-                        if sl["host"] is None or sl["host"]["roi_features"].shape != t["roi_features"].shape:
-                            sl["host"] = {k_: torch.empty(t[k_].shape, dtype=t[k_].dtype).pin_memory() for k_ in keys}
-                        with torch.cuda.stream(s_out):
-                            s_out.wait_event(sl["ev_done"])
-                            for k_ in keys:
-                                sl["host"][k_].copy_(t[k_], non_blocking=True)
-                            sl["ev_out"].record(s_out)
+                        if not on_device:
+                            if sl["host"] is None or sl["host"]["roi_features"].shape != t["roi_features"].shape:
+                                sl["host"] = {k_: torch.empty(t[k_].shape, dtype=t[k_].dtype).pin_memory() for k_ in keys}
+                            with torch.cuda.stream(s_out):
+                                s_out.wait_event(sl["ev_done"])
+                                for k_ in keys:
+                                    sl["host"][k_].copy_(t[k_], non_blocking=True)
+                                sl["ev_out"].record(s_out)
                         sl["dev_out"], sl["sizes"], sl["scales"], sl["busy"] = t, sizes, scales, True
                         pending.append(sl)
                         if len(pending) >= depth:
