@@ -383,6 +383,8 @@ int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMa
   int bn = (cout_pad % 256 == 0) ? 256 : (cout_pad % 128 == 0 ? 128 : 64);
   if (K <= smallk && cout_pad % 128 == 0) bn = 128;
   if (out_f32) { VLTK_CHECK(cout_pad % 128 == 0, "conv_tcx: fp32 output needs cout_pad %% 128 == 0"); bn = 128; }
+  static const int res_bn = [] { const char* e = getenv("VLTK_TCX_RES_BN"); return e ? atoi(e) : 256; }();   // tuning knob
+  if (p.residual && bn == 256 && res_bn == 128) bn = 128;
   if (p.residual && bn == 64) { VLTK_CHECK(false, "conv_tcx: residual layers need Cout %% 128 == 0"); }
   if (cache->maps.size() > 8192) cache->maps.clear();
   auto cached = [&](const TensorMapCache::Key& k, CUtensorMap* dst, auto make) -> int {
