@@ -161,6 +161,10 @@ int vltk_conv2d_dual_nhwc(const void* x, const float* weight, const void* x2, co
  * Defaults: 32768 and 0 (environment: VLTK_CTA2, VLTK_CTA2_RES).  Both kernels accumulate in the same order and
  * produce bit-identical outputs.  Always returns 0. */
 int vltk_conv_tc_set_cta_pairs(int min_pixels, int residual_layers);
+/* The same switch for the exact_tc kernels (csrc/conv_tcx.cu): layers with a 256-wide cout tile and at least
+ * `min_pixels` output pixels run on CTA pairs (five 32 KB operand stages instead of three 48 KB ones); 0 = never,
+ * negative = unchanged.  Default 32768 (environment: VLTK_TCX_CTA2).  Bit-identical outputs.  Always returns 0. */
+int vltk_conv_tcx_set_cta_pairs(int min_pixels);
 
 /* One PART of the model through the engine's own layers, weights and arithmetic mode, on caller-provided DEVICE fp32
  * tensors (converted to / from the mode's activation type inside): the teacher-forced stage tests feed the oracle's

@@ -208,6 +208,32 @@ def test_cta_pair_kernel_is_bit_identical_to_single_cta_kernel(dev, case):
     assert ((y3.float().cpu().double() - ref.double()).abs() <= 2.0 ** -7 * (ref.double().abs() + 1e-2)).all()
 
 
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_exact_tc_cta_pair_kernel_is_bit_identical_to_single_cta_kernel(dev, case):
+    """conv_tcx_kernel<PAIR> (exact_tc on CTA pairs: five 32 KB stages, half a W tile per CTA) runs the same passes,
+    k-blocks and chunk promotions in the same order as the single-CTA kernel: bit-identical outputs (fp32 inputs,
+    split on the way in), fp32-faithful against an fp64 evaluation."""
+    from vltk_b200 import stages
+    n, h, w, cin, cout, k, pad, dil, has_res = case
+    g = torch.Generator().manual_seed(n * 1000 + cin + k + 5)
+    x = torch.randn(n, h, w, cin, generator=g).to(dev)
+    wt = (torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5).to(dev)
+    sc = (torch.rand(cout, generator=g) * 0.5 + 0.75).to(dev)
+    sh = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    res = torch.randn(n, h, w, cout, generator=g).to(dev) if has_res else None
+    try:
+        stages.set_cta_pairs_exact(0)
+        y1 = stages.conv2d_nhwc(x, wt, sc, sh, res, 1, pad, dil, True, mode="exact_tc")
+        stages.set_cta_pairs_exact(1)
+        y2 = stages.conv2d_nhwc(x, wt, sc, sh, res, 1, pad, dil, True, mode="exact_tc")
+        y2b = stages.conv2d_nhwc(x, wt, sc, sh, res, 1, pad, dil, True, mode="exact_tc")
+    finally:
+        stages.set_cta_pairs_exact(CTA_PAIRS_DEFAULT)
+    assert torch.equal(y2, y1) and torch.equal(y2b, y2)
+    ref = _ref_conv(x, wt, sc, sh, res, 1, pad, dil, True).double()
+    assert ((y2.cpu().double() - ref).abs() <= 3e-6 * (ref.abs() + 1.0)).all()
+
+
 @pytest.mark.parametrize("rois,cin,cout", [(1, 512, 256), (3, 512, 2048), (80, 512, 2048)])
 def test_cta_pair_fused_meanpool_and_concat_are_bit_identical_to_single_cta(dev, rois, cin, cout):
     """The ROI-aligned fused 14x14 mean (one ROI per CTA pair: rank 0 rows [0,128), rank 1 rows [128,196)) and the

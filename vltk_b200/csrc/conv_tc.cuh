@@ -58,6 +58,8 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
 //   w3: fp16 [cout_pad][3*K] = rows of (WA | WB | WC), built by pack_weight_h3; p.scale must already carry the
 //   per-row 2^-s of the packing.  out_dtype DT_H2 (optional DT_H2 residual) or DT_F32 (cout_pad % 128 == 0).
 int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMapCache* cache, cudaStream_t st);
+// conv_tcx layers with a 256-wide cout tile and at least `min_pixels` output pixels run on CTA pairs (0 = never)
+void conv_tcx_set_cta_pairs(int min_pixels);
 
 // CTA-pair (tcgen05 cta_group::2) dispatch: layers with BN = 256, bf16 output and at least `min_pixels` output pixels
 // run on conv_tc3_kernel (0 = never); `residual_layers` = 0 keeps residual / pooled layers on v2.  Negative = unchanged.

@@ -23,6 +23,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
@@ -54,10 +55,10 @@ struct TcxParams {
   int out_plane, res_plane;                    // column offset of the lo' plane in y / residual
 };
 
-template <int BN, int STAGES, int EG>
+template <int BN, int STAGES, int EG, bool PAIR = false>
 struct SmemX {
   static constexpr int NS_OWN = BN / XSLAB / EG;                 // 64-column units per epilogue group
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int B_STAGE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;   // a CTA of a pair stages half of the W tile
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
   static constexpr int OFF_OUT = STAGES * STAGE_BYTES;
@@ -81,12 +82,19 @@ __device__ __forceinline__ void split_h2(float x, float& hi, float& lo) {
   lo = fminf(fmaxf((x - hi) * LO_SCALE, -65504.f), 65504.f);
 }
 
-template <int BN, int STAGES, int EG, bool HAS_RES, bool OUT_F32, bool BIGREG>
+// PAIR: CTA pairs (tcgen05 cta_group::2, launched as 2-CTA clusters), as conv_tc3_kernel does for the bf16 mode: the pair
+// computes a 256-pixel x 256-cout tile with ONE MMA stream issued by the leader (rank 0); each CTA stages its own 128
+// im2col rows and HALF of the W tile (a stage is 32 KB instead of 48 KB -> five stages instead of three, and W crosses
+// L2 -> SM once per pair); all TMA bytes of a stage complete on the leader's full barrier, tcgen05.commit multicasts to
+// both CTAs' empty / accumulator-full barriers, each CTA promotes and finishes its own 128 TMEM lanes and releases the
+// chunk accumulator on the leader's barrier.  Same k-block / pass / chunk order, same arithmetic: bit-identical outputs.
+template <int BN, int STAGES, int EG, bool HAS_RES, bool OUT_F32, bool BIGREG, bool PAIR = false>
 __global__ void __launch_bounds__(128 + 128 * EG, 1)
 conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, TcxParams p) {
-  using S = SmemX<BN, STAGES, EG>;
+  using S = SmemX<BN, STAGES, EG, PAIR>;
   static_assert(!(HAS_RES && OUT_F32), "fp32 output has no residual path");
+  static_assert(!PAIR || BN == 256, "CTA pairs share one 256-cout W tile");
   constexpr int NS_OWN = S::NS_OWN;
   extern __shared__ __align__(1024) unsigned char smem_dynx[];
   const uint32_t base = smem_u32(smem_dynx);
@@ -108,6 +116,11 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = (p.num_kb + p.chunk_kb - 1) / p.chunk_kb;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  // work unit w (a tile, or a pair tile) -> first output row of THIS CTA and first cout
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, unit_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto unit_m0 = [&](uint32_t mt) -> uint32_t { return PAIR ? (mt * 2 + rank) * BM : mt * BM; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY);
@@ -115,15 +128,24 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * EG); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), (PAIR ? 2 : 1) * 4 * EG); }
     for (int g = 0; g < EG; ++g) mbar_init(res_bar(g), 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
+  if constexpr (PAIR) {
+    cluster_sync_all();                            // barriers of both CTAs are initialised before anyone signals them
+    if (warp == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(2 * BN) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+  } else {
+    if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if constexpr (PAIR) cluster_sync_all();
 
   // Programmatic dependent launch (see conv_tc2_kernel): nothing above touched an activation.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -138,11 +160,11 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ================= TMA producer =================
     int stage = 0; uint32_t phase = 0;
     const int cb_mask = (1 << p.lg_cblocks) - 1;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    for (int t = unit0; t < p.num_tiles; t += unit_step) {
       uint32_t mt, nt, q, ow0, img0, oh0;
       p.fd_ntiles.divmod((uint32_t)t, mt, nt);
       const int n0 = (int)nt * BN;
-      const uint32_t m0 = mt * BM;
+      const uint32_t m0 = unit_m0(mt);
       p.fd_ow.divmod(m0, q, ow0);
       p.fd_oh.divmod(q, img0, oh0);
       const int bw = (int)ow0 * p.stride - p.pad, bh = (int)oh0 * p.stride - p.pad;
@@ -156,21 +178,28 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int kh = p.KW == 1 ? tap : (tap * 11) >> 5;      // tap / 3 for tap < 9
             const int kw = tap - kh * p.KW;
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), S::STAGE_BYTES);
-            tma_load_im2col_4d(sA + stage * A_STAGE_BYTES, &tmA, full_bar(stage), a_off + cb * BK, bw, bh, (int)img0,
-                               (uint16_t)(kw * p.dil), (uint16_t)(kh * p.dil));
-            tma_load_2d(sB + stage * S::B_STAGE_BYTES, &tmB, full_bar(stage), b_off + kb * BK, n0);
+            if constexpr (PAIR) {
+              if (leader) mbar_expect_tx(full_bar(stage), 2 * S::STAGE_BYTES);   // both CTAs' bytes land on the leader's barrier
+              tma2_load_im2col_4d(sA + stage * A_STAGE_BYTES, &tmA, full_bar(stage), a_off + cb * BK, bw, bh, (int)img0,
+                                  (uint16_t)(kw * p.dil), (uint16_t)(kh * p.dil));
+              tma2_load_2d(sB + stage * S::B_STAGE_BYTES, &tmB, full_bar(stage), b_off + kb * BK, n0 + (int)rank * (BN / 2));
+            } else {
+              mbar_expect_tx(full_bar(stage), S::STAGE_BYTES);
+              tma_load_im2col_4d(sA + stage * A_STAGE_BYTES, &tmA, full_bar(stage), a_off + cb * BK, bw, bh, (int)img0,
+                                 (uint16_t)(kw * p.dil), (uint16_t)(kh * p.dil));
+              tma_load_2d(sB + stage * S::B_STAGE_BYTES, &tmB, full_bar(stage), b_off + kb * BK, n0);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ================= MMA issuer =================
-    constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ================= MMA issuer (PAIR: the leader CTA issues for both SMs) =================
+    constexpr uint32_t idesc = make_idesc_f16(PAIR ? 2 * BM : BM, BN);
     int stage = 0; uint32_t phase = 0;
     int seq = 0;                                   // chunk sequence number of this CTA (across tiles)
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    for (int t = unit0; t < p.num_tiles; t += unit_step) {
       for (int c0 = 0; c0 < p.num_kb; c0 += p.chunk_kb, ++seq) {
         const int nkb = min(p.chunk_kb, p.num_kb - c0) * 3;
         const int acc = seq & 1;
@@ -183,12 +212,14 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tc_fence_after();
           const uint32_t a = sA + stage * A_STAGE_BYTES, b = sB + stage * S::B_STAGE_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16(d, make_smem_desc(a + k * UMMA_K * 2), make_smem_desc(b + k * UMMA_K * 2), idesc, (kb | k) ? 1u : 0u);
-          umma_commit(empty_bar(stage));
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            if constexpr (PAIR) umma2_bf16(d, make_smem_desc(a + k * UMMA_K * 2), make_smem_desc(b + k * UMMA_K * 2), idesc, (kb | k) ? 1u : 0u);
+            else umma_bf16(d, make_smem_desc(a + k * UMMA_K * 2), make_smem_desc(b + k * UMMA_K * 2), idesc, (kb | k) ? 1u : 0u);
+          }
+          if constexpr (PAIR) umma2_commit_mc(empty_bar(stage)); else umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));
+        if constexpr (PAIR) umma2_commit_mc(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
       }
     }
   }
@@ -210,10 +241,10 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t rphase = 0;
     int seq = 0;
     float run[NS_OWN][XSLAB];
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    for (int t = unit0; t < p.num_tiles; t += unit_step) {
       uint32_t umt, unt;
       p.fd_ntiles.divmod((uint32_t)t, umt, unt);
-      const int n0 = (int)unt * BN, m0 = (int)umt * BM;
+      const int n0 = (int)unt * BN, m0 = (int)unit_m0(umt);
       // scale / shift of my columns (read in the tile finish, at least one chunk of MMAs from now)
       for (int i = et; i < NS_OWN * XSLAB; i += 128) {
         const int col = n0 + (g + (i >> 6) * EG) * XSLAB + (i & 63);
@@ -252,7 +283,9 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));   // hand the accumulator back to the MMA warp
+        if (lane == 0) {                               // hand the accumulator back to the MMA warp (PAIR: the leader's)
+          if (PAIR && !leader) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc));
+        }
       }
       // ---- tile finish: scale/shift (+ residual) (+ ReLU) -> two fp16 planes (or fp32) -> TMA store
 #pragma unroll
@@ -333,36 +366,48 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<2 * BN>(tmem_base);
+  if constexpr (PAIR) {
+    cluster_sync_all();                            // the peer may still be reading / the leader still issuing into its TMEM
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
+  } else {
+    if (warp == 2) tmem_dealloc<2 * BN>(tmem_base);
+  }
 }
 
-template <int BN, int STAGES, int EG, bool HAS_RES, bool OUT_F32, bool BIGREG>
+template <int BN, int STAGES, int EG, bool HAS_RES, bool OUT_F32, bool BIGREG, bool PAIR = false>
 int launchx(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& my, const CUtensorMap& mr, TcxParams tp,
             int cout_pad, cudaStream_t st) {
-  using S = SmemX<BN, STAGES, EG>;
-  auto kern = conv_tcx_kernel<BN, STAGES, EG, HAS_RES, OUT_F32, BIGREG>;
+  using S = SmemX<BN, STAGES, EG, PAIR>;
+  auto kern = conv_tcx_kernel<BN, STAGES, EG, HAS_RES, OUT_F32, BIGREG, PAIR>;
   static DeviceOnce once;
   if (once.first()) VLTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   tp.n_tiles = cout_pad / BN;
   tp.fd_ntiles.init((uint32_t)tp.n_tiles);
-  const int64_t tiles = ceil_div64(tp.M, BM) * tp.n_tiles;
+  const int64_t row_tiles = ceil_div64(tp.M, BM);
+  const int64_t tiles = (PAIR ? ceil_div64(row_tiles, 2) : row_tiles) * tp.n_tiles;   // PAIR: 256-row pair tiles
   VLTK_CHECK(tiles < (1ll << 31), "conv_tcx: too many tiles");
   tp.num_tiles = (int)tiles;
-  const int grid = (int)std::min<int64_t>(tiles, tc_num_sms());   // persistent: one CTA per SM
+  // persistent: one CTA (or one CTA pair) per SM (pair of SMs)
+  const int grid = PAIR ? 2 * (int)std::min<int64_t>(tiles, tc_num_sms() / 2) : (int)std::min<int64_t>(tiles, tc_num_sms());
   static const bool use_pdl = [] { const char* e = getenv("VLTK_PDL"); return !(e && e[0] == '0'); }();
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128 + 128 * EG); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (PAIR) { attr[na].id = cudaLaunchAttributeClusterDimension; attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; ++na; }
+  if (use_pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+  cfg.attrs = attr; cfg.numAttrs = na;
   VLTK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, my, mr, tp));
   VLTK_LAUNCH_CHECK();
   return 0;
 }
 
+std::atomic<int> g_tcx_cta2_min_m{[] { const char* e = getenv("VLTK_TCX_CTA2"); return e ? atoi(e) : 32768; }()};
+
 }  // namespace
+
+void conv_tcx_set_cta_pairs(int min_pixels) { if (min_pixels >= 0) g_tcx_cta2_min_m.store(min_pixels); }
 
 int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMapCache* cache, cudaStream_t st) {
   const bool out_f32 = p.out_dtype == DT_F32;
@@ -386,6 +431,8 @@ int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMa
   static const int res_bn = [] { const char* e = getenv("VLTK_TCX_RES_BN"); return e ? atoi(e) : 256; }();   // tuning knob
   if (p.residual && bn == 256 && res_bn == 128) bn = 128;
   if (p.residual && bn == 64) { VLTK_CHECK(false, "conv_tcx: residual layers need Cout %% 128 == 0"); }
+  // CTA pairs for the wide layers with enough rows to fill 74 pairs (all of res5); VLTK_TCX_CTA2=0 switches them off
+  const bool pair = bn == 256 && !out_f32 && g_tcx_cta2_min_m.load() > 0 && M >= g_tcx_cta2_min_m.load();
   if (cache->maps.size() > 8192) cache->maps.clear();
   auto cached = [&](const TensorMapCache::Key& k, CUtensorMap* dst, auto make) -> int {
     auto it = cache->maps.find(k);
@@ -399,8 +446,9 @@ int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMa
   if (cached(TensorMapCache::Key(p.x, p.N, p.H, p.W, p.Cin, p.ldx, p.KH, p.stride, p.pad, p.dil, 10), &ma, [&](CUtensorMap* d) {
         return tc_encode_im2col(d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.x, p.N, p.H, p.W, 2 * p.Cin, p.ldx, 2, p.KH, p.KW, p.stride, p.pad, p.dil);
       })) return -1;
-  if (cached(TensorMapCache::Key(w3, K, cout_pad, bn, 0, 0, 0, 0, 0, 0, 11), &mb, [&](CUtensorMap* d) {
-        return tc_encode_tiled(d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, w3, (uint64_t)3 * K, (uint64_t)cout_pad, (uint64_t)3 * K * 2, BK, (uint32_t)bn, true);
+  const int b_rows = pair ? bn / 2 : bn;           // a CTA of a pair loads half of the W tile
+  if (cached(TensorMapCache::Key(w3, K, cout_pad, b_rows, 0, 0, 0, 0, 0, 0, 11), &mb, [&](CUtensorMap* d) {
+        return tc_encode_tiled(d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, w3, (uint64_t)3 * K, (uint64_t)cout_pad, (uint64_t)3 * K * 2, BK, (uint32_t)b_rows, true);
       })) return -1;
   if (cached(TensorMapCache::Key(p.y, (int)M, p.Cout, p.ldy, out_f32 ? 1 : 0, 0, 0, 0, 0, 0, 12), &my, [&](CUtensorMap* d) {
         return out_f32 ? tc_encode_tiled(d, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.y, (uint64_t)p.Cout, (uint64_t)M, (uint64_t)p.ldy * 4, 32, BM, false)
@@ -422,6 +470,11 @@ int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMa
   t.out_plane = p.Cout; t.res_plane = p.Cout;
   t.fd_ow.init((uint32_t)p.OW); t.fd_oh.init((uint32_t)p.OH);
   if (out_f32) return launchx<128, 5, 2, false, true, false>(ma, mb, my, mr, t, cout_pad, st);
+  if (pair) {
+    VLTK_CHECK(M + 256 < (1ll << 31), "conv_tcx: M too large for pair tiles");
+    return p.residual ? launchx<256, 5, 2, true, false, true, true>(ma, mb, my, mr, t, cout_pad, st)
+                      : launchx<256, 5, 2, false, false, true, true>(ma, mb, my, mr, t, cout_pad, st);
+  }
   if (p.residual) {
     if (bn == 256) return launchx<256, 3, 2, true, false, true>(ma, mb, my, mr, t, cout_pad, st);
     return launchx<128, 5, 2, true, false, false>(ma, mb, my, mr, t, cout_pad, st);

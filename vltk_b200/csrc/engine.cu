@@ -1398,6 +1398,11 @@ int vltk_conv_tc_set_cta_pairs(int min_pixels, int residual_layers) {
   return 0;
 }
 
+int vltk_conv_tcx_set_cta_pairs(int min_pixels) {
+  conv_tcx_set_cta_pairs(min_pixels);
+  return 0;
+}
+
 int vltk_linear_tc3(const float* x, const float* weight, const float* bias, float* y, int m, int k, int n, int relu,
                     void* stream) {
   VLTK_CHECK(x && weight && y, "linear_tc3: null argument");

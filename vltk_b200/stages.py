@@ -100,6 +100,11 @@ def set_cta_pairs(min_pixels=-1, residual_layers=-1):
     _lib.lib().vltk_conv_tc_set_cta_pairs(int(min_pixels), int(residual_layers))
 
 
+def set_cta_pairs_exact(min_pixels=-1):
+    """The same switch for the exact_tc kernels (vltk_conv_tcx_set_cta_pairs); 0 = never, -1 = unchanged."""
+    _lib.lib().vltk_conv_tcx_set_cta_pairs(int(min_pixels))
+
+
 def linear_tc3(x, weight, bias=None, relu=False):
     """F.linear(x, weight, bias) on the tensor pipe with split-bf16 (hi*hi + lo*hi + hi*lo) operands
     and fp32 accumulate/output — how the predictor linears (frcnn.py:1729-1737) run in bf16 mode."""
