@@ -11,10 +11,12 @@ dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 R = int(os.environ.get("PROBE_ROIS", "2400"))
 REPS = int(os.environ.get("PROBE_REPS", "3"))
+MODE = os.environ.get("PROBE_MODE", "bf16")        # exact_tc: fp32 tensors through conv_tcx (concat has no stage entry there)
 
 
 def act(c):
-    return torch.randn(R, 14, 14, c, device=dev).bfloat16()
+    x = torch.randn(R, 14, 14, c, device=dev)
+    return x if MODE == "exact_tc" else x.bfloat16()
 
 
 def w(cout, cin, k=1):
@@ -28,17 +30,17 @@ def run(name):
         f = lambda: stages.conv2d_dual_nhwc(x, w1, x2, w2, None, stride2=1, relu=True)
     elif name == "conv1":
         x, wt = act(2048), w(512, 2048); sc, sh = one(512)
-        f = lambda: stages.conv2d_nhwc(x, wt, sc, sh, None, 1, 0, 1, True, mode="bf16", tensor_cores=True)
+        f = lambda: stages.conv2d_nhwc(x, wt, sc, sh, None, 1, 0, 1, True, mode=MODE, tensor_cores=True)
     elif name == "conv2":
         x, wt = act(512), w(512, 512, 3); sc, sh = one(512)
-        f = lambda: stages.conv2d_nhwc(x, wt, sc, sh, None, 1, 2, 2, True, mode="bf16", tensor_cores=True)
+        f = lambda: stages.conv2d_nhwc(x, wt, sc, sh, None, 1, 2, 2, True, mode=MODE, tensor_cores=True)
     elif name in ("conv3res", "conv3"):
         x, wt = act(512), w(2048, 512); sc, sh = one(2048)
         res = act(2048) if name == "conv3res" else None
-        f = lambda: stages.conv2d_nhwc(x, wt, sc, sh, res, 1, 0, 1, True, mode="bf16", tensor_cores=True)
+        f = lambda: stages.conv2d_nhwc(x, wt, sc, sh, res, 1, 0, 1, True, mode=MODE, tensor_cores=True)
     elif name == "c512":
         x, wt = act(512), w(512, 512); sc, sh = one(512)
-        f = lambda: stages.conv2d_nhwc(x, wt, sc, sh, None, 1, 0, 1, True, mode="bf16", tensor_cores=True)
+        f = lambda: stages.conv2d_nhwc(x, wt, sc, sh, None, 1, 0, 1, True, mode=MODE, tensor_cores=True)
     else:
         raise SystemExit(f"unknown layer {name}")
     for _ in range(REPS):

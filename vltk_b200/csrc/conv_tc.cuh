@@ -57,7 +57,10 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
 // planes, three kind::f16 passes per K chunk, chunk sums promoted to an fp32 register accumulator.
 //   w3: fp16 [cout_pad][3*K] = rows of (WA | WB | WC), built by pack_weight_h3; p.scale must already carry the
 //   per-row 2^-s of the packing.  out_dtype DT_H2 (optional DT_H2 residual) or DT_F32 (cout_pad % 128 == 0).
-int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMapCache* cache, cudaStream_t st);
+// Optional `concat` (x2 / ldx2 / H2 / W2 / Cin2 / stride2; w2 unused): K-concatenation as in conv_tc_launch — x2 is a
+// DT_H2 tensor, and every plane of a w3 row is the concatenation [K primary | Cin2] (planes 3 * (K + Cin2) per row).
+int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMapCache* cache, cudaStream_t st,
+                    const TcConcat* concat = nullptr);
 // conv_tcx layers with a 256-wide cout tile and at least `min_pixels` output pixels run on CTA pairs (0 = never)
 void conv_tcx_set_cta_pairs(int min_pixels);
 

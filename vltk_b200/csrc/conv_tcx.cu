@@ -52,6 +52,7 @@ struct TcxParams {
   int cin;                                     // channel offset of the lo' plane in x (= Cin)
   int K;                                       // element offset between the weight planes WA | WB | WC
   int n_tiles, num_tiles, chunk_kb;
+  int kb1, cin2, stride2;                      // K-concatenated second operand: k-blocks [kb1, num_kb) come from tmA2
   int out_plane, res_plane;                    // column offset of the lo' plane in y / residual
 };
 
@@ -90,8 +91,9 @@ __device__ __forceinline__ void split_h2(float x, float& hi, float& lo) {
 // chunk accumulator on the leader's barrier.  Same k-block / pass / chunk order, same arithmetic: bit-identical outputs.
 template <int BN, int STAGES, int EG, bool HAS_RES, bool OUT_F32, bool BIGREG, bool PAIR = false>
 __global__ void __launch_bounds__(128 + 128 * EG, 1)
-conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, TcxParams p) {
+conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY,
+                const __grid_constant__ CUtensorMap tmR, TcxParams p) {
   using S = SmemX<BN, STAGES, EG, PAIR>;
   static_assert(!(HAS_RES && OUT_F32), "fp32 output has no residual path");
   static_assert(!PAIR || BN == 256, "CTA pairs share one 256-cout W tile");
@@ -124,6 +126,7 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY);
+    if (p.kb1 < p.num_kb) tma_prefetch_desc(&tmA2);
     if (HAS_RES) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
@@ -168,25 +171,30 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       p.fd_ow.divmod(m0, q, ow0);
       p.fd_oh.divmod(q, img0, oh0);
       const int bw = (int)ow0 * p.stride - p.pad, bh = (int)oh0 * p.stride - p.pad;
+      const int bw2 = (int)ow0 * p.stride2, bh2 = (int)oh0 * p.stride2;
       for (int c0 = 0; c0 < p.num_kb; c0 += p.chunk_kb) {
         const int c1 = min(c0 + p.chunk_kb, p.num_kb);
         for (int ps = 0; ps < 3; ++ps) {
           const int a_off = ps == 0 ? p.cin : 0;
           const int b_off = ps == 0 ? p.K : (ps == 1 ? 2 * p.K : 0);
           for (int kb = c0; kb < c1; ++kb) {
+            // A box of this k-block: primary tensor (tap, channel block) or, past kb1, the concatenated 1x1 operand
+            const bool second = kb >= p.kb1;
             const int tap = kb >> p.lg_cblocks, cb = kb & cb_mask;
             const int kh = p.KW == 1 ? tap : (tap * 11) >> 5;      // tap / 3 for tap < 9
             const int kw = tap - kh * p.KW;
+            const CUtensorMap* ma = second ? &tmA2 : &tmA;
+            const int ac = second ? (ps == 0 ? p.cin2 : 0) + (kb - p.kb1) * BK : a_off + cb * BK;
+            const int aw = second ? bw2 : bw, ah = second ? bh2 : bh;
+            const uint16_t ow_off = second ? (uint16_t)0 : (uint16_t)(kw * p.dil), oh_off = second ? (uint16_t)0 : (uint16_t)(kh * p.dil);
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if constexpr (PAIR) {
               if (leader) mbar_expect_tx(full_bar(stage), 2 * S::STAGE_BYTES);   // both CTAs' bytes land on the leader's barrier
-              tma2_load_im2col_4d(sA + stage * A_STAGE_BYTES, &tmA, full_bar(stage), a_off + cb * BK, bw, bh, (int)img0,
-                                  (uint16_t)(kw * p.dil), (uint16_t)(kh * p.dil));
+              tma2_load_im2col_4d(sA + stage * A_STAGE_BYTES, ma, full_bar(stage), ac, aw, ah, (int)img0, ow_off, oh_off);
               tma2_load_2d(sB + stage * S::B_STAGE_BYTES, &tmB, full_bar(stage), b_off + kb * BK, n0 + (int)rank * (BN / 2));
             } else {
               mbar_expect_tx(full_bar(stage), S::STAGE_BYTES);
-              tma_load_im2col_4d(sA + stage * A_STAGE_BYTES, &tmA, full_bar(stage), a_off + cb * BK, bw, bh, (int)img0,
-                                 (uint16_t)(kw * p.dil), (uint16_t)(kh * p.dil));
+              tma_load_im2col_4d(sA + stage * A_STAGE_BYTES, ma, full_bar(stage), ac, aw, ah, (int)img0, ow_off, oh_off);
               tma_load_2d(sB + stage * S::B_STAGE_BYTES, &tmB, full_bar(stage), b_off + kb * BK, n0);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -375,8 +383,8 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 template <int BN, int STAGES, int EG, bool HAS_RES, bool OUT_F32, bool BIGREG, bool PAIR = false>
-int launchx(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& my, const CUtensorMap& mr, TcxParams tp,
-            int cout_pad, cudaStream_t st) {
+int launchx(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const CUtensorMap& my, const CUtensorMap& mr,
+            TcxParams tp, int cout_pad, cudaStream_t st) {
   using S = SmemX<BN, STAGES, EG, PAIR>;
   auto kern = conv_tcx_kernel<BN, STAGES, EG, HAS_RES, OUT_F32, BIGREG, PAIR>;
   static DeviceOnce once;
@@ -398,7 +406,7 @@ int launchx(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& my,
   if (PAIR) { attr[na].id = cudaLaunchAttributeClusterDimension; attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; ++na; }
   if (use_pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
   cfg.attrs = attr; cfg.numAttrs = na;
-  VLTK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, my, mr, tp));
+  VLTK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, ma2, mb, my, mr, tp));
   VLTK_LAUNCH_CHECK();
   return 0;
 }
@@ -409,7 +417,8 @@ std::atomic<int> g_tcx_cta2_min_m{[] { const char* e = getenv("VLTK_TCX_CTA2"); 
 
 void conv_tcx_set_cta_pairs(int min_pixels) { if (min_pixels >= 0) g_tcx_cta2_min_m.store(min_pixels); }
 
-int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMapCache* cache, cudaStream_t st) {
+int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMapCache* cache, cudaStream_t st,
+                    const TcConcat* cc) {
   const bool out_f32 = p.out_dtype == DT_F32;
   VLTK_CHECK(p.in_dtype == DT_H2 && (out_f32 || p.out_dtype == DT_H2), "conv_tcx: split-fp16 activations in, split-fp16 or fp32 out");
   VLTK_CHECK(p.Cin % BK == 0 && ((p.Cin / BK) & (p.Cin / BK - 1)) == 0, "conv_tcx: Cin=%d must be 64 * 2^k", p.Cin);
@@ -422,7 +431,12 @@ int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMa
   const int64_t M = (int64_t)p.N * p.OH * p.OW;
   if (M == 0) return 0;
   VLTK_CHECK(M < (1ll << 31) - 512, "conv_tcx: M=%lld output pixels exceed the 32-bit tile arithmetic", (long long)M);
-  const int K = p.KH * p.KW * p.Cin;
+  if (cc) {
+    VLTK_CHECK(p.KH == 1 && p.KW == 1 && p.pad == 0, "conv_tcx: K-concatenation needs a 1x1 primary convolution");
+    VLTK_CHECK(cc->x2 && cc->Cin2 % BK == 0 && cc->ldx2 == 2 * cc->Cin2 && cc->stride2 >= 1, "conv_tcx: bad concatenated operand");
+    VLTK_CHECK((cc->H2 - 1) / cc->stride2 + 1 == p.OH && (cc->W2 - 1) / cc->stride2 + 1 == p.OW, "conv_tcx: concatenated operand does not map onto the output grid");
+  }
+  const int K = p.KH * p.KW * p.Cin + (cc ? cc->Cin2 : 0);     // row length of one weight plane
   static const int smallk = [] { const char* e = getenv("VLTK_TCX_SMALLK"); return e ? atoi(e) : 256; }();
   static const int chunk = [] { const char* e = getenv("VLTK_TCX_CHUNK"); return e ? std::max(1, atoi(e)) : 4; }();
   int bn = (cout_pad % 256 == 0) ? 256 : (cout_pad % 128 == 0 ? 128 : 64);
@@ -442,9 +456,14 @@ int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMa
     } else *dst = it->second;
     return 0;
   };
-  CUtensorMap ma, mb, my, mr;
+  CUtensorMap ma, ma2, mb, my, mr;
   if (cached(TensorMapCache::Key(p.x, p.N, p.H, p.W, p.Cin, p.ldx, p.KH, p.stride, p.pad, p.dil, 10), &ma, [&](CUtensorMap* d) {
         return tc_encode_im2col(d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.x, p.N, p.H, p.W, 2 * p.Cin, p.ldx, 2, p.KH, p.KW, p.stride, p.pad, p.dil);
+      })) return -1;
+  ma2 = ma;
+  if (cc &&
+      cached(TensorMapCache::Key(cc->x2, p.N, cc->H2, cc->W2, cc->Cin2, cc->ldx2, 1, cc->stride2, 0, 1, 10), &ma2, [&](CUtensorMap* d) {
+        return tc_encode_im2col(d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, cc->x2, p.N, cc->H2, cc->W2, 2 * cc->Cin2, cc->ldx2, 2, 1, 1, cc->stride2, 0, 1);
       })) return -1;
   const int b_rows = pair ? bn / 2 : bn;           // a CTA of a pair loads half of the W tile
   if (cached(TensorMapCache::Key(w3, K, cout_pad, b_rows, 0, 0, 0, 0, 0, 0, 11), &mb, [&](CUtensorMap* d) {
@@ -466,22 +485,24 @@ int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMa
   const int cblocks = p.Cin / BK;
   t.lg_cblocks = 0;
   while ((1 << t.lg_cblocks) < cblocks) ++t.lg_cblocks;
-  t.num_kb = p.KH * p.KW * cblocks; t.cin = p.Cin; t.K = K; t.chunk_kb = chunk;
+  t.kb1 = p.KH * p.KW * cblocks;
+  t.num_kb = t.kb1 + (cc ? cc->Cin2 / BK : 0); t.cin = p.Cin; t.K = K; t.chunk_kb = chunk;
+  t.cin2 = cc ? cc->Cin2 : 0; t.stride2 = cc ? cc->stride2 : 1;
   t.out_plane = p.Cout; t.res_plane = p.Cout;
   t.fd_ow.init((uint32_t)p.OW); t.fd_oh.init((uint32_t)p.OH);
-  if (out_f32) return launchx<128, 5, 2, false, true, false>(ma, mb, my, mr, t, cout_pad, st);
+  if (out_f32) return launchx<128, 5, 2, false, true, false>(ma, ma2, mb, my, mr, t, cout_pad, st);
   if (pair) {
     VLTK_CHECK(M + 256 < (1ll << 31), "conv_tcx: M too large for pair tiles");
-    return p.residual ? launchx<256, 5, 2, true, false, true, true>(ma, mb, my, mr, t, cout_pad, st)
-                      : launchx<256, 5, 2, false, false, true, true>(ma, mb, my, mr, t, cout_pad, st);
+    return p.residual ? launchx<256, 5, 2, true, false, true, true>(ma, ma2, mb, my, mr, t, cout_pad, st)
+                      : launchx<256, 5, 2, false, false, true, true>(ma, ma2, mb, my, mr, t, cout_pad, st);
   }
   if (p.residual) {
-    if (bn == 256) return launchx<256, 3, 2, true, false, true>(ma, mb, my, mr, t, cout_pad, st);
-    return launchx<128, 5, 2, true, false, false>(ma, mb, my, mr, t, cout_pad, st);
+    if (bn == 256) return launchx<256, 3, 2, true, false, true>(ma, ma2, mb, my, mr, t, cout_pad, st);
+    return launchx<128, 5, 2, true, false, false>(ma, ma2, mb, my, mr, t, cout_pad, st);
   }
-  if (bn == 256) return launchx<256, 3, 2, false, false, true>(ma, mb, my, mr, t, cout_pad, st);
-  if (bn == 128) return launchx<128, 5, 2, false, false, false>(ma, mb, my, mr, t, cout_pad, st);
-  return launchx<64, 6, 1, false, false, false>(ma, mb, my, mr, t, cout_pad, st);
+  if (bn == 256) return launchx<256, 3, 2, false, false, true>(ma, ma2, mb, my, mr, t, cout_pad, st);
+  if (bn == 128) return launchx<128, 5, 2, false, false, false>(ma, ma2, mb, my, mr, t, cout_pad, st);
+  return launchx<64, 6, 1, false, false, false>(ma, ma2, mb, my, mr, t, cout_pad, st);
 }
 
 }  // namespace vltk

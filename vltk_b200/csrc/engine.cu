@@ -50,6 +50,9 @@ struct Block {
   // Both frozen-BN scales are folded into the bf16 weights, the shifts are summed.
   LayerW c3f;               // w_nk = bf16(scale3 * W3), scale = nullptr, shift = shift3 + shift_sc
   bf16* scf_w = nullptr;    // bf16(scale_sc * W_sc)  [cout][cin]
+  // exact_tc: the same fusion on conv_tcx — w_h3 = planes of the fp32 rows [scale3 * W3 | scale_sc * W_sc], scale_x = the
+  // rows' 2^-s, shift = shift3 + shift_sc
+  LayerW c3x;
 };
 
 struct Tap { const void* p = nullptr; int64_t n = 0; DType dt = DT_F32; int c = 0; };   // c: channels per row (DT_H2)
@@ -296,6 +299,26 @@ int pack_block(vltk_frcnn* h, Block& B, const std::string& p, int cin, int mid, 
     VLTK_CUDA(cudaMemcpy(B.scf_w, fs.data(), fs.size() * 2, cudaMemcpyHostToDevice));
     if (upload(h, b3, &B.c3f.shift)) return -1;
   }
+  if (h->use_tcx && B.has_sc && B.c3.w_h3 && B.sc.w_h3 && cin % 64 == 0 && mid % 64 == 0) {
+    const auto* w3 = find(h, p + ".conv3.weight", (int64_t)cout * mid);
+    const auto* ws = find(h, p + ".shortcut.weight", (int64_t)cout * cin);
+    if (!w3 || !ws) return -2;
+    std::vector<float> s3(cout), b3(cout), ss(cout), bs(cout);
+    if (bn_fold(h, p + ".conv3.norm", cout, s3, b3) || bn_fold(h, p + ".shortcut.norm", cout, ss, bs)) return -2;
+    const int K = mid + cin;
+    std::vector<float> wk((size_t)cout * K);
+    for (int o = 0; o < cout; ++o) {
+      for (int c = 0; c < mid; ++c) wk[(size_t)o * K + c] = s3[o] * (*w3)[(size_t)o * mid + c];
+      for (int c = 0; c < cin; ++c) wk[(size_t)o * K + mid + c] = ss[o] * (*ws)[(size_t)o * cin + c];
+      b3[o] += bs[o];
+    }
+    B.c3x = B.c3;
+    B.c3x.scale = nullptr;
+    if (pack_h3(h, B.c3x, wk, cout, K, round_up(cout, 64), nullptr)) return -1;
+    std::vector<float> sh(std::max(B.c3.ldw, B.c3x.cout_pad), 0.f);
+    for (int o = 0; o < cout; ++o) sh[o] = b3[o];
+    if (upload(h, sh, &B.c3x.shift)) return -1;
+  }
   return 0;
 }
 
@@ -364,12 +387,12 @@ int run_conv(vltk_frcnn* h, const LayerW& L, const void* x, DType xdt, int N, in
     rec.e0 = get_event(); rec.e1 = get_event();
     cudaEventRecord(rec.e0, st);
   }
-  if ((pool || cc) && !tc) { set_error("internal: fused mean-pool / concat need the tensor-core path"); return -2; }
+  if ((pool && !tc) || (cc && !tc && !tcx)) { set_error("internal: fused mean-pool / concat need the tensor-core path"); return -2; }
   int rc;
   if (tcx) {
     VLTK_CHECK(ydt == DT_H2, "internal: run_conv on split-fp16 input writes split-fp16");
     p.scale = L.scale_x;
-    rc = conv_tcx_launch(p, L.w_h3, L.cout_pad, &h->tmaps, st);
+    rc = conv_tcx_launch(p, L.w_h3, L.cout_pad, &h->tmaps, st, cc);
   } else {
     VLTK_CHECK(xdt != DT_H2 && ydt != DT_H2, "internal: layer %dx%d k%d has no exact_tc weights", L.cin, L.cout, L.k);
     rc = tc ? conv_tc_launch(p, L.w_nk, L.cout_pad, &h->tmaps, st, nullptr, pool, cc) : conv_simt_launch(p, L.w_kn, L.ldw, st);
@@ -438,6 +461,13 @@ int run_block(vltk_frcnn* h, const Block& B, const void* x, int N, int H, int W,
     TcConcat cc;
     cc.x2 = x; cc.ldx2 = B.sc.cin_pad; cc.H2 = H; cc.W2 = W; cc.Cin2 = B.sc.cin; cc.stride2 = B.sc.stride; cc.w2 = B.scf_w;
     if (run_conv(h, B.c3f, t2, d, N, h1, w1, out, d, B.c3.ldw, nullptr, 0, 1, st, nullptr, nullptr, nullptr, &cc)) return -1;
+    *oh = h1; *ow = w1;
+    return 0;
+  }
+  if (fuse_sc && B.has_sc && B.c3x.w_h3 && h->use_tcx && d == DT_H2 && !pool) {
+    TcConcat cc;
+    cc.x2 = x; cc.ldx2 = 2 * B.sc.cin; cc.H2 = H; cc.W2 = W; cc.Cin2 = B.sc.cin; cc.stride2 = B.sc.stride;
+    if (run_conv(h, B.c3x, t2, d, N, h1, w1, out, d, B.c3.ldw, nullptr, 0, 1, st, nullptr, nullptr, nullptr, &cc)) return -1;
     *oh = h1; *ow = w1;
     return 0;
   }
