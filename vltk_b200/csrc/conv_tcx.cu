@@ -71,16 +71,14 @@ struct SmemX {
   static_assert(TOTAL <= 232448, "exceeds the 227 KB shared memory of one sm_100 CTA");
 };
 
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-
-// x -> (hi, lo') ; saturating (|x| > 65504 cannot be represented: documented limit of the mode)
-__device__ __forceinline__ void split_h2(float x, float& hi, float& lo) {
-  const float c = fminf(fmaxf(x, -65504.f), 65504.f);
-  hi = __half2float(__float2half_rn(c));
-  lo = fminf(fmaxf((x - hi) * LO_SCALE, -65504.f), 65504.f);
+// (x0, x1) -> packed fp16 pairs hi = fp16(x), lo' = fp16((x - hi) * 2^11); saturating to the largest finite fp16
+// (|x| > 65504 cannot be represented: documented limit of the mode).  7 instructions per pair: the tile finish is what
+// bounds the K <= 512 layers, so it works on packed fp32x2 / f16x2 throughout.
+__device__ __forceinline__ void split_pair(float2 x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x.y), "f"(x.x));
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  const float2 d = __fmul2_rn(make_float2(x.x - h.x, x.y - h.y), make_float2(LO_SCALE, LO_SCALE));   // both exact
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d.y), "f"(d.x));
 }
 
 // PAIR: CTA pairs (tcgen05 cta_group::2, launched as 2-CTA clusters), as conv_tc3_kernel does for the bf16 mode: the pair
@@ -334,11 +332,11 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int c = j * XSLAB + q * 8;
             const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + c), sc1 = *reinterpret_cast<const float4*>(s_scale + c + 4);
             const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + c), sh1 = *reinterpret_cast<const float4*>(s_shift + c + 4);
-            float y[8];
-            y[0] = fmaf(run[j][q * 8 + 0], sc0.x, sh0.x); y[1] = fmaf(run[j][q * 8 + 1], sc0.y, sh0.y);
-            y[2] = fmaf(run[j][q * 8 + 2], sc0.z, sh0.z); y[3] = fmaf(run[j][q * 8 + 3], sc0.w, sh0.w);
-            y[4] = fmaf(run[j][q * 8 + 4], sc1.x, sh1.x); y[5] = fmaf(run[j][q * 8 + 5], sc1.y, sh1.y);
-            y[6] = fmaf(run[j][q * 8 + 6], sc1.z, sh1.z); y[7] = fmaf(run[j][q * 8 + 7], sc1.w, sh1.w);
+            float2 y[4];                           // packed fp32x2 arithmetic (FFMA2 / FADD2), same roundings as scalar code
+            y[0] = __ffma2_rn(make_float2(run[j][q * 8 + 0], run[j][q * 8 + 1]), make_float2(sc0.x, sc0.y), make_float2(sh0.x, sh0.y));
+            y[1] = __ffma2_rn(make_float2(run[j][q * 8 + 2], run[j][q * 8 + 3]), make_float2(sc0.z, sc0.w), make_float2(sh0.z, sh0.w));
+            y[2] = __ffma2_rn(make_float2(run[j][q * 8 + 4], run[j][q * 8 + 5]), make_float2(sc1.x, sc1.y), make_float2(sh1.x, sh1.y));
+            y[3] = __ffma2_rn(make_float2(run[j][q * 8 + 6], run[j][q * 8 + 7]), make_float2(sc1.z, sc1.w), make_float2(sh1.z, sh1.w));
             if (HAS_RES) {
               const uint4 rh = lds128(buf0 + coff), rl = lds128(buf1 + coff);
               const uint32_t hw[4] = {rh.x, rh.y, rh.z, rh.w}, lw[4] = {rl.x, rl.y, rl.z, rl.w};
@@ -346,19 +344,18 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               for (int i = 0; i < 4; ++i) {
                 const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
                 const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
-                y[2 * i] = __fadd_rn(y[2 * i], fmaf(fl.x, LO_INV, fh.x));
-                y[2 * i + 1] = __fadd_rn(y[2 * i + 1], fmaf(fl.y, LO_INV, fh.y));
+                y[i] = __fadd2_rn(y[i], __ffma2_rn(fl, make_float2(LO_INV, LO_INV), fh));
               }
             }
             if (p.relu) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], 0.f);
+              for (int i = 0; i < 4; ++i) { y[i].x = fmaxf(y[i].x, 0.f); y[i].y = fmaxf(y[i].y, 0.f); }
             }
-            float hi[8], lo[8];
+            uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) split_h2(y[i], hi[i], lo[i]);
-            sts128(buf0 + coff, make_uint4(pack_half2(hi[0], hi[1]), pack_half2(hi[2], hi[3]), pack_half2(hi[4], hi[5]), pack_half2(hi[6], hi[7])));
-            sts128(buf1 + coff, make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]), pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7])));
+            for (int i = 0; i < 4; ++i) split_pair(y[i], hi[i], lo[i]);
+            sts128(buf0 + coff, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+            sts128(buf1 + coff, make_uint4(lo[0], lo[1], lo[2], lo[3]));
           }
         }
         fence_proxy_async_smem();                  // generic-proxy smem writes -> visible to the TMA unit

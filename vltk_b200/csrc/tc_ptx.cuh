@@ -177,8 +177,13 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {          // arri
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {       // arrive on the same barrier of CTA rank 0
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
+// Arrive on the same barrier of CTA rank 0.  Default (.release at CTA scope) semantics, as the 2-SM GEMMs of the
+// vendor library do for their TMEM-empty barriers: what the waiter needs is the completion of this warp's tcgen05.ld
+// (tcgen05.wait::ld + tcgen05.fence::before_thread_sync precede the arrive), not a cluster-wide release of earlier
+// memory traffic — `.release.cluster` here compiled to MEMBAR + ERRBAR and cost the peer CTA's epilogue ~9 % of its time
+// (ncu source page, profiles/r02_summary.md).
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
 }
 
 // UMMA shared-memory descriptor, K-major operand in 128B-swizzled rows (8-row atoms of 1024 B):
