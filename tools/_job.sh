@@ -1,8 +1,17 @@
-set -x
-python -m pytest tests/test_gpu_stages.py -x -q -k "exact or pair" 2>&1 | tail -3 > gpurun_out/pytest_ep.log
-python -m pytest tests/test_gpu_e2e.py -x -q -k "golden" 2>&1 | tail -3 >> gpurun_out/pytest_ep.log
-B="python bench.py --steps 40 --warmup 3 --no-cpu-baseline --no-configs"
-$B > gpurun_out/bench_ep_1.json 2> gpurun_out/bench_ep_1.err
-M=gpu__time_duration.sum,sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed,sm__cycles_elapsed.max
-PROBE_MODE=exact_tc PROBE_REPS=2 ncu --metrics $M --clock-control none -k regex:conv_tcx --csv --log-file gpurun_out/probe_ep.csv python tools/layer_probe.py conv1 conv2 conv3res c512 > gpurun_out/probe_ep.log 2>&1
-cat gpurun_out/pytest_ep.log; cut -c1-220 gpurun_out/bench_ep_1.json
+B="python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-configs --fast-mode none"
+run() { tag=$1; shift; env "$@" $B > gpurun_out/bench_x_$tag.json 2> gpurun_out/bench_x_$tag.err; python - gpurun_out/bench_x_$tag.json $tag <<'PY'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(sys.argv[2], 'value %.1f e2e %.1f tc_ms %.2f frac %.3f clk %s parity %s'%(d['value'],d['e2e']['value'],d['roofline']['ms_per_step'],d['roofline']['frac'],d['clocks']['sm_mhz'],d['parity']['ok']))
+except Exception as e: print(sys.argv[2],'FAILED',e)
+PY
+}
+run base A=1
+run cta2_4096 VLTK_TCX_CTA2=4096
+run cta2_1 VLTK_TCX_CTA2=1
+run chunk8 VLTK_TCX_CHUNK=8
+run smallk128 VLTK_TCX_SMALLK=128
+run smallk512 VLTK_TCX_SMALLK=512
+run nosplit VLTK_SPLIT_BACKBONE=0
+run base2 A=1

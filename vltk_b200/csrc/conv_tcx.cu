@@ -52,6 +52,7 @@ struct TcxParams {
   int cin;                                     // channel offset of the lo' plane in x (= Cin)
   int K;                                       // element offset between the weight planes WA | WB | WC
   int n_tiles, num_tiles, chunk_kb;
+  const __half* res; int ldr;                  // residual tensor (two planes per row) and its row stride in elements
   int kb1, cin2, stride2;                      // K-concatenated second operand: k-blocks [kb1, num_kb) come from tmA2
   int out_plane, res_plane;                    // column offset of the lo' plane in y / residual
 };
@@ -260,8 +261,8 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int ci = 0; ci < nchunks; ++ci, ++seq) {
         const int acc = seq & 1;
         const uint32_t use = (uint32_t)(seq >> 1) & 1u;
-        if (HAS_RES && ci == nchunks - 1 && issuer) {
-          // residual planes of my first unit -> my staging buffers, hidden behind the last chunk's MMAs
+        if (HAS_RES && ci == 0 && issuer) {
+          // residual planes of my first unit -> my staging buffers (free until the tile finish), a whole tile of MMAs ahead
           bulk_wait_read<0>();                     // the stores that last read the buffers have drained them
           mbar_expect_tx(res_bar(g), 2 * XBUF_BYTES);
           tma_load_2d(gbuf0, &tmR, res_bar(g), n0 + g * XSLAB, m0);
@@ -294,16 +295,34 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
       // ---- tile finish: scale/shift (+ residual) (+ ReLU) -> two fp16 planes (or fp32) -> TMA store
+      // Residual of the units after the first: the staging buffers are busy with the first unit until its store has
+      // read them, so a TMA load into them would start a full memory latency before it is needed (ncu: 21 % of the
+      // epilogue's time).  Each thread owns one output row, i.e. 128 contiguous bytes per plane: fetch them straight into
+      // registers with 32-byte (sector-sized) loads now, behind the first unit's arithmetic.
+      uint32_t rr[HAS_RES && NS_OWN > 1 ? (NS_OWN - 1) * 64 : 1];
+      (void)rr;
+      if constexpr (HAS_RES && NS_OWN > 1) {
+        const bool in = (int64_t)m0 + row < p.M;
+#pragma unroll
+        for (int j = 1; j < NS_OWN; ++j) {
+          const __half* rp = p.res + (int64_t)(m0 + row) * p.ldr + n0 + (g + j * EG) * XSLAB;
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              uint32_t* d = rr + (j - 1) * 64 + pl * 32 + v * 8;
+              if (in) ldg256_nc(rp + pl * p.res_plane + v * 16, d);
+              else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d[i] = 0u;
+              }
+            }
+        }
+      }
 #pragma unroll
       for (int j = 0; j < NS_OWN; ++j) {
         const int col0 = n0 + (g + j * EG) * XSLAB;
-        if (HAS_RES) {
-          if (j > 0 && issuer) {
-            bulk_wait_read<0>();
-            mbar_expect_tx(res_bar(g), 2 * XBUF_BYTES);
-            tma_load_2d(gbuf0, &tmR, res_bar(g), col0, m0);
-            tma_load_2d(gbuf1, &tmR, res_bar(g), p.res_plane + col0, m0);
-          }
+        if (HAS_RES && j == 0) {
           mbar_wait(res_bar(g), rphase);
           rphase ^= 1u;
         } else if (issuer) {
@@ -338,8 +357,14 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             y[2] = __ffma2_rn(make_float2(run[j][q * 8 + 4], run[j][q * 8 + 5]), make_float2(sc1.x, sc1.y), make_float2(sh1.x, sh1.y));
             y[3] = __ffma2_rn(make_float2(run[j][q * 8 + 6], run[j][q * 8 + 7]), make_float2(sc1.z, sc1.w), make_float2(sh1.z, sh1.w));
             if (HAS_RES) {
-              const uint4 rh = lds128(buf0 + coff), rl = lds128(buf1 + coff);
-              const uint32_t hw[4] = {rh.x, rh.y, rh.z, rh.w}, lw[4] = {rl.x, rl.y, rl.z, rl.w};
+              uint32_t hw[4], lw[4];
+              if (j == 0) {
+                const uint4 rh = lds128(buf0 + coff), rl = lds128(buf1 + coff);
+                hw[0] = rh.x; hw[1] = rh.y; hw[2] = rh.z; hw[3] = rh.w; lw[0] = rl.x; lw[1] = rl.y; lw[2] = rl.z; lw[3] = rl.w;
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { hw[i] = rr[(j > 0 ? j - 1 : 0) * 64 + q * 4 + i]; lw[i] = rr[(j > 0 ? j - 1 : 0) * 64 + 32 + q * 4 + i]; }
+              }
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
@@ -486,6 +511,7 @@ int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMa
   t.num_kb = t.kb1 + (cc ? cc->Cin2 / BK : 0); t.cin = p.Cin; t.K = K; t.chunk_kb = chunk;
   t.cin2 = cc ? cc->Cin2 : 0; t.stride2 = cc ? cc->stride2 : 1;
   t.out_plane = p.Cout; t.res_plane = p.Cout;
+  t.res = (const __half*)p.residual; t.ldr = p.ldr;
   t.fd_ow.init((uint32_t)p.OW); t.fd_oh.init((uint32_t)p.OH);
   if (out_f32) return launchx<128, 5, 2, false, true, false>(ma, ma2, mb, my, mr, t, cout_pad, st);
   if (pair) {

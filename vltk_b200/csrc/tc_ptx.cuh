@@ -131,6 +131,12 @@ __device__ __forceinline__ void warp_colsum64(float (&v)[64], int lane) {
     }
   }
 }
+// 32 B (one sector) per thread, read-only path, no L1 allocation: row-per-thread reads of a streamed tensor
+__device__ __forceinline__ void ldg256_nc(const void* p, uint32_t* r) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));

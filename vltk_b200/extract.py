@@ -165,9 +165,12 @@ class _AsyncArrowWriter:
         tmp = self.path + ".partial"
         try:
             while True:
-                cols = self.q.get()
-                if cols is None:
+                item = self.q.get()
+                if item is None:
                     break
+                cols, ready, done = item if isinstance(item, tuple) else (item, None, None)
+                if ready is not None:
+                    ready()                     # e.g. a CUDA event: the columns' host buffers are still being filled
                 table = _to_table(cols)
                 if writer is None:
                     schema = table.schema.with_metadata(_schema_metadata(self.meta_user, cols, self.img_to_row_map))
@@ -177,6 +180,9 @@ class _AsyncArrowWriter:
                 for b in table.to_batches(max_chunksize=128):
                     writer.write_batch(b)
                 self.rows += table.num_rows
+                del table
+                if done is not None:
+                    done()                      # the host buffers may be reused
         except Exception as e:  # surfaced by close()
             self.err = e
             while self.q.get() is not None:
@@ -193,10 +199,12 @@ class _AsyncArrowWriter:
             elif os.path.exists(tmp):
                 os.remove(tmp)
 
-    def put(self, cols):
+    def put(self, cols, ready=None, done=None):
+        """Appends rows.  `ready()` (optional) is called by the writer thread before it touches the columns, `done()`
+        after their bytes are in the file — the hand-shake for columns that live in recycled pinned buffers."""
         if self.err:
             raise self.err
-        self.q.put(cols)
+        self.q.put(cols if ready is None and done is None else (cols, ready, done))
 
     def close(self, abort: bool = False):
         self.aborted = self.aborted or abort
@@ -321,6 +329,9 @@ def extract(image_source: Callable[[int], np.ndarray], image_ids: Sequence[str],
     return gather.run(windows())
 
 
+_PINNED_SETS: Dict[tuple, list] = {}       # writer-rank pinned column buffers of the last single-file job, by geometry
+
+
 class _WindowGather:
     """single_file=True: the ONE collective of the path.  Every rank packs each finished window of its shard (all
     fixed-size columns of a row back to back, ~297 KB per image) into one byte tensor on its device and rank 0 receives
@@ -357,6 +368,15 @@ class _WindowGather:
         parts = [cols_t[k].to(self.dev).contiguous().reshape(n, -1).view(torch.uint8) for k, _, _ in self.spec]
         return torch.cat(parts, 1)
 
+    def _col_layout(self):
+        out, off = [], 0
+        for k, dt, sh in self.spec:
+            tdt = getattr(torch, dt)
+            nb = int(np.prod(sh, dtype=np.int64)) * torch.empty((), dtype=tdt).element_size()
+            out.append((k, tdt, tuple(sh), off, nb))
+            off += nb
+        return out
+
     def _unpack(self, host: np.ndarray):
         out, off = {}, 0
         for k, dt, sh in self.spec:
@@ -365,6 +385,26 @@ class _WindowGather:
             out[k] = np.ascontiguousarray(host[:, off:off + nb]).view(npdt).reshape((host.shape[0],) + tuple(sh))
             off += nb
         return out
+
+    def _writer_side_setup(self):
+        """Rank 0, NCCL: two device receive buffers, and three sets of column-contiguous pinned host buffers that cycle
+        between the copy stream and the writer thread — the main thread never waits for a D2H copy or a file write
+        unless all three sets are still in the writer's hands (the file is then the bottleneck, not the GPUs)."""
+        import queue
+        rows = self.window * self.world
+        self.recv = [torch.empty((self.world, self.window, self.row_bytes), dtype=torch.uint8, device=self.dev) for _ in range(2)]
+        self.recv_free = [None, None]               # event: the copy stream has finished reading recv[i]
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.layout = self._col_layout()
+        self.host_sets = queue.Queue()
+        key = (rows, tuple((k, str(tdt), sh) for k, tdt, sh, _, _ in self.layout))
+        sets = _PINNED_SETS.get(key)                # page-locking ~0.5 GB costs more than a window of work: keep the sets
+        if sets is None:
+            sets = [{k: torch.empty((rows,) + sh, dtype=tdt).pin_memory() for k, tdt, sh, _, _ in self.layout} for _ in range(3)]
+            _PINNED_SETS.clear()
+            _PINNED_SETS[key] = sets
+        for hs in sets:
+            self.host_sets.put(hs)
 
     def run(self, windows):
         ok = False
@@ -379,15 +419,41 @@ class _WindowGather:
                 if cols_t is not None:
                     pk = self._pack(cols_t)
                     buf[: pk.shape[0]] = pk
-                out = [torch.empty_like(buf) for _ in range(self.world)] if self.rank == 0 else None
-                self.dist.gather(buf, out, dst=0)
-                if self.rank == 0:
-                    lo = w * self.window * self.world
-                    hi = min(lo + self.window * self.world, self.n_total)
-                    g = torch.stack(out).permute(1, 0, 2).reshape(self.window * self.world, self.row_bytes)[: hi - lo]
+                lo = w * self.window * self.world
+                hi = min(lo + self.window * self.world, self.n_total)
+                if self.rank == 0 and self.on_device:
+                    if w == 0:
+                        self._writer_side_setup()
+                    slot = w & 1
+                    if self.recv_free[slot] is not None:
+                        torch.cuda.current_stream().wait_event(self.recv_free[slot])
+                    self.dist.gather(buf, list(self.recv[slot].unbind(0)), dst=0)
+                    # copy stream: [world, window, row] -> global order, one contiguous device tensor per column, D2H
+                    # into a free pinned set; the writer thread waits for the event, not this thread
+                    got = torch.cuda.Event()
+                    got.record()
+                    hs = self.host_sets.get()       # blocks only while the writer holds all three sets
+                    with torch.cuda.stream(self.copy_stream):
+                        self.copy_stream.wait_event(got)
+                        g = self.recv[slot].permute(1, 0, 2)
+                        for k, tdt, sh, off, nb in self.layout:
+                            colb = g[:, :, off:off + nb].contiguous().view(tdt).reshape((self.window * self.world,) + sh)
+                            hs[k].copy_(colb, non_blocking=True)
+                        self.recv_free[slot] = torch.cuda.Event()
+                        self.recv_free[slot].record()
+                        landed = torch.cuda.Event()
+                        landed.record()
                     cols = {"imgid": np.asarray([str(x) for x in self.ids[lo:hi]], dtype=object)}
-                    cols.update(self._unpack(g.cpu().numpy()))
-                    self.writer.put(cols)
+                    cols.update({k: hs[k].numpy()[: hi - lo] for k, *_ in self.layout})
+                    self.writer.put(cols, ready=landed.synchronize, done=lambda hs=hs: self.host_sets.put(hs))
+                else:
+                    out = [torch.empty_like(buf) for _ in range(self.world)] if self.rank == 0 else None
+                    self.dist.gather(buf, out, dst=0)
+                    if self.rank == 0:
+                        g = torch.stack(out).permute(1, 0, 2).reshape(self.window * self.world, self.row_bytes)[: hi - lo]
+                        cols = {"imgid": np.asarray([str(x) for x in self.ids[lo:hi]], dtype=object)}
+                        cols.update(self._unpack(g.cpu().numpy()))
+                        self.writer.put(cols)
             ok = True
         finally:
             if self.writer is not None:
