@@ -148,6 +148,13 @@ int vltk_conv2d_meanpool_nhwc(const void* x, const float* weight, const float* s
  * already folded into w / w2 by the caller.  x [N,h,w,cin], x2 [N,h2,w2,cin2] bf16 NHWC (DEVICE) with
  * (h2-1)/stride2+1 == h (same for w); weight [cout,cin], weight2 [cout,cin2] DEVICE f32 (rounded to bf16);
  * shift [cout] or NULL; y [N,h,w,cout] bf16.  cin, cin2, cout % 64 == 0. */
+/* The same fused tail in exact_tc mode (csrc/conv_tcx.cu on CTA pairs, ROI-aligned tiles): x [N,h,w,cin], residual
+ * [N,h,w,cout] and weight [Cout,Cin] are DEVICE fp32 (split into fp16 planes inside), a 1x1 convolution;
+ * 128 < pool_rows <= 256. */
+int vltk_conv2d_meanpool_exact_nhwc(const float* x, const float* weight, const float* scale, const float* shift,
+                                    const float* residual, float* pooled, int n, int h, int w, int cin, int cout,
+                                    int relu, int pool_rows, void* stream);
+
 int vltk_conv2d_dual_nhwc(const void* x, const float* weight, const void* x2, const float* weight2,
                           const float* shift, void* y, int n, int h, int w, int cin, int h2, int w2,
                           int cin2, int stride2, int cout, int relu, void* stream);

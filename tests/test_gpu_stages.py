@@ -234,6 +234,31 @@ def test_exact_tc_cta_pair_kernel_is_bit_identical_to_single_cta_kernel(dev, cas
     assert ((y2.cpu().double() - ref).abs() <= 3e-6 * (ref.abs() + 1.0)).all()
 
 
+@pytest.mark.parametrize("rois,cin,cout", [(1, 512, 256), (3, 512, 2048), (80, 512, 2048), (301, 512, 512)])
+def test_exact_tc_fused_meanpool_matches_conv_then_mean_and_is_position_independent(dev, rois, cin, cout):
+    """conv_tcx_kernel<POOL>: the res5 tail's 14x14 mean reduced in the epilogue of the last conv3 (ROI-aligned pair
+    tiles) against the stored exact_tc layer followed by an fp64 mean (the stored tensor adds only its 2^-24 split
+    error), against fp64 end to end, and ROI by ROI against the same ROI run alone (bit-identical: an image's features
+    may not depend on its batch neighbours)."""
+    from vltk_b200 import stages
+    g = torch.Generator().manual_seed(rois * 17 + cout)
+    x = torch.randn(rois, 14, 14, cin, generator=g).to(dev)
+    wt = (torch.randn(cout, cin, 1, 1, generator=g) * (2.0 / cin) ** 0.5).to(dev)
+    sc = (torch.rand(cout, generator=g) * 0.2 + 0.1).to(dev)
+    sh = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    res = torch.randn(rois, 14, 14, cout, generator=g).abs().to(dev)
+    pooled = stages.conv2d_meanpool_exact_nhwc(x, wt, sc, sh, res, 196)
+    again = stages.conv2d_meanpool_exact_nhwc(x, wt, sc, sh, res, 196)
+    assert torch.equal(pooled, again)
+    stored = stages.conv2d_nhwc(x, wt, sc, sh, res, 1, 0, 1, True, mode="exact_tc")
+    np.testing.assert_allclose(pooled.cpu().numpy(), stored.double().reshape(rois, 196, cout).mean(1).cpu().numpy(), rtol=2e-6, atol=2e-6)
+    ref = _ref_conv(x, wt, sc, sh, res, 1, 0, 1, True).double().reshape(rois, 196, cout).mean(1)
+    np.testing.assert_allclose(pooled.cpu().numpy(), ref.numpy(), rtol=3e-6, atol=3e-6)
+    for r in sorted({0, rois // 2, rois - 1}):
+        alone = stages.conv2d_meanpool_exact_nhwc(x[r:r + 1].contiguous(), wt, sc, sh, res[r:r + 1].contiguous(), 196)
+        assert torch.equal(alone[0], pooled[r]), r
+
+
 @pytest.mark.parametrize("rois,cin,cout", [(1, 512, 256), (3, 512, 2048), (80, 512, 2048)])
 def test_cta_pair_fused_meanpool_and_concat_are_bit_identical_to_single_cta(dev, rois, cin, cout):
     """The ROI-aligned fused 14x14 mean (one ROI per CTA pair: rank 0 rows [0,128), rank 1 rows [128,196)) and the

@@ -1,17 +1,9 @@
-B="python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-configs --fast-mode none"
-run() { tag=$1; shift; env "$@" $B > gpurun_out/bench_x_$tag.json 2> gpurun_out/bench_x_$tag.err; python - gpurun_out/bench_x_$tag.json $tag <<'PY'
-import json,sys
-try:
-    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-    print(sys.argv[2], 'value %.1f e2e %.1f tc_ms %.2f frac %.3f clk %s parity %s'%(d['value'],d['e2e']['value'],d['roofline']['ms_per_step'],d['roofline']['frac'],d['clocks']['sm_mhz'],d['parity']['ok']))
-except Exception as e: print(sys.argv[2],'FAILED',e)
-PY
-}
-run base A=1
-run cta2_4096 VLTK_TCX_CTA2=4096
-run cta2_1 VLTK_TCX_CTA2=1
-run chunk8 VLTK_TCX_CHUNK=8
-run smallk128 VLTK_TCX_SMALLK=128
-run smallk512 VLTK_TCX_SMALLK=512
-run nosplit VLTK_SPLIT_BACKBONE=0
-run base2 A=1
+set -x
+python -m pytest tests/test_gpu_stages.py -x -q -k "exact" 2>&1 | tail -3 > gpurun_out/pytest_pool.log
+python -m pytest tests/test_gpu_e2e.py -x -q 2>&1 | tail -3 >> gpurun_out/pytest_pool.log
+B="python bench.py --steps 40 --warmup 3 --no-cpu-baseline --no-configs --fast-mode none"
+VLTK_FUSE_MEAN=0 $B > gpurun_out/bench_pool_0.json 2> gpurun_out/bench_pool_0.err
+$B > gpurun_out/bench_pool_1.json 2> gpurun_out/bench_pool_1.err
+VLTK_FUSE_MEAN=0 $B > gpurun_out/bench_pool_0b.json 2>> gpurun_out/bench_pool_0.err
+$B > gpurun_out/bench_pool_1b.json 2>> gpurun_out/bench_pool_1.err
+cat gpurun_out/pytest_pool.log

@@ -82,6 +82,7 @@ SYMBOLS = {
     "vltk_conv_tcx_set_cta_pairs": (C.c_int, [C.c_int]),
     "vltk_conv_tc_set_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "vltk_conv2d_meanpool_nhwc": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 11 + [C.c_void_p]),
+    "vltk_conv2d_meanpool_exact_nhwc": (C.c_int, [C.c_void_p] * 6 + [C.c_int] * 7 + [C.c_void_p]),
     "vltk_linear_tc3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_void_p]),
     "vltk_rpn_proposals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 7

@@ -1150,6 +1150,14 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const TcParams& tp, int c
 // ---- descriptor encoders shared with conv_tcx.cu (fp16 split-plane kernels)
 int tc_num_sms() { return num_sms(); }
 
+int tc_pool_finish(const float* partial, float* out, int rois, int rows, int C, cudaStream_t st) {
+  const int64_t tot = (int64_t)rois * (C / 4);
+  if (tot == 0) return 0;
+  pool_finish_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(partial, out, rois, rows, C);
+  VLTK_LAUNCH_CHECK();
+  return 0;
+}
+
 int tc_encode_tiled(CUtensorMap* out, CUtensorMapDataType dt, const void* ptr, uint64_t cols, uint64_t rows,
                     uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows, bool promote256) {
   if (load_driver_entry_points()) return -1;

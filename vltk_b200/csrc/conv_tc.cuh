@@ -59,8 +59,12 @@ int conv_tc_launch(const ConvProblem& p, const bf16* w_nk, int cout_pad, TensorM
 //   per-row 2^-s of the packing.  out_dtype DT_H2 (optional DT_H2 residual) or DT_F32 (cout_pad % 128 == 0).
 // Optional `concat` (x2 / ldx2 / H2 / W2 / Cin2 / stride2; w2 unused): K-concatenation as in conv_tc_launch — x2 is a
 // DT_H2 tensor, and every plane of a w3 row is the concatenation [K primary | Cin2] (planes 3 * (K + Cin2) per row).
+// Optional `pool`: the fused row-group mean of conv_tc_launch (needs a residual, Cout % 256 == 0, 128 < rows <= 256; runs on
+// CTA pairs with ROI-aligned tiles); p.y is not written.
 int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMapCache* cache, cudaStream_t st,
-                    const TcConcat* concat = nullptr);
+                    const TcConcat* concat = nullptr, const TcPool* pool = nullptr);
+// out[roi][c] = (partial[2 roi][c] + partial[2 roi + 1][c]) / rows  (second pass of the pooled epilogues)
+int tc_pool_finish(const float* partial, float* out, int rois, int rows, int C, cudaStream_t st);
 // conv_tcx layers with a 256-wide cout tile and at least `min_pixels` output pixels run on CTA pairs (0 = never)
 void conv_tcx_set_cta_pairs(int min_pixels);
 

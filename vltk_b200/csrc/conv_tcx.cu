@@ -53,6 +53,7 @@ struct TcxParams {
   int K;                                       // element offset between the weight planes WA | WB | WC
   int n_tiles, num_tiles, chunk_kb;
   const __half* res; int ldr;                  // residual tensor (two planes per row) and its row stride in elements
+  float* pool_partial; int pool_rows;          // POOL: per (ROI half, cout) column sums; rows per ROI
   int kb1, cin2, stride2;                      // K-concatenated second operand: k-blocks [kb1, num_kb) come from tmA2
   int out_plane, res_plane;                    // column offset of the lo' plane in y / residual
 };
@@ -88,7 +89,11 @@ __device__ __forceinline__ void split_pair(float2 x, uint32_t& hi, uint32_t& lo)
 // L2 -> SM once per pair); all TMA bytes of a stage complete on the leader's full barrier, tcgen05.commit multicasts to
 // both CTAs' empty / accumulator-full barriers, each CTA promotes and finishes its own 128 TMEM lanes and releases the
 // chunk accumulator on the leader's barrier.  Same k-block / pass / chunk order, same arithmetic: bit-identical outputs.
-template <int BN, int STAGES, int EG, bool HAS_RES, bool OUT_F32, bool BIGREG, bool PAIR = false>
+// POOL (pairs only): the res5 tail's 14x14 mean (frcnn.py:1401) fused as in conv_tc3_kernel — a pair tile is ONE ROI
+// (rank 0 rows [0,128), rank 1 rows [128, pool_rows), the rows past the ROI computed and masked), the finish reduces the
+// fp32 tile over its rows (fixed-order warp butterfly + fixed-order combine of the group's four warps) and writes one
+// partial sum per (ROI half, cout) instead of storing the tile; an ROI's mean does not depend on its place in the batch.
+template <int BN, int STAGES, int EG, bool HAS_RES, bool OUT_F32, bool BIGREG, bool PAIR = false, bool POOL = false>
 __global__ void __launch_bounds__(128 + 128 * EG, 1)
 conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY,
@@ -96,6 +101,7 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   using S = SmemX<BN, STAGES, EG, PAIR>;
   static_assert(!(HAS_RES && OUT_F32), "fp32 output has no residual path");
   static_assert(!PAIR || BN == 256, "CTA pairs share one 256-cout W tile");
+  static_assert(!POOL || (PAIR && HAS_RES && !OUT_F32), "the pooled finish is the res5 conv3 tail on CTA pairs");
   constexpr int NS_OWN = S::NS_OWN;
   extern __shared__ __align__(1024) unsigned char smem_dynx[];
   const uint32_t base = smem_u32(smem_dynx);
@@ -121,10 +127,13 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const bool leader = rank == 0;
   // work unit w (a tile, or a pair tile) -> first output row of THIS CTA and first cout
   const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, unit_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  auto unit_m0 = [&](uint32_t mt) -> uint32_t { return PAIR ? (mt * 2 + rank) * BM : mt * BM; };
+  auto unit_m0 = [&](uint32_t mt) -> uint32_t {
+    return POOL ? mt * (uint32_t)p.pool_rows + rank * BM : (PAIR ? (mt * 2 + rank) * BM : mt * BM);
+  };
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY);
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+    if (!POOL) tma_prefetch_desc(&tmY);
     if (p.kb1 < p.num_kb) tma_prefetch_desc(&tmA2);
     if (HAS_RES) tma_prefetch_desc(&tmR);
   }
@@ -263,7 +272,8 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t use = (uint32_t)(seq >> 1) & 1u;
         if (HAS_RES && ci == 0 && issuer) {
           // residual planes of my first unit -> my staging buffers (free until the tile finish), a whole tile of MMAs ahead
-          bulk_wait_read<0>();                     // the stores that last read the buffers have drained them
+          if constexpr (POOL) fence_proxy_async_smem();   // the last tile's column-sum scratch lived in these buffers
+          else bulk_wait_read<0>();                // the stores that last read the buffers have drained them
           mbar_expect_tx(res_bar(g), 2 * XBUF_BYTES);
           tma_load_2d(gbuf0, &tmR, res_bar(g), n0 + g * XSLAB, m0);
           tma_load_2d(gbuf1, &tmR, res_bar(g), p.res_plane + n0 + g * XSLAB, m0);
@@ -325,10 +335,11 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (HAS_RES && j == 0) {
           mbar_wait(res_bar(g), rphase);
           rphase ^= 1u;
-        } else if (issuer) {
+        } else if (!POOL && issuer) {
           bulk_wait_read<0>();
         }
         group_barrier();                           // staging reusable; scale/shift visible
+        float (&pv)[XSLAB] = run[j];               // POOL: the finished values replace the sums they came from
         if constexpr (OUT_F32) {
 #pragma unroll
           for (int hb = 0; hb < 2; ++hb) {
@@ -376,23 +387,51 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
               for (int i = 0; i < 4; ++i) { y[i].x = fmaxf(y[i].x, 0.f); y[i].y = fmaxf(y[i].y, 0.f); }
             }
-            uint32_t hi[4], lo[4];
+            if constexpr (POOL) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) split_pair(y[i], hi[i], lo[i]);
-            sts128(buf0 + coff, make_uint4(hi[0], hi[1], hi[2], hi[3]));
-            sts128(buf1 + coff, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+              for (int i = 0; i < 4; ++i) { pv[q * 8 + 2 * i] = y[i].x; pv[q * 8 + 2 * i + 1] = y[i].y; }
+            } else {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) split_pair(y[i], hi[i], lo[i]);
+              sts128(buf0 + coff, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+              sts128(buf1 + coff, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+            }
           }
         }
-        fence_proxy_async_smem();                  // generic-proxy smem writes -> visible to the TMA unit
-        group_barrier();
-        if (issuer) {
-          tma_store_2d(&tmY, gbuf0, col0, m0);
-          tma_store_2d(&tmY, gbuf1, col0 + (OUT_F32 ? 32 : p.out_plane), m0);
-          bulk_commit();
+        if constexpr (POOL) {
+          // column sums over this CTA's rows of the ROI: rows past the ROI contribute nothing
+          const int valid = rank ? p.pool_rows - BM : BM;
+          float* comb = reinterpret_cast<float*>(gbase + S::OFF_OUT + (size_t)(g * 2) * XBUF_BYTES) + (j & 1) * 256;
+          float2 ts = make_float2(0.f, 0.f);
+          if (j == 0) group_barrier();             // every thread has read its residual out of the staging buffers
+          if (e * 32 < valid) {                    // warp-uniform
+            const bool in = row < valid;
+#pragma unroll
+            for (int i = 0; i < XSLAB; ++i) pv[i] = in ? pv[i] : 0.f;
+            warp_colsum64(pv, lane);
+            ts = make_float2(pv[0], pv[1]);
+          }
+          *reinterpret_cast<float2*>(comb + e * 64 + 2 * lane) = ts;
+          group_barrier();
+          if (et < 64) {
+            const float* c4 = comb + et;
+            const float tot = ((c4[0] + c4[64]) + c4[128]) + c4[192];
+            p.pool_partial[((int64_t)umt * 2 + rank) * p.Cout + col0 + et] = tot;
+          }
+          if (j == NS_OWN - 1) group_barrier();    // scratch readers done before the next tile's residual lands on it
+        } else {
+          fence_proxy_async_smem();                // generic-proxy smem writes -> visible to the TMA unit
+          group_barrier();
+          if (issuer) {
+            tma_store_2d(&tmY, gbuf0, col0, m0);
+            tma_store_2d(&tmY, gbuf1, col0 + (OUT_F32 ? 32 : p.out_plane), m0);
+            bulk_commit();
+          }
         }
       }
     }
-    if (issuer) bulk_wait_all();                   // all output bytes are in global memory
+    if (!POOL && issuer) bulk_wait_all();          // all output bytes are in global memory
   }
   tc_fence_before();
   __syncthreads();
@@ -404,17 +443,17 @@ conv_tcx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <int BN, int STAGES, int EG, bool HAS_RES, bool OUT_F32, bool BIGREG, bool PAIR = false>
+template <int BN, int STAGES, int EG, bool HAS_RES, bool OUT_F32, bool BIGREG, bool PAIR = false, bool POOL = false>
 int launchx(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const CUtensorMap& my, const CUtensorMap& mr,
             TcxParams tp, int cout_pad, cudaStream_t st) {
   using S = SmemX<BN, STAGES, EG, PAIR>;
-  auto kern = conv_tcx_kernel<BN, STAGES, EG, HAS_RES, OUT_F32, BIGREG, PAIR>;
+  auto kern = conv_tcx_kernel<BN, STAGES, EG, HAS_RES, OUT_F32, BIGREG, PAIR, POOL>;
   static DeviceOnce once;
   if (once.first()) VLTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   tp.n_tiles = cout_pad / BN;
   tp.fd_ntiles.init((uint32_t)tp.n_tiles);
   const int64_t row_tiles = ceil_div64(tp.M, BM);
-  const int64_t tiles = (PAIR ? ceil_div64(row_tiles, 2) : row_tiles) * tp.n_tiles;   // PAIR: 256-row pair tiles
+  const int64_t tiles = (POOL ? tp.M / tp.pool_rows : (PAIR ? ceil_div64(row_tiles, 2) : row_tiles)) * tp.n_tiles;   // PAIR: 256-row pair tiles; POOL: one ROI each
   VLTK_CHECK(tiles < (1ll << 31), "conv_tcx: too many tiles");
   tp.num_tiles = (int)tiles;
   // persistent: one CTA (or one CTA pair) per SM (pair of SMs)
@@ -440,7 +479,8 @@ std::atomic<int> g_tcx_cta2_min_m{[] { const char* e = getenv("VLTK_TCX_CTA2"); 
 void conv_tcx_set_cta_pairs(int min_pixels) { if (min_pixels >= 0) g_tcx_cta2_min_m.store(min_pixels); }
 
 int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMapCache* cache, cudaStream_t st,
-                    const TcConcat* cc) {
+                    const TcConcat* cc, const TcPool* pool) {
+  const bool pooled = pool && pool->out;
   const bool out_f32 = p.out_dtype == DT_F32;
   VLTK_CHECK(p.in_dtype == DT_H2 && (out_f32 || p.out_dtype == DT_H2), "conv_tcx: split-fp16 activations in, split-fp16 or fp32 out");
   VLTK_CHECK(p.Cin % BK == 0 && ((p.Cin / BK) & (p.Cin / BK - 1)) == 0, "conv_tcx: Cin=%d must be 64 * 2^k", p.Cin);
@@ -468,7 +508,11 @@ int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMa
   if (p.residual && bn == 256 && res_bn == 128) bn = 128;
   if (p.residual && bn == 64) { VLTK_CHECK(false, "conv_tcx: residual layers need Cout %% 128 == 0"); }
   // CTA pairs for the wide layers with enough rows to fill 74 pairs (all of res5); VLTK_TCX_CTA2=0 switches them off
-  const bool pair = bn == 256 && !out_f32 && g_tcx_cta2_min_m.load() > 0 && M >= g_tcx_cta2_min_m.load();
+  const bool pair = bn == 256 && !out_f32 && (pooled || (g_tcx_cta2_min_m.load() > 0 && M >= g_tcx_cta2_min_m.load()));
+  if (pooled) {
+    VLTK_CHECK(bn == 256 && !out_f32 && p.residual && !cc, "conv_tcx: the pooled finish needs a residual layer with Cout %% 256 == 0");
+    VLTK_CHECK(pool->partial && pool->rows > BM && pool->rows <= 2 * BM && M % pool->rows == 0, "conv_tcx: pooled rows=%d must be in (128, 256] and divide M", pool->rows);
+  }
   if (cache->maps.size() > 8192) cache->maps.clear();
   auto cached = [&](const TensorMapCache::Key& k, CUtensorMap* dst, auto make) -> int {
     auto it = cache->maps.find(k);
@@ -491,11 +535,12 @@ int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMa
   if (cached(TensorMapCache::Key(w3, K, cout_pad, b_rows, 0, 0, 0, 0, 0, 0, 11), &mb, [&](CUtensorMap* d) {
         return tc_encode_tiled(d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, w3, (uint64_t)3 * K, (uint64_t)cout_pad, (uint64_t)3 * K * 2, BK, (uint32_t)b_rows, true);
       })) return -1;
-  if (cached(TensorMapCache::Key(p.y, (int)M, p.Cout, p.ldy, out_f32 ? 1 : 0, 0, 0, 0, 0, 0, 12), &my, [&](CUtensorMap* d) {
+  if (pooled) my = ma;                             // no output tensor: the tile is reduced, not stored
+  else if (cached(TensorMapCache::Key(p.y, (int)M, p.Cout, p.ldy, out_f32 ? 1 : 0, 0, 0, 0, 0, 0, 12), &my, [&](CUtensorMap* d) {
         return out_f32 ? tc_encode_tiled(d, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.y, (uint64_t)p.Cout, (uint64_t)M, (uint64_t)p.ldy * 4, 32, BM, false)
                        : tc_encode_tiled(d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.y, (uint64_t)2 * p.Cout, (uint64_t)M, (uint64_t)p.ldy * 2, XSLAB, BM, false);
       })) return -1;
-  mr = my;
+  mr = ma;
   if (p.residual &&
       cached(TensorMapCache::Key(p.residual, (int)M, p.Cout, p.ldr, 0, 0, 0, 0, 0, 0, 13), &mr, [&](CUtensorMap* d) {
         return tc_encode_tiled(d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.residual, (uint64_t)2 * p.Cout, (uint64_t)M, (uint64_t)p.ldr * 2, XSLAB, BM, false);
@@ -514,6 +559,11 @@ int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMa
   t.res = (const __half*)p.residual; t.ldr = p.ldr;
   t.fd_ow.init((uint32_t)p.OW); t.fd_oh.init((uint32_t)p.OH);
   if (out_f32) return launchx<128, 5, 2, false, true, false>(ma, ma2, mb, my, mr, t, cout_pad, st);
+  t.pool_partial = pooled ? pool->partial : nullptr; t.pool_rows = pooled ? pool->rows : 0;
+  if (pooled) {
+    if (launchx<256, 5, 2, true, false, true, true, true>(ma, ma2, mb, my, mr, t, cout_pad, st)) return -1;
+    return tc_pool_finish(pool->partial, pool->out, (int)(M / pool->rows), pool->rows, p.Cout, st);
+  }
   if (pair) {
     VLTK_CHECK(M + 256 < (1ll << 31), "conv_tcx: M too large for pair tiles");
     return p.residual ? launchx<256, 5, 2, true, false, true, true>(ma, ma2, mb, my, mr, t, cout_pad, st)

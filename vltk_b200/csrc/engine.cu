@@ -387,12 +387,12 @@ int run_conv(vltk_frcnn* h, const LayerW& L, const void* x, DType xdt, int N, in
     rec.e0 = get_event(); rec.e1 = get_event();
     cudaEventRecord(rec.e0, st);
   }
-  if ((pool && !tc) || (cc && !tc && !tcx)) { set_error("internal: fused mean-pool / concat need the tensor-core path"); return -2; }
+  if ((pool || cc) && !tc && !tcx) { set_error("internal: fused mean-pool / concat need the tensor-core path"); return -2; }
   int rc;
   if (tcx) {
     VLTK_CHECK(ydt == DT_H2, "internal: run_conv on split-fp16 input writes split-fp16");
     p.scale = L.scale_x;
-    rc = conv_tcx_launch(p, L.w_h3, L.cout_pad, &h->tmaps, st, cc);
+    rc = conv_tcx_launch(p, L.w_h3, L.cout_pad, &h->tmaps, st, cc, pool);
   } else {
     VLTK_CHECK(xdt != DT_H2 && ydt != DT_H2, "internal: layer %dx%d k%d has no exact_tc weights", L.cin, L.cout, L.k);
     rc = tc ? conv_tc_launch(p, L.w_nk, L.cout_pad, &h->tmaps, st, nullptr, pool, cc) : conv_simt_launch(p, L.w_kn, L.ldw, st);
@@ -745,7 +745,7 @@ static size_t plan(vltk_frcnn* h, const Shapes& s, void* base, size_t cap, void*
   p[B_FHI] = b.take((size_t)NR * D * pe); p[B_FLO] = b.take((size_t)NR * D * 2);
   p[B_AHHI] = b.take((size_t)NR * (D / 4) * pe); p[B_AHLO] = b.take((size_t)NR * (D / 4) * 2);
   p[B_STEMA] = b.take(h->stem_tc.w_nk ? (size_t)N * s.Hs * s.Ws * 192 * 2 : 0);
-  p[B_PARTIAL] = b.take(h->use_tc ? conv_tc_pool_partial_bytes((int64_t)NR * PP, D) : 0);
+  p[B_PARTIAL] = b.take((h->use_tc || h->use_tcx) ? conv_tc_pool_partial_bytes((int64_t)NR * PP, D) : 0);
   p[B_NMSDONE] = b.take((size_t)N * 4);
   p[B_ROISTAT] = b.take((size_t)NR * 32);
   p[B_RES4] = b.take((size_t)N * s.h4 * s.w4 * c2 * 4 * e);
@@ -1009,7 +1009,9 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
   // bit-independent of its batch neighbours (test_full_batch8_equals_smaller_batches).  VLTK_FUSE_MEAN=0 restores the
   // separate mean_rows pass over the stored bf16 tensor.
   static const bool want_fuse = [] { const char* e = getenv("VLTK_FUSE_MEAN"); return !(e && e[0] == '0'); }();
-  const bool fuse_mean = want_fuse && h->use_tc && h->res5.back().c3.w_nk && PP > 128 && PP <= 256 && D % 256 == 0 && h->res5.back().c3.cin > 256;
+  const LayerW& tail = h->res5.back().c3;
+  const bool fuse_mean = want_fuse && PP > 128 && PP <= 256 && D % 256 == 0 && tail.cin > 256 && !h->res5.back().has_sc &&
+                         ((h->use_tc && tail.w_nk) || (h->use_tcx && tail.w_h3));
   TcPool pool;
   pool.out = (float*)p[B_FEATS]; pool.partial = (float*)p[B_PARTIAL]; pool.rows = PP;
   for (size_t bi = 0; bi < h->res5.size(); ++bi) {
@@ -1315,6 +1317,45 @@ int vltk_conv2d_meanpool_nhwc(const void* x, const float* weight, const float* s
   TensorMapCache cache;
   if (!rc) rc = conv_tc_launch(p, w_nk, cout, &cache, st, nullptr, &pool);
   cudaStreamSynchronize(st);
+  return rc;
+}
+
+int vltk_conv2d_meanpool_exact_nhwc(const float* x, const float* weight, const float* scale, const float* shift,
+                                    const float* residual, float* pooled, int n, int hh, int ww, int cin, int cout,
+                                    int relu, int pool_rows, void* stream) {
+  VLTK_CHECK(x && weight && residual && pooled, "conv2d_meanpool_exact: null argument");
+  VLTK_CHECK(cin % 64 == 0 && cout % 256 == 0, "conv2d_meanpool_exact: cin %% 64 and cout %% 256 required");
+  cudaStream_t st = (cudaStream_t)stream;
+  Scratch scratch(st);
+  const int64_t M = (int64_t)n * hh * ww;
+  std::vector<float> hw((size_t)cout * cin), hs(cout, 1.f);
+  VLTK_CUDA(cudaStreamSynchronize(st));
+  VLTK_CUDA(cudaMemcpy(hw.data(), weight, hw.size() * 4, cudaMemcpyDeviceToHost));
+  if (scale) VLTK_CUDA(cudaMemcpy(hs.data(), scale, (size_t)cout * 4, cudaMemcpyDeviceToHost));
+  std::vector<__half> pl;
+  std::vector<float> sx;
+  build_h3(hw.data(), cout, cin, cout, hs.data(), pl, sx);
+  void *w3 = nullptr, *xh = nullptr, *rh = nullptr;
+  float *dsx = nullptr, *partial = nullptr;
+  VLTK_CUDA(scratch.get(&w3, pl.size() * 2));
+  VLTK_CUDA(scratch.get(&dsx, sx.size() * 4));
+  VLTK_CUDA(scratch.get(&xh, (size_t)M * cin * 4));
+  VLTK_CUDA(scratch.get(&rh, (size_t)M * cout * 4));
+  VLTK_CUDA(scratch.get(&partial, conv_tc_pool_partial_bytes(M, cout)));
+  VLTK_CUDA(cudaMemcpyAsync(w3, pl.data(), pl.size() * 2, cudaMemcpyHostToDevice, st));
+  VLTK_CUDA(cudaMemcpyAsync(dsx, sx.data(), sx.size() * 4, cudaMemcpyHostToDevice, st));
+  int rc = split_f32_h2(x, nullptr, 0, xh, M, cin, st);
+  if (!rc) rc = split_f32_h2(residual, nullptr, 0, rh, M, cout, st);
+  ConvProblem p;
+  memset(&p, 0, sizeof(p));
+  p.x = xh; p.ldx = 2 * cin; p.residual = rh; p.ldr = 2 * cout; p.ldy = 2 * cout;
+  p.N = n; p.H = p.OH = hh; p.W = p.OW = ww; p.Cin = cin; p.KH = p.KW = 1; p.stride = 1; p.dil = 1;
+  p.Cout = cout; p.relu = relu; p.in_dtype = DT_H2; p.out_dtype = DT_H2; p.scale = dsx; p.shift = shift;
+  TcPool pool; pool.out = pooled; pool.partial = partial; pool.rows = pool_rows;
+  TensorMapCache cache;
+  if (!rc) rc = conv_tcx_launch(p, w3, cout, &cache, st, nullptr, &pool);
+  cudaStreamSynchronize(st);
+  if (!rc) VLTK_LAUNCH_CHECK();
   return rc;
 }
 

@@ -71,6 +71,25 @@ def conv2d_meanpool_nhwc(x, weight, scale, shift, residual, pool_rows, stride=1,
     return out
 
 
+def conv2d_meanpool_exact_nhwc(x, weight, scale, shift, residual, pool_rows, relu=True):
+    """The same fused tail in exact_tc mode (vltk_conv2d_meanpool_exact_nhwc): fp32 NHWC x / residual, 1x1 weight
+    [cout, cin, 1, 1]; returns f32 [N*h*w/pool_rows, cout]."""
+    L = _lib.lib()
+    assert x.dtype == torch.float32 and residual.dtype == torch.float32 and x.is_contiguous() and residual.is_contiguous()
+    n, h, w, cin = x.shape
+    cout = weight.shape[0]
+    m = n * h * w
+    assert m % pool_rows == 0
+    out = torch.empty((m // pool_rows, cout), dtype=torch.float32, device=x.device)
+    wt = weight.to(x.device, torch.float32).reshape(cout, cin).contiguous()
+    sc, sh = scale.to(x.device, torch.float32).contiguous(), shift.to(x.device, torch.float32).contiguous()
+    with torch.cuda.device(x.device):
+        _lib.check(L.vltk_conv2d_meanpool_exact_nhwc(x.data_ptr(), wt.data_ptr(), sc.data_ptr(), sh.data_ptr(),
+                                                     residual.data_ptr(), out.data_ptr(), n, h, w, cin, cout, int(relu),
+                                                     pool_rows, _stream(x)), "vltk_conv2d_meanpool_exact_nhwc")
+    return out
+
+
 def conv2d_dual_nhwc(x, weight, x2, weight2, shift=None, stride2=1, relu=True):
     """A projection bottleneck's tail on the tensor pipe (frcnn.py:918-925, 971-979): conv3(x) + shortcut(x2)
     as ONE K-concatenated GEMM, y = act(x.w^T + x2[:, ::stride2, ::stride2].w2^T + shift); BN scales are
