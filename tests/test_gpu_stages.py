@@ -234,6 +234,36 @@ def test_exact_tc_cta_pair_kernel_is_bit_identical_to_single_cta_kernel(dev, cas
     assert ((y2.cpu().double() - ref).abs() <= 3e-6 * (ref.abs() + 1.0)).all()
 
 
+def test_exact_tc_pair_residual_layer_is_deterministic_at_hbm_scale(dev):
+    """res5 conv3 + identity residual in exact_tc at HBM scale (M = 600*196 rows, K = 512 -> 2048, ~4.6 GB of traffic) on
+    CTA pairs: the residual reaches the epilogue by two routes (TMA prefetch into the staging buffers a tile ahead for a
+    group's first unit, 32-byte register loads for the second) while the staging buffers are recycled by the TMA stores
+    and the accumulators by the chunk hand-off across the two CTAs.  compute-sanitizer is closed on this GPU pool
+    (profiles/r02_sanitizer_closed.log), so a protocol bug has to show here: eight back-to-back runs must be
+    bit-identical, equal the single-CTA kernel, and match an fp64 evaluation on sampled rows."""
+    from vltk_b200 import stages
+    g = torch.Generator().manual_seed(78)
+    rois, cin, cout = 600, 512, 2048
+    x = torch.randn(rois, 14, 14, cin, generator=g).to(dev)
+    wt = (torch.randn(cout, cin, 1, 1, generator=g) * (2.0 / cin) ** 0.5).to(dev)
+    sc = (torch.rand(cout, generator=g) * 0.2 + 0.9).to(dev)
+    sh = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    res = torch.randn(rois, 14, 14, cout, generator=g).to(dev)
+    y0 = stages.conv2d_nhwc(x, wt, sc, sh, res, 1, 0, 1, True, mode="exact_tc")
+    for _ in range(7):
+        assert torch.equal(stages.conv2d_nhwc(x, wt, sc, sh, res, 1, 0, 1, True, mode="exact_tc"), y0)
+    try:
+        stages.set_cta_pairs_exact(0)
+        assert torch.equal(stages.conv2d_nhwc(x, wt, sc, sh, res, 1, 0, 1, True, mode="exact_tc"), y0)
+    finally:
+        stages.set_cta_pairs_exact(CTA_PAIRS_DEFAULT)
+    rows = torch.randint(0, rois * 196, (512,), generator=g).to(dev)
+    ref = torch.relu(x.reshape(-1, cin)[rows].double() @ wt.reshape(cout, cin).double().T * sc.double() + sh.double()
+                     + res.reshape(-1, cout)[rows].double()).cpu()
+    got = y0.reshape(-1, cout)[rows].double().cpu()
+    assert ((got - ref).abs() <= 3e-6 * (ref.abs() + 1.0)).all()
+
+
 @pytest.mark.parametrize("rois,cin,cout", [(1, 512, 256), (3, 512, 2048), (80, 512, 2048), (301, 512, 512)])
 def test_exact_tc_fused_meanpool_matches_conv_then_mean_and_is_position_independent(dev, rois, cin, cout):
     """conv_tcx_kernel<POOL>: the res5 tail's 14x14 mean reduced in the epilogue of the last conv3 (ROI-aligned pair

@@ -1,9 +1,5 @@
-set -x
-python -m pytest tests/test_gpu_stages.py -x -q -k "exact" 2>&1 | tail -3 > gpurun_out/pytest_pool.log
-python -m pytest tests/test_gpu_e2e.py -x -q 2>&1 | tail -3 >> gpurun_out/pytest_pool.log
-B="python bench.py --steps 40 --warmup 3 --no-cpu-baseline --no-configs --fast-mode none"
-VLTK_FUSE_MEAN=0 $B > gpurun_out/bench_pool_0.json 2> gpurun_out/bench_pool_0.err
-$B > gpurun_out/bench_pool_1.json 2> gpurun_out/bench_pool_1.err
-VLTK_FUSE_MEAN=0 $B > gpurun_out/bench_pool_0b.json 2>> gpurun_out/bench_pool_0.err
-$B > gpurun_out/bench_pool_1b.json 2>> gpurun_out/bench_pool_1.err
-cat gpurun_out/pytest_pool.log
+M=gpu__time_duration.sum,sm__cycles_elapsed.max,lts__throughput.avg.pct_of_peak_sustained_elapsed,l1tex__m_xbar2l1tex_read_bytes.sum
+for st in 5 4 3; do
+VLTK_TCX_PROBE_STAGES=$st PROBE_MODE=exact_tc PROBE_REPS=2 ncu --metrics $M --clock-control none -k regex:conv_tcx --csv --log-file gpurun_out/probe_stages_$st.csv python tools/layer_probe.py conv2 conv1 > gpurun_out/probe_stages.log 2>&1
+done
+python -m pytest tests/test_gpu_stages.py -x -q -k "hbm_scale" 2>&1 | tail -3

@@ -566,6 +566,9 @@ int conv_tcx_launch(const ConvProblem& p, const void* w3, int cout_pad, TensorMa
   }
   if (pair) {
     VLTK_CHECK(M + 256 < (1ll << 31), "conv_tcx: M too large for pair tiles");
+    static const int probe_stages = [] { const char* e = getenv("VLTK_TCX_PROBE_STAGES"); return e ? atoi(e) : 5; }();   // diagnosis knob
+    if (!p.residual && probe_stages == 4) return launchx<256, 4, 2, false, false, true, true>(ma, ma2, mb, my, mr, t, cout_pad, st);
+    if (!p.residual && probe_stages == 3) return launchx<256, 3, 2, false, false, true, true>(ma, ma2, mb, my, mr, t, cout_pad, st);
     return p.residual ? launchx<256, 5, 2, true, false, true, true>(ma, ma2, mb, my, mr, t, cout_pad, st)
                       : launchx<256, 5, 2, false, false, true, true>(ma, ma2, mb, my, mr, t, cout_pad, st);
   }
