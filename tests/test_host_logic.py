@@ -224,3 +224,21 @@ def test_our_arrow_files_load_through_the_reference_adapter(tmp_path):
         assert ours.data.schema.field(k).type == theirs.data.schema.field(k).type      # same Arrow storage type
     r0 = theirs.get(theirs.imgids[0])
     assert np.asarray(r0["features"], np.float32).shape == (36, 2048) and np.asarray(r0["box"], np.float32).shape == (36, 4)
+
+
+def test_synthetic_images_do_not_depend_on_the_thread_count():
+    """torchrun starts every rank with OMP_NUM_THREADS=1, and ATen's single-thread bilinear path rounds differently from
+    the multi-thread one: the same seed must still give the golden's image (vltk_b200/synthetic.py::make_raw_image) —
+    otherwise rank 0's in-run parity check of `bench.py --gpus N` compares against the wrong pixels."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    from vltk_b200 import synthetic
+    code = ("import hashlib, sys; sys.path.insert(0, %r); from vltk_b200 import synthetic; "
+            "print(hashlib.md5(synthetic.make_raw_image(150, 200, 4010).numpy().tobytes()).hexdigest())") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    here = hashlib.md5(synthetic.make_raw_image(150, 200, 4010).numpy().tobytes()).hexdigest()
+    for n in ("1", "2"):
+        env = dict(os.environ, OMP_NUM_THREADS=n)
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env).stdout.strip().splitlines()[-1]
+        assert out == here, (n, out, here)

@@ -386,6 +386,15 @@ class _WindowGather:
             off += nb
         return out
 
+    def _free_host_set(self):
+        import queue
+        while True:
+            try:
+                return self.host_sets.get(timeout=0.5)
+            except queue.Empty:
+                if self.writer.err:                 # a dead writer never hands a set back: fail instead of hanging the job
+                    raise self.writer.err
+
     def _writer_side_setup(self):
         """Rank 0, NCCL: two device receive buffers, and three sets of column-contiguous pinned host buffers that cycle
         between the copy stream and the writer thread — the main thread never waits for a D2H copy or a file write
@@ -432,7 +441,7 @@ class _WindowGather:
                     # into a free pinned set; the writer thread waits for the event, not this thread
                     got = torch.cuda.Event()
                     got.record()
-                    hs = self.host_sets.get()       # blocks only while the writer holds all three sets
+                    hs = self._free_host_set()      # blocks only while the writer holds all three sets
                     with torch.cuda.stream(self.copy_stream):
                         self.copy_stream.wait_event(got)
                         g = self.recv[slot].permute(1, 0, 2)

@@ -119,8 +119,19 @@ def make_raw_image(h: int, w: int, seed: int) -> torch.Tensor:
     g = torch.Generator().manual_seed(2000 + seed)
     ch, cw = max(h // 32, 2), max(w // 32, 2)
     coarse = torch.empty((1, 3, ch, cw), dtype=torch.float32).normal_(generator=g)
-    low = torch.nn.functional.interpolate(coarse, size=(h, w), mode="bilinear",
-                                          align_corners=False)[0]
+    # ATen's CPU bilinear kernel takes a different code path (results 1 ulp apart on half of the elements, a few dozen
+    # flipped u8 pixels per image) when the process has ONE intra-op thread — which is what torchrun sets up
+    # (OMP_NUM_THREADS=1).  The goldens were made with the multi-thread path (identical for 2, 3, 8, 16 threads), so pin it:
+    # the same seed must give the same image in every launch mode.
+    nthr = torch.get_num_threads()
+    if nthr < 2:
+        torch.set_num_threads(2)
+    try:
+        low = torch.nn.functional.interpolate(coarse, size=(h, w), mode="bilinear",
+                                              align_corners=False)[0]
+    finally:
+        if nthr < 2:
+            torch.set_num_threads(nthr)
     fine = torch.empty((3, h, w), dtype=torch.float32).normal_(generator=g)
     img = torch.round(128.0 + 48.0 * low + 16.0 * fine).clamp_(0, 255)
     return img.permute(1, 2, 0).contiguous().to(torch.uint8)
