@@ -121,6 +121,38 @@ def test_fp32_matches_oracle_full_tensors(case, mode):
     np.testing.assert_allclose(dense["boxes"], ref["boxes"].numpy(), rtol=0, atol=1e-2)
 
 
+def test_exact_tc_matches_the_oracle_on_fresh_uncommitted_seeds():
+    """Index parity that cannot be an artefact of the committed cases: ten image seeds no golden uses, the oracle run here
+    on the box's CPU, its decision margins measured (oracle/margins.py), and — on every seed whose margins clear the
+    certification thresholds, i.e. where two fp32 implementations are REQUIRED to agree — kept indices, ids and counts
+    must equal the oracle's in exact_tc mode.  Uncertified seeds (a near-tie somewhere) are reported, not asserted."""
+    from oracle import frcnn_oracle as O, margins
+    from vltk_b200.preprocess import Preprocess
+    model, cfg = get_model("tiny", "exact_tc")
+    certified = exact = 0
+    for seed in range(7100, 7110):
+        raws = [cases.raw_image(192, 256, seed)]
+        oimg, osz, osc = O.preprocess(cfg, raws)
+        st = {}
+        ref = O.forward(weights(0), cfg, oimg, osz, osc, stages=st)
+        ok = margins.certified(margins.margins(cfg, st, ref))
+        ids, images, sizes, scales = Preprocess(cfg)(raws)
+        out = model(images, sizes, scales_yx=scales)
+        same = (out["preds_per_image"].tolist() == ref["preds_per_image"].tolist()
+                and torch.equal(out["keep_idx"][0].cpu(), ref["keep"][0])
+                and torch.equal(out["obj_ids"][0].cpu(), ref["obj_ids"][0])
+                and torch.equal(out["attr_ids"][0].cpu(), ref["attr_ids"][0]))
+        certified += ok
+        exact += same
+        print(f"seed {seed}: margins {'certified' if ok else 'near-tie'}, exact_tc {'== oracle' if same else 'differs'}")
+        if ok:
+            assert same, f"seed {seed}: margins are certified but exact_tc differs from the oracle"
+            np.testing.assert_allclose(out["boxes"][0].cpu().numpy(), ref["boxes"][0].numpy(), rtol=0, atol=1e-2)
+            np.testing.assert_allclose(out["roi_features"][0].cpu().numpy(), ref["roi_features"][0].numpy(), rtol=1e-4, atol=1e-4)
+    print(f"{certified} of 10 fresh seeds certified; exact_tc equals the oracle on {exact} of 10")
+    assert certified >= 2, "too few certified seeds for the test to mean anything"
+
+
 def test_ignorey_on_a_batch_applies_the_per_image_rule():
     """forward(..., ignorey=[N,J,2]) on a 2-image batch with different ranges per image.  The reference's branch
     cannot run this (it overwrites the shared level_ids after the first image, frcnn.py:340); the engine applies
