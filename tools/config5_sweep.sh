@@ -1,4 +1,4 @@
-# usage: _job_c5.sh N   -> profiles-ready JSON lines in gpurun_out/r02_config5_n$N.jsonl
+# usage: config5_sweep.sh N   -> profiles-ready JSON lines in gpurun_out/r02_config5_n$N.jsonl
 N=$1
 OUT=gpurun_out/r02_config5_n$N.jsonl
 : > $OUT
