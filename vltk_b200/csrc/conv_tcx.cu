@@ -15,8 +15,15 @@
 // fills the other accumulator.  Truncation then acts on chunk-sized partial sums only (<= 16 MMAs of the big pass).
 //
 // Pipeline roles as in conv_tc2_kernel (TMA producer / MMA issuer / TMEM allocator / epilogue warpgroups); the
-// epilogue writes the two output planes through two 128B-swizzled staging buffers per group and TMA stores, and
-// a residual tensor (two planes) is TMA-loaded INTO those staging buffers and consumed in place.
+// epilogue writes the two output planes through two 128B-swizzled staging buffers per group and TMA stores.  A
+// residual tensor (two planes) reaches it by two routes: the first 64-column unit of a group is TMA-prefetched INTO
+// those staging buffers a whole tile ahead and consumed in place, later units are fetched into registers with 32-byte
+// loads behind the first unit's arithmetic (the staging buffers are busy until the first unit's store has read them).
+//
+// Variants (template parameters):  PAIR = CTA pairs, tcgen05 cta_group::2 (all res5 layers: five 32 KB stages, half a W
+// tile per CTA);  K-concatenation (run time, kb1 < num_kb) = a second 1x1 operand accumulated into the same tile, i.e. a
+// projection block's conv3 + shortcut as ONE GEMM;  POOL = the res5 tail's 14x14 mean reduced in the epilogue instead of
+// storing the tile;  OUT_F32 = fp32 rows out (RPN head, predictor linears).
 //
 // Reference layers: every Conv2d+BN(+ReLU)(+residual) of res2-res5, the RPN convs and the predictor linears
 // (frcnn.py:794-822, 963-979, 1345-1355, 1561-1572, 1726-1740), computed in fp32 by the reference.
