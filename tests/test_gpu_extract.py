@@ -109,3 +109,38 @@ def test_extract_writes_arrow_rows_equal_to_direct_calls(engine, tmp_path):
     plan = plan_batches([_source(i).shape[:2] for i in range(7)], cfg, 3, True)
     assert sorted(j for b in plan for j in b) == list(range(7))
     check_against_direct_batches({r["imgid"]: r for r in rows_b}, None, 3, batches=plan)
+
+
+def test_single_file_gather_device_path_writes_the_same_file_as_the_direct_writer(engine, tmp_path):
+    """single_file=True on GPUs: windows are packed on the device, gathered with NCCL into rank 0's device buffers, split
+    into column-contiguous tensors on a copy stream and handed to the writer thread through cycling pinned buffers
+    (vltk_b200/extract.py::_WindowGather).  A 1-rank NCCL group runs exactly that machinery on one GPU; the file must
+    equal the direct writer's, column for column and bit for bit, with several windows (buffer reuse) and a partial last
+    window."""
+    import socket
+    import torch.distributed as dist
+    from vltk_b200.extract import extract, read_arrow
+    from vltk_b200.preprocess import Preprocess
+    model, cfg = engine
+    pre = Preprocess(cfg)
+    ids = [f"img{i:03d}" for i in range(21)]
+    direct = extract(_source, ids, model, pre, str(tmp_path / "direct"), batch_size=4, window=8, bucket=False)
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1,
+                            device_id=torch.device("cuda", torch.cuda.current_device()))
+    try:
+        gathered = extract(_source, ids, model, pre, str(tmp_path / "gather"), batch_size=4, window=8, bucket=False,
+                           single_file=True, _force_gather=True)
+        again = extract(_source, ids, model, pre, str(tmp_path / "gather2"), batch_size=4, window=8, bucket=False,
+                        single_file=True, _force_gather=True)      # second job of the process: pinned sets are reused
+    finally:
+        dist.destroy_process_group()
+    ta, ma = read_arrow(direct)
+    for pth in (gathered, again):
+        tb, mb = read_arrow(pth)
+        assert tb.num_rows == ta.num_rows == 21 and tb.schema.names == ta.schema.names
+        assert json.loads(mb["img_to_row_map"]) == json.loads(ma["img_to_row_map"])
+        for name in ta.schema.names:
+            assert tb.column(name).combine_chunks().equals(ta.column(name).combine_chunks()), name

@@ -256,7 +256,7 @@ def extract(image_source: Callable[[int], np.ndarray], image_ids: Sequence[str],
             out_dir: str, split: str = "train", batch_size: int = 8, rank: int = 0, world: int = 1,
             single_file: bool = False, max_detections: Optional[int] = None,
             meta: Optional[dict] = None, progress: Optional[Callable[[int], None]] = None,
-            window: int = 64, bucket: bool = True) -> Optional[str]:
+            window: int = 64, bucket: bool = True, _force_gather: bool = False) -> Optional[str]:
     """Runs this rank's shard.  image_source(i) -> raw BGR u8 [h,w,3] (array / tensor) or the encoded JPEG bytes
     of global index i.  Returns the path written by this rank (None on non-writer ranks with single_file).
 
@@ -273,8 +273,10 @@ def extract(image_source: Callable[[int], np.ndarray], image_ids: Sequence[str],
     meta.setdefault("dataset", "synthetic")
     meta.setdefault("model_config", {})
     meta.setdefault("processor_args", {})
-    direct = (not single_file) or world == 1
+    # world == 1 needs no collective; `_force_gather` (tests) runs the single-file machinery anyway, on a 1-rank group
+    direct = (not single_file) or (world == 1 and not _force_gather)
     path = os.path.join(out_dir, f"{split}.arrow" if world == 1 else f"{split}.rank{rank}.arrow")
+    os.makedirs(out_dir, exist_ok=True)
     cfg = getattr(preprocess, "cfg", None)
     bucket = bucket and cfg is not None
     plan: List[tuple] = []          # (window number, first shard row, rows, positions inside the window) per batch, in feed order
