@@ -153,6 +153,30 @@ def test_exact_tc_matches_the_oracle_on_fresh_uncommitted_seeds():
     assert certified >= 2, "too few certified seeds for the test to mean anything"
 
 
+@pytest.mark.parametrize("mode", ["exact_tc", "bf16", "fp32"])
+def test_engine_roi_pool_equals_torchvision_semantics_on_its_own_inputs(mode):
+    """The RoIPool kernels the engine actually runs (roi_pool_h2_kernel on split-fp16 planes in exact_tc — the maximum is
+    selected with packed fp16 compares of the (hi, lo') pair —, roi_pool_kernel<bf16 / f32> otherwise) against the oracle's
+    restatement of torchvision.ops.RoIPool applied to the engine's OWN res4 map and proposals: a max copies values, so the
+    pooled tensor must be bit-identical, including the zero rows past the proposal count."""
+    from oracle import frcnn_oracle as O
+    model, cfg, images, sizes, scales, out = run_case("few", mode)      # fewer proposals than the 300-slot budget
+    n = images.shape[0]
+    h4, w4 = cfg.res4_hw(images.shape[2], images.shape[3])
+    res4 = torch.from_numpy(model.debug_read("res4")).view(n, h4, w4, -1).permute(0, 3, 1, 2).contiguous()
+    cnt = model.debug_read("proposal_count", np.int32)
+    props = torch.from_numpy(model.debug_read("proposals")).view(n, -1, 4)
+    R = props.shape[1]
+    pooled = torch.from_numpy(model.debug_read("pooled")).view(n, R, 14, 14, -1)
+    assert 0 < int(cnt[0]) < R
+    for i in range(n):
+        c = int(cnt[i])
+        rois = torch.cat([torch.full((c, 1), float(i)), props[i, :c]], 1)
+        ref = O.roi_pool_np(res4, rois, 14, 1.0 / cfg.anchor_stride).permute(0, 2, 3, 1)
+        assert torch.equal(pooled[i, :c], ref), mode
+        assert not pooled[i, c:].any()
+
+
 def test_ignorey_on_a_batch_applies_the_per_image_rule():
     """forward(..., ignorey=[N,J,2]) on a 2-image batch with different ranges per image.  The reference's branch
     cannot run this (it overwrites the shared level_ids after the first image, frcnn.py:340); the engine applies

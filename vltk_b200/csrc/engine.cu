@@ -999,6 +999,7 @@ int vltk_frcnn_forward(vltk_frcnn_t* h, const float* images, const int32_t* size
                    : roi_pool(res4, d, n, s.h4, s.w4, C4, (const float*)p[B_PROP], (const int*)p[B_COUNT], s.R, s.P,
                               1.0f / (float)c.anchor_stride, p[B_POOLED], st)) return -1; }
   h->launches++;
+  tap(h, "pooled", p[B_POOLED], (int64_t)NR * PP * C4, d, C4);
   x = p[B_POOLED];
   void* r5[2] = {p[B_R5A], p[B_R5B]};
   flip = 0;

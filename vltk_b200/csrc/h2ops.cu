@@ -82,23 +82,27 @@ roi_pool_h2_kernel(const __half* __restrict__ feat, int H, int W, int C, const f
       int ws = (int)floorf((float)pw * bin_w) + sw, we = (int)ceilf((float)(pw + 1) * bin_w) + sw;
       ws = min(max(ws, 0), W); we = min(max(we, 0), W);
       const bool empty = he <= hs || we <= ws;
-      float m[8];
-      uint4 bh = zero, bl = zero;                          // pair of the current maximum
-#pragma unroll
-      for (int i = 0; i < 8; ++i) m[i] = empty ? 0.f : -INFINITY;
+      // x = hi + lo' 2^-11 with hi = fp16(x): x is ordered like the pair (hi, lo') lexicographically (hi is monotone in x,
+      // and for equal hi the remainder decides), so the maximum is selected with packed fp16 compares — no conversion to
+      // fp32.  A strict ">" keeps the FIRST maximum like the scalar loop (and torchvision); NaNs never win, as before.
+      uint4 bh = empty ? zero : make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);   // -inf | 0
+      uint4 bl = zero;
       for (int h = hs; h < he; ++h) {
         const __half* row = fc + (int64_t)h * W * 2 * C;
         for (int w = ws; w < we; ++w) {
           const uint4 vh = *reinterpret_cast<const uint4*>(row + (int64_t)w * 2 * C);
           const uint4 vl = *reinterpret_cast<const uint4*>(row + (int64_t)w * 2 * C + C);
-          const __half* ph_ = reinterpret_cast<const __half*>(&vh);
-          const __half* pl_ = reinterpret_cast<const __half*>(&vl);
-          __half* sh_ = reinterpret_cast<__half*>(&bh);
-          __half* sl_ = reinterpret_cast<__half*>(&bl);
+          const uint32_t* ph_ = reinterpret_cast<const uint32_t*>(&vh);
+          const uint32_t* pl_ = reinterpret_cast<const uint32_t*>(&vl);
+          uint32_t* sh_ = reinterpret_cast<uint32_t*>(&bh);
+          uint32_t* sl_ = reinterpret_cast<uint32_t*>(&bl);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float v = join1(ph_[i], pl_[i]);
-            if (v > m[i]) { m[i] = v; sh_[i] = ph_[i]; sl_[i] = pl_[i]; }
+          for (int i = 0; i < 4; ++i) {
+            const __half2 h2 = *reinterpret_cast<const __half2*>(&ph_[i]), l2 = *reinterpret_cast<const __half2*>(&pl_[i]);
+            const __half2 mh = *reinterpret_cast<const __half2*>(&sh_[i]), ml = *reinterpret_cast<const __half2*>(&sl_[i]);
+            const uint32_t take = __hgt2_mask(h2, mh) | (__heq2_mask(h2, mh) & __hgt2_mask(l2, ml));
+            sh_[i] = (ph_[i] & take) | (sh_[i] & ~take);
+            sl_[i] = (pl_[i] & take) | (sl_[i] & ~take);
           }
         }
       }
